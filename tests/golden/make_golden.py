@@ -1,0 +1,204 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+    python tests/golden/make_golden.py
+
+The GPU box has no /root/reference, so the outputs are committed; tests compare the oracle
+(oracle/) and the CUDA path (anoddpm_b200/) against these files.  Everything here CALLS the
+reference; there is no arithmetic of our own except input generation.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import refload  # noqa: E402
+
+simplex, UNet, GD = refload.load()
+from oracle.unet_oracle import fill_state_dict  # noqa: E402  (weight filler only: deterministic inputs)
+
+
+def sha(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def gen_simplex():
+    out = {}
+    seeds = [3, 12345, -9999999999, 9999999999, 1, -1, 2 ** 62 + 12345, -2 ** 63 + 5, 6569750267]
+    out["seeds"] = np.array([str(s) for s in seeds])
+    perms, pgis = [], []
+    for s in seeds:
+        p, g = simplex._init(s)
+        perms.append(p), pgis.append(g)
+    out["perm"] = np.stack(perms).astype(np.int16)
+    out["pgi3"] = np.stack(pgis).astype(np.int16)
+    S = simplex.Simplex_CLASS()
+    S.newSeed(12345)
+    rng = np.random.default_rng(1234)
+    pts = rng.uniform(-40, 40, size=(3000, 3))
+    f = 2.0 ** rng.integers(1, 7, size=(3000, 1))
+    lat = rng.integers(0, 1000, size=(3000, 3)) / f          # exact dyadic: lattice-boundary hits are common
+    named = np.array([[0, 0, 0], [0.5, 0.25, 0.125], [1, 1, 1], [3.984375, 2.0, 7.796875], [100.3, -4.2, 55.5]])
+    P = np.concatenate([named, pts, lat])
+    out["points"] = P
+    out["noise3"] = np.array([S.noise3(*p) for p in P])
+    out["noise2"] = np.array([S.noise2(p[0], p[1]) for p in P])
+    # octave fields (seed 12345): small ones stored whole, the 256x256 hot-path field by crop + hash + moments
+    out["fixedT_64_t17"] = S.rand_3d_fixed_T_octaves((64, 64), np.array([17]), 6, 0.8, 64)
+    out["fixedT_48x80_t999_o3"] = S.rand_3d_fixed_T_octaves((48, 80), np.array([999]), 3, 0.6, 16)
+    big = S.rand_3d_fixed_T_octaves((256, 256), np.array([500]), 6, 0.8, 64)
+    out["fixedT_256_t500_sha1"] = np.array(sha(big))
+    out["fixedT_256_t500_f32_sha1"] = np.array(sha(big.astype(np.float32)))
+    out["fixedT_256_t500_crop"] = big[0, 96:160:1, 100:132]
+    out["fixedT_256_t500_stats"] = np.array([big.sum(), big.mean(), big.std(), big.min(), big.max()])
+    vol = S.rand_3d_octaves((32, 256, 256), 8, 0.8, 64)      # BASELINE config 5
+    out["vol_32x256x256_o8_sha1"] = np.array(sha(vol))
+    out["vol_32x256x256_o8_f32_sha1"] = np.array(sha(vol.astype(np.float32)))
+    out["vol_32x256x256_o8_stats"] = np.array([vol.sum(), vol.mean(), vol.std(), vol.min(), vol.max()])
+    out["vol_32x256x256_o8_crop"] = vol[::8, 120:136, 64:96]
+    out["vol_4x32x32_o8"] = S.rand_3d_octaves((4, 32, 32), 8, 0.8, 64)
+    out["noise3array_5x7x9"] = S.noise3array(np.arange(9) / 3.0, np.arange(7) / 5.0, np.arange(5) / 7.0)
+    # host RNG stream consumed by newSeed() (simplex.py:19-22)
+    np.random.seed(0)
+    out["np_seed0_draws"] = np.array([np.random.randint(-10000000000, 10000000000) for _ in range(8)], dtype=np.int64)
+    # generate_simplex_noise at B=1 (the only batch the reference supports)
+    np.random.seed(42)
+    x = torch.zeros(1, 2, 32, 32)
+    out["gsn_B1_C2_t123"] = GD.generate_simplex_noise(simplex.Simplex_CLASS(), x, torch.tensor([123]),
+                                                       in_channels=2).numpy()
+    np.savez_compressed(os.path.join(HERE, "simplex.npz"), **out)
+    print("simplex.npz", {k: getattr(v, "shape", None) for k, v in out.items()})
+
+
+def gen_diffusion():
+    out = {}
+    for T, name in [(100, "linear"), (1000, "linear"), (100, "cosine"), (1000, "cosine")]:
+        D = GD.GaussianDiffusionModel([64, 64], GD.get_beta_schedule(T, name))
+        for n in ("betas", "sqrt_alphas", "sqrt_betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod",
+                  "sqrt_one_minus_alphas_cumprod", "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod",
+                  "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped",
+                  "posterior_mean_coef1", "posterior_mean_coef2"):
+            out[f"{name}{T}/{n}"] = getattr(D, n)
+        g = torch.Generator().manual_seed(T)
+        x = torch.rand(4, 1, 24, 40, generator=g) * 2 - 1
+        n1 = torch.randn(4, 1, 24, 40, generator=g)
+        e1 = torch.randn(4, 1, 24, 40, generator=g) * 1.5
+        t = torch.tensor([0, 1, T // 2, T - 1])
+        out[f"{name}{T}/x"], out[f"{name}{T}/noise"], out[f"{name}{T}/eps"], out[f"{name}{T}/t"] = \
+            x.numpy(), n1.numpy(), e1.numpy(), t.numpy()
+        out[f"{name}{T}/sample_q"] = D.sample_q(x, t, n1).numpy()
+        out[f"{name}{T}/sample_q_gradual"] = D.sample_q_gradual(x, t, n1).numpy()
+        pmv = D.p_mean_variance(None, x, t, e1)
+        for k, v in pmv.items():
+            out[f"{name}{T}/pmv_{k}"] = v.contiguous().numpy()
+        sp = D.sample_p(lambda a, b: e1, x, t, denoise_fn=lambda a, b: n1)
+        out[f"{name}{T}/sample_p"] = sp["sample"].numpy()
+        out[f"{name}{T}/sample_p_pred_x_0"] = sp["pred_x_0"].numpy()
+        out[f"{name}{T}/predict_eps_from_x_0"] = D.predict_eps_from_x_0(x, t[:1].repeat(4) + 5, pmv["pred_x_0"]).numpy()
+    np.savez_compressed(os.path.join(HERE, "diffusion.npz"), **out)
+    print("diffusion.npz", len(out), "arrays")
+
+
+UNET_CASES = {
+    # name: (ctor kwargs, batch, timesteps)
+    "c1_64_b32_h2": (dict(img_size=64, base_channels=32, n_heads=2), 2, [3, 77]),                 # BASELINE config 1 model
+    "s32_b32_attn168": (dict(img_size=32, base_channels=32, attention_resolutions="16,8"), 3, [0, 999, 500]),
+    "s64_b64_hc32_rgb": (dict(img_size=64, base_channels=64, n_head_channels=32, in_channels=3), 1, [12]),
+    "s128_b32_h4": (dict(img_size=128, base_channels=32, n_heads=4), 1, [250]),
+}
+
+
+def gen_unet():
+    out = {}
+    for name, (kw, B, ts) in UNET_CASES.items():
+        torch.manual_seed(0)
+        m = UNet.UNetModel(**kw).eval()
+        m.load_state_dict(fill_state_dict(m.state_dict(), seed=1))
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn(B, kw.get("in_channels", 1), kw["img_size"], kw["img_size"], generator=g)
+        t = torch.tensor(ts)
+        acts = {}
+        hooks = []
+        for mod_name in ("down.0", "down.1", "down.3", "middle", "up.0", f"up.{len(m.up) - 1}"):
+            mod = m.get_submodule(mod_name)
+            hooks.append(mod.register_forward_hook(lambda _m, _i, o, n=mod_name: acts.__setitem__(n, o.detach())))
+        with torch.no_grad():
+            y = m(x, t)
+        for h in hooks:
+            h.remove()
+        out[f"{name}/x"], out[f"{name}/t"], out[f"{name}/y"] = x.numpy(), t.numpy(), y.numpy()
+        for k, v in acts.items():   # intermediate taps: moments + a strided sample (small)
+            out[f"{name}/tap/{k}/stats"] = np.array([v.mean().item(), v.std().item(), v.abs().max().item()])
+            out[f"{name}/tap/{k}/sample"] = v.flatten()[:: max(1, v.numel() // 512)][:512].numpy()
+        out[f"{name}/n_params"] = np.array(sum(p.numel() for p in m.parameters()))
+        out[f"{name}/keys_sha1"] = np.array(hashlib.sha1(
+            "\n".join(f"{k}:{tuple(v.shape)}" for k, v in m.state_dict().items()).encode()).hexdigest())
+    # the BASELINE model (256^2, base 128, attn "16,8", 2 heads): one bs-1 forward
+    torch.manual_seed(0)
+    kw = dict(img_size=256, base_channels=128, n_heads=2, attention_resolutions="16,8")
+    m = UNet.UNetModel(**kw).eval()
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed=1))
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(1, 1, 256, 256, generator=g)
+    t = torch.tensor([431])
+    with torch.no_grad():
+        y = m(x, t)
+    out["base256/x_seed"] = np.array(6)
+    out["base256/t"] = t.numpy()
+    out["base256/y_f16"] = y.numpy().astype(np.float16)          # compact copy (parity bar is 1e-3 relative)
+    out["base256/y_crop"] = y.numpy()[0, 0, 100:132, 64:128]
+    out["base256/y_stats"] = np.array([y.mean().item(), y.std().item(), y.abs().max().item()])
+    out["base256/n_params"] = np.array(sum(p.numel() for p in m.parameters()))
+    out["base256/keys_sha1"] = np.array(hashlib.sha1(
+        "\n".join(f"{k}:{tuple(v.shape)}" for k, v in m.state_dict().items()).encode()).hexdigest())
+    np.savez_compressed(os.path.join(HERE, "unet.npz"), **out)
+    print("unet.npz", len(out), "arrays")
+
+
+def gen_loop():
+    """BASELINE config 1: 64x64, T=100, base 32, Gaussian noise replayed through a callable."""
+    out = {}
+    torch.manual_seed(0)
+    m = UNet.UNetModel(64, 32, n_heads=2).eval()
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed=1))
+    D = GD.GaussianDiffusionModel([64, 64], GD.get_beta_schedule(100, "linear"), noise="gauss")
+    g = torch.Generator().manual_seed(0)
+    x0 = torch.rand(1, 1, 64, 64, generator=g) * 2 - 1
+    for tag, td in (("td100", 100), ("td12", 12)):
+        gz = torch.Generator().manual_seed(99)
+        bank = torch.randn(td + 1, 1, 1, 64, 64, generator=gz)
+        it = iter(bank)
+        D.noise_fn = lambda x, t: next(it)
+        seq = D.forward_backward(m, x0, see_whole_sequence="half", t_distance=td, denoise_fn=lambda x, t: next(it))
+        assert len(seq) == td + 2
+        out[f"{tag}/x0"] = x0.numpy()
+        out[f"{tag}/final"] = seq[-1].numpy()
+        out[f"{tag}/x_T"] = seq[1].numpy()
+        out[f"{tag}/step_absmax"] = np.array([s.abs().max().item() for s in seq])
+        out[f"{tag}/step_mean"] = np.array([s.mean().item() for s in seq])
+    # "whole" sequence variant, short
+    gz = torch.Generator().manual_seed(7)
+    bank = torch.randn(2 * 6, 1, 1, 64, 64, generator=gz)
+    it = iter(bank)
+    D.noise_fn = lambda x, t: next(it)
+    seq = D.forward_backward(m, x0, see_whole_sequence="whole", t_distance=6, denoise_fn="noise_fn")
+    assert len(seq) == 13
+    out["whole6/final"] = seq[-1].numpy()
+    out["whole6/mid"] = seq[6].numpy()
+    # simplex-noise loop at B=1 with the host RNG pinned (np.random.seed) -- the reference's own noise path
+    np.random.seed(2024)
+    D2 = GD.GaussianDiffusionModel([64, 64], GD.get_beta_schedule(100, "linear"), noise="simplex")
+    y = D2.forward_backward(m, x0, see_whole_sequence=None, t_distance=8, denoise_fn="noise_fn")
+    out["simplex_td8/final"] = y.numpy()
+    np.savez_compressed(os.path.join(HERE, "loop.npz"), **out)
+    print("loop.npz", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["simplex", "diffusion", "unet", "loop"]
+    for w in which:
+        globals()["gen_" + w]()
