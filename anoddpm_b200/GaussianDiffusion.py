@@ -1,0 +1,424 @@
+"""Drop-in for the reference module ``GaussianDiffusion`` (reference GaussianDiffusion.py).
+
+Same functions, class, method names, return conventions and public numpy tables.  The hot path --
+``sample_q`` / ``sample_q_gradual`` / ``sample_p`` / ``forward_backward`` and simplex noise generation --
+runs on the sm_100a kernels (csrc/diffusion.cu, csrc/simplex.cu) through the C ABI:
+
+  * coefficient tables are uploaded once per device as fp32 (the reference re-uploads a T-entry fp64
+    table on every ``extract``, GaussianDiffusion.py:32-36);
+  * ``sample_p`` is one fused kernel after the UNet (x0 prediction, clamp, posterior mean, noise mix);
+  * simplex noise is written straight into the (B,C,H,W) fp32 noise tensor on the device, with no
+    device->host sync of ``t`` (the reference does D2H t -> numba CPU -> H2D per call).
+
+Batched simplex semantic (the reference only supports B == 1): sample b / channel c gets its
+own seed, drawn from ``np.random.randint(-1e10, 1e10)`` in (b-major, c-minor) order, i.e. the result
+for sample b equals the reference run at B=1 after ``newSeed(seed[b,c])``; B=1 consumes the host RNG
+exactly like the reference.
+
+The VLB / hybrid-loss helpers (normal_kl, discretised_gaussian_log_likelihood, calc_vlb_xt,
+calc_total_vlb, prior_vlb) and the detection_A/B experiment drivers are kept as plain torch / python
+(outside the accelerated path).
+"""
+import os
+import random
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream
+from .simplex import Simplex_CLASS, init_tables
+
+
+def get_beta_schedule(num_diffusion_steps, name="cosine"):
+    """fp64 beta schedule (GaussianDiffusion.py:12-29)."""
+    if name == "cosine":
+        f = lambda t: np.cos((t + 0.008) / 1.008 * np.pi / 2) ** 2
+        betas = [min(1 - f((i + 1) / num_diffusion_steps) / f(i / num_diffusion_steps), 0.999)
+                 for i in range(num_diffusion_steps)]
+        return np.array(betas)
+    if name == "linear":
+        scale = 1000 / num_diffusion_steps
+        return np.linspace(scale * 0.0001, scale * 0.02, num_diffusion_steps, dtype=np.float64)
+    raise NotImplementedError(f"unknown beta schedule: {name}")
+
+
+def extract(arr, timesteps, broadcast_shape, device):
+    """fp64 table -> gather by t -> fp32 -> broadcast (GaussianDiffusion.py:32-36).  Kept for API parity;
+    the kernels read device-resident fp32 tables instead."""
+    res = torch.from_numpy(arr).to(device=timesteps.device)[timesteps].float()
+    while len(res.shape) < len(broadcast_shape):
+        res = res[..., None]
+    return res.expand(broadcast_shape).to(device)
+
+
+def mean_flat(tensor):
+    return torch.mean(tensor, dim=list(range(1, len(tensor.shape))))
+
+
+def normal_kl(mean1, logvar1, mean2, logvar2):
+    return 0.5 * (-1 + logvar2 - logvar1 + torch.exp(logvar1 - logvar2) + ((mean1 - mean2) ** 2) * torch.exp(-logvar2))
+
+
+def approx_standard_normal_cdf(x):
+    return 0.5 * (1.0 + torch.tanh(np.sqrt(2.0 / np.pi) * (x + 0.044715 * torch.pow(x, 3))))
+
+
+def discretised_gaussian_log_likelihood(x, means, log_scales):
+    assert x.shape == means.shape == log_scales.shape
+    centered_x = x - means
+    inv_stdv = torch.exp(-log_scales)
+    cdf_plus = approx_standard_normal_cdf(inv_stdv * (centered_x + 1.0 / 255.0))
+    cdf_min = approx_standard_normal_cdf(inv_stdv * (centered_x - 1.0 / 255.0))
+    log_cdf_plus = torch.log(cdf_plus.clamp(min=1e-12))
+    log_one_minus_cdf_min = torch.log((1.0 - cdf_min).clamp(min=1e-12))
+    cdf_delta = cdf_plus - cdf_min
+    log_probs = torch.where(x < -0.999, log_cdf_plus,
+                            torch.where(x > 0.999, log_one_minus_cdf_min, torch.log(cdf_delta.clamp(min=1e-12))))
+    assert log_probs.shape == x.shape
+    return log_probs
+
+
+_RANDOM_PARAMS = [(2, 0.6, 16), (6, 0.6, 32), (7, 0.7, 32), (10, 0.8, 64), (5, 0.8, 16), (4, 0.6, 16), (1, 0.6, 64),
+                  (7, 0.8, 128), (6, 0.9, 64), (2, 0.85, 128), (2, 0.85, 64), (2, 0.85, 32), (2, 0.85, 16),
+                  (2, 0.85, 8), (2, 0.85, 4), (2, 0.85, 2), (1, 0.85, 128), (1, 0.85, 64), (1, 0.85, 32),
+                  (1, 0.85, 16), (1, 0.85, 8), (1, 0.85, 4), (1, 0.85, 2)]
+
+
+def draw_simplex_seeds(n):
+    """n host seeds, consumed exactly like n calls of ``Simplex_CLASS.newSeed()`` (simplex.py:19-22)."""
+    return [int(np.random.randint(-10000000000, 10000000000)) for _ in range(n)]
+
+
+def simplex_noise_from_seeds(seeds, shape, t, octave=6, persistence=0.8, frequency=64, shared_seed=False):
+    """fp32 noise tensor ``shape`` = (B,C,H,W) on t.device from explicit seeds: (B*C) seeds in b-major /
+    c-minor order, or C seeds when ``shared_seed``.  One kernel launch; t stays on the device."""
+    B, C, H, W = shape
+    _lib.require_cuda(t, "t")
+    tables = torch.from_numpy(init_tables(seeds))
+    if tables.shape[0] != (C if shared_seed else B * C):
+        raise ValueError("wrong number of simplex seeds")
+    tables_dev = tables.pin_memory().to(t.device, non_blocking=True)
+    noise = torch.empty((B, C, H, W), device=t.device, dtype=torch.float32)
+    t64 = t.to(torch.int64).contiguous()
+    call("anoddpm_simplex_noise", ptr(noise), B, C, H, W, ptr(tables_dev), int(shared_seed), ptr(t64), int(octave),
+         float(persistence), float(frequency), stream())
+    return noise
+
+
+def generate_simplex_noise(Simplex_instance, x, t, random_param=False, octave=6, persistence=0.8, frequency=64,
+                           in_channels=1):
+    """GaussianDiffusion.py:96-137, batched per sample (see module docstring)."""
+    _lib.require_cuda(x, "x")
+    B = x.shape[0]
+    H, W = x.shape[-2:]
+    seeds = []
+    for _ in range(B):
+        for _c in range(in_channels):
+            seeds.append(draw_simplex_seeds(1)[0])
+            if random_param:
+                random.choice(_RANDOM_PARAMS)  # drawn and discarded: the reference overwrites that field
+    # leave the instance in the state the reference leaves it in: tables of the last seed drawn
+    Simplex_instance._load_seed(seeds[-1])
+    noise = simplex_noise_from_seeds(seeds, (B, in_channels, H, W), t.to(x.device), octave, persistence, frequency)
+    if tuple(x.shape) != tuple(noise.shape):
+        out = torch.empty(x.shape, device=x.device)
+        out[:, :in_channels] = noise  # same broadcasting as the reference's noise[:, i] assignment
+        return out
+    return noise
+
+
+def random_noise(Simplex_instance, x, t):
+    param = random.choice(["gauss", "simplex"])
+    if param == "gauss":
+        return torch.randn_like(x)
+    return generate_simplex_noise(Simplex_instance, x, t)
+
+
+class GaussianDiffusionModel:
+    """Diffusion process of reference GaussianDiffusion.py:150-623 (not an nn.Module; numpy tables are public)."""
+
+    TABLE_ROWS = ("sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod", "sqrt_alphas", "sqrt_betas",
+                  "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+                  "posterior_mean_coef2")
+
+    def __init__(self, img_size, betas, img_channels=1, loss_type="l2", loss_weight="none", noise="gauss"):
+        super().__init__()
+        if noise == "gauss":
+            self.noise_fn = lambda x, t: torch.randn_like(x)
+        else:
+            self.simplex = Simplex_CLASS()
+            if noise == "simplex_randParam":
+                self.noise_fn = lambda x, t: generate_simplex_noise(self.simplex, x, t, True, in_channels=img_channels)
+            elif noise == "random":
+                self.noise_fn = lambda x, t: random_noise(self.simplex, x, t)
+            else:
+                self.noise_fn = lambda x, t: generate_simplex_noise(self.simplex, x, t, False, in_channels=img_channels)
+
+        self.img_size = img_size
+        self.img_channels = img_channels
+        self.loss_type = loss_type
+        self.num_timesteps = len(betas)
+        if loss_weight == "prop-t":
+            self.weights = np.arange(self.num_timesteps, 0, -1)
+        elif loss_weight == "uniform":
+            self.weights = np.ones(self.num_timesteps)
+        self.loss_weight = loss_weight
+
+        alphas = 1 - betas
+        self.betas = betas
+        self.sqrt_alphas = np.sqrt(alphas)
+        self.sqrt_betas = np.sqrt(betas)
+        self.alphas_cumprod = np.cumprod(alphas, axis=0)
+        self.alphas_cumprod_prev = np.append(1.0, self.alphas_cumprod[:-1])
+        self.sqrt_alphas_cumprod = np.sqrt(self.alphas_cumprod)
+        self.sqrt_one_minus_alphas_cumprod = np.sqrt(1.0 - self.alphas_cumprod)
+        self.log_one_minus_alphas_cumprod = np.log(1.0 - self.alphas_cumprod)
+        self.sqrt_recip_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod)
+        self.sqrt_recipm1_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod - 1)
+        self.posterior_variance = betas * (1.0 - self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_log_variance_clipped = np.log(np.append(self.posterior_variance[1], self.posterior_variance[1:]))
+        self.posterior_mean_coef1 = betas * np.sqrt(self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_mean_coef2 = (1.0 - self.alphas_cumprod_prev) * np.sqrt(alphas) / (1.0 - self.alphas_cumprod)
+        self._dev_tables = {}
+
+    # ---- device-resident fp32 tables -------------------------------------------------------------
+    def _model_var(self):
+        model_var = np.append(self.posterior_variance[1], self.betas[1:])  # GaussianDiffusion.py:282-283
+        return model_var, np.log(model_var)
+
+    def _tables(self, device):
+        """fp32(round(fp64)) rows [8 coefficient tables | sigma0], built from the CURRENT public numpy tables."""
+        key = str(device)
+        if key not in self._dev_tables:
+            T = self.num_timesteps
+            rows = [torch.from_numpy(np.asarray(getattr(self, n), dtype=np.float64)).float() for n in self.TABLE_ROWS]
+            _, logvar = self._model_var()
+            # sigma0[t] = [t != 0] * exp(0.5 * fp32(logvar[t])), evaluated in fp32 like the reference (:314-317)
+            sigma = torch.exp(0.5 * torch.from_numpy(logvar).float())
+            sigma[0] = 0.0
+            tab = torch.stack(rows + [sigma]).contiguous()
+            assert tab.shape == (9, T)
+            self._dev_tables[key] = tab.to(device)
+        return self._dev_tables[key]
+
+    @staticmethod
+    def _prep(x, what):
+        _lib.require_cuda(x, what)
+        return x.contiguous().float()
+
+    def _t(self, t, x):
+        return t.to(device=x.device, dtype=torch.int64).contiguous()
+
+    # ---- reference API ---------------------------------------------------------------------------
+    def sample_t_with_weights(self, b_size, device):
+        p = self.weights / np.sum(self.weights)
+        indices_np = np.random.choice(len(p), size=b_size, p=p)
+        indices = torch.from_numpy(indices_np).long().to(device)
+        weights_np = 1 / len(p) * p[indices_np]
+        weights = torch.from_numpy(weights_np).float().to(device)
+        return indices, weights
+
+    def predict_x_0_from_eps(self, x_t, t, eps):
+        return (extract(self.sqrt_recip_alphas_cumprod, t, x_t.shape, x_t.device) * x_t
+                - extract(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape, x_t.device) * eps)
+
+    def predict_eps_from_x_0(self, x_t, t, pred_x_0):
+        return (extract(self.sqrt_recip_alphas_cumprod, t, x_t.shape, x_t.device) * x_t - pred_x_0) \
+            / extract(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape, x_t.device)
+
+    def q_mean_variance(self, x_0, t):
+        mean = extract(self.sqrt_alphas_cumprod, t, x_0.shape, x_0.device) * x_0
+        variance = extract(1.0 - self.alphas_cumprod, t, x_0.shape, x_0.device)
+        log_variance = extract(self.log_one_minus_alphas_cumprod, t, x_0.shape, x_0.device)
+        return mean, variance, log_variance
+
+    def q_posterior_mean_variance(self, x_0, x_t, t):
+        posterior_mean = (extract(self.posterior_mean_coef1, t, x_t.shape, x_t.device) * x_0
+                          + extract(self.posterior_mean_coef2, t, x_t.shape, x_t.device) * x_t)
+        posterior_var = extract(self.posterior_variance, t, x_t.shape, x_t.device)
+        posterior_log_var_clipped = extract(self.posterior_log_variance_clipped, t, x_t.shape, x_t.device)
+        return posterior_mean, posterior_var, posterior_log_var_clipped
+
+    def p_mean_variance(self, model, x_t, t, estimate_noise=None):
+        """dict mean / variance / log_variance / pred_x_0 (GaussianDiffusion.py:269-296).  Full dict kept for
+        the VLB helpers; the sampling path uses the fused kernel in sample_p instead."""
+        if estimate_noise is None:
+            estimate_noise = model(x_t, t)
+        model_var, model_logvar = self._model_var()
+        model_var = extract(model_var, t, x_t.shape, x_t.device)
+        model_logvar = extract(model_logvar, t, x_t.shape, x_t.device)
+        pred_x_0 = self.predict_x_0_from_eps(x_t, t, estimate_noise).clamp(-1, 1)
+        model_mean, _, _ = self.q_posterior_mean_variance(pred_x_0, x_t, t)
+        return {"mean": model_mean, "variance": model_var, "log_variance": model_logvar, "pred_x_0": pred_x_0}
+
+    def _draw_denoise_noise(self, x_t, t, denoise_fn):
+        if type(denoise_fn) == str:
+            if denoise_fn == "gauss" or denoise_fn == "random":
+                return torch.randn_like(x_t)
+            if denoise_fn == "noise_fn":
+                return self.noise_fn(x_t, t).float()
+            return generate_simplex_noise(self.simplex, x_t, t, False, in_channels=self.img_channels).float()
+        return denoise_fn(x_t, t)
+
+    def sample_p(self, model, x_t, t, denoise_fn="gauss"):
+        """One reverse step (GaussianDiffusion.py:298-318): UNet forward, noise draw, one fused kernel."""
+        x_t = self._prep(x_t, "x_t")
+        tt = self._t(t, x_t)
+        eps = self._prep(model(x_t, t), "model output")
+        noise = self._prep(self._draw_denoise_noise(x_t, t, denoise_fn), "denoise noise")
+        if noise.shape != x_t.shape:
+            noise = noise.expand_as(x_t).contiguous()
+        tab = self._tables(x_t.device)
+        sample, pred = torch.empty_like(x_t), torch.empty_like(x_t)
+        B = x_t.shape[0]
+        call("anoddpm_p_sample", ptr(sample), ptr(pred), ptr(x_t), ptr(eps), ptr(noise), ptr(tt), ptr(tab[4:]),
+             self.num_timesteps, B, x_t.numel() // B, stream())
+        return {"sample": sample, "pred_x_0": pred}
+
+    def _q(self, x, t, noise, row):
+        x = self._prep(x, "x")
+        noise = self._prep(noise, "noise")
+        if noise.shape != x.shape:
+            noise = noise.expand_as(x).contiguous()
+        tt = self._t(t, x)
+        tab = self._tables(x.device)
+        out = torch.empty_like(x)
+        B = x.shape[0]
+        call("anoddpm_q_sample", ptr(out), ptr(x), ptr(noise), ptr(tt), ptr(tab[row]), ptr(tab[row + 1]), B,
+             x.numel() // B, stream())
+        return out
+
+    def sample_q(self, x_0, t, noise):
+        """q(x_t | x_0) (GaussianDiffusion.py:361-371)."""
+        return self._q(x_0, t, noise, 0)
+
+    def sample_q_gradual(self, x_t, t, noise):
+        """q(x_t | x_{t-1}) (GaussianDiffusion.py:373-382)."""
+        return self._q(x_t, t, noise, 2)
+
+    def forward_backward(self, model, x, see_whole_sequence="half", t_distance=None, denoise_fn="gauss"):
+        """Noise to t_distance then denoise back (GaussianDiffusion.py:320-359) -- the detection loop."""
+        assert see_whole_sequence == "whole" or see_whole_sequence == "half" or see_whole_sequence == None
+        if t_distance == 0:
+            return x.detach()
+        if t_distance is None:
+            t_distance = self.num_timesteps
+        seq = [x.cpu().detach()] if see_whole_sequence else []  # (the reference copies x to the host even when unused)
+        B = x.shape[0]
+        if see_whole_sequence == "whole":
+            for t in range(int(t_distance)):
+                t_batch = torch.full((B,), t, device=x.device, dtype=torch.int64)
+                noise = self.noise_fn(x, t_batch).float()
+                with torch.no_grad():
+                    x = self.sample_q_gradual(x, t_batch, noise)
+                seq.append(x.cpu().detach())
+        else:
+            t_tensor = torch.full((B,), t_distance - 1, device=x.device, dtype=torch.int64)
+            x = self.sample_q(x, t_tensor, self.noise_fn(x, t_tensor).float())
+            if see_whole_sequence == "half":
+                seq.append(x.cpu().detach())
+        for t in range(int(t_distance) - 1, -1, -1):
+            t_batch = torch.full((B,), t, device=x.device, dtype=torch.int64)
+            with torch.no_grad():
+                x = self.sample_p(model, x, t_batch, denoise_fn)["sample"]
+            if see_whole_sequence:
+                seq.append(x.cpu().detach())
+        return x.detach() if not see_whole_sequence else seq
+
+    # aliases named in BASELINE.json's north star
+    q_sample = sample_q
+    p_sample = sample_p
+    p_sample_loop = forward_backward
+
+    # ---- VLB / loss (plain torch) --------------------------------------------------
+    def calc_vlb_xt(self, model, x_0, x_t, t, estimate_noise=None):
+        true_mean, _, true_log_var = self.q_posterior_mean_variance(x_0, x_t, t)
+        output = self.p_mean_variance(model, x_t, t, estimate_noise)
+        kl = mean_flat(normal_kl(true_mean, true_log_var, output["mean"], output["log_variance"])) / np.log(2.0)
+        decoder_nll = -discretised_gaussian_log_likelihood(x_0, output["mean"], log_scales=0.5 * output["log_variance"])
+        decoder_nll = mean_flat(decoder_nll) / np.log(2.0)
+        nll = torch.where((t == 0), decoder_nll, kl)
+        return {"output": nll, "pred_x_0": output["pred_x_0"]}
+
+    def calc_loss(self, model, x_0, t):
+        noise = self.noise_fn(x_0, t).float()
+        x_t = self.sample_q(x_0, t, noise)
+        estimate_noise = model(x_t, t)
+        loss = {}
+        if self.loss_type == "l1":
+            loss["loss"] = mean_flat((estimate_noise - noise).abs())
+        elif self.loss_type == "hybrid":
+            loss["vlb"] = self.calc_vlb_xt(model, x_0, x_t, t, estimate_noise)["output"]
+            loss["loss"] = loss["vlb"] + mean_flat((estimate_noise - noise).square())
+        else:
+            loss["loss"] = mean_flat((estimate_noise - noise).square())
+        return loss, x_t, estimate_noise
+
+    def p_loss(self, model, x_0, args):
+        if self.loss_weight == "none":
+            if args["train_start"]:
+                t = torch.randint(0, min(args["sample_distance"], self.num_timesteps), (x_0.shape[0],), device=x_0.device)
+            else:
+                t = torch.randint(0, self.num_timesteps, (x_0.shape[0],), device=x_0.device)
+            weights = 1
+        else:
+            t, weights = self.sample_t_with_weights(x_0.shape[0], x_0.device)
+        loss, x_t, eps_t = self.calc_loss(model, x_0, t)
+        return ((loss["loss"] * weights).mean(), (loss, x_t, eps_t))
+
+    def prior_vlb(self, x_0, args):
+        t = torch.tensor([self.num_timesteps - 1] * args["Batch_Size"], device=x_0.device)
+        qt_mean, _, qt_log_variance = self.q_mean_variance(x_0, t)
+        kl_prior = normal_kl(mean1=qt_mean, logvar1=qt_log_variance, mean2=torch.tensor(0.0, device=x_0.device),
+                             logvar2=torch.tensor(0.0, device=x_0.device))
+        return mean_flat(kl_prior) / np.log(2.0)
+
+    def calc_total_vlb(self, x_0, model, args):
+        vb, x_0_mse, mse = [], [], []
+        for t in reversed(list(range(self.num_timesteps))):
+            t_batch = torch.tensor([t] * args["Batch_Size"], device=x_0.device)
+            noise = torch.randn_like(x_0)
+            x_t = self.sample_q(x_0=x_0, t=t_batch, noise=noise)
+            with torch.no_grad():
+                out = self.calc_vlb_xt(model, x_0=x_0, x_t=x_t, t=t_batch)
+            vb.append(out["output"])
+            x_0_mse.append(mean_flat((out["pred_x_0"] - x_0) ** 2))
+            eps = self.predict_eps_from_x_0(x_t, t_batch, out["pred_x_0"])
+            mse.append(mean_flat((eps - noise) ** 2))
+        vb, x_0_mse, mse = torch.stack(vb, dim=1), torch.stack(x_0_mse, dim=1), torch.stack(mse, dim=1)
+        prior_vlb = self.prior_vlb(x_0, args)
+        total_vlb = vb.sum(dim=1) + prior_vlb
+        return {"total_vlb": total_vlb, "prior_vlb": prior_vlb, "vb": vb, "x_0_mse": x_0_mse, "mse": mse}
+
+    # ---- detection experiment drivers (callers of the hot path; reference :480-623) -----------------
+    def _denoise_from(self, model, x, t_distance, denoise_fn="gauss"):
+        for t in range(int(t_distance) - 1, -1, -1):
+            t_batch = torch.full((x.shape[0],), t, device=x.device, dtype=torch.int64)
+            with torch.no_grad():
+                x = self.sample_p(model, x, t_batch, denoise_fn)["sample"]
+        return x
+
+    def detection_A_fixedT(self, model, x_0, args, mask, end_freq=6):
+        """Frequency sweep at fixed t_distance = 250 (GaussianDiffusion.py:596-623); returns the image strip."""
+        t_distance = 250
+        output = torch.empty((6 * end_freq, 1, *args["img_size"]), device=x_0.device)
+        for i in range(1, end_freq + 1):
+            freq = 2 ** i
+            noise_fn = lambda x, t: generate_simplex_noise(self.simplex, x, t, False, frequency=freq).float()
+            t_tensor = torch.full((x_0.shape[0],), t_distance - 1, device=x_0.device, dtype=torch.int64)
+            x = self.sample_q(x_0, t_tensor, noise_fn(x_0, t_tensor).float())
+            x_noised = x.clone().detach()
+            x = self._denoise_from(model, x, t_distance, denoise_fn=noise_fn)
+            mse = ((x_0 - x).square() * 2) - 1
+            mse_threshold = ((mse > 0).float() * 2) - 1
+            output[(i - 1) * 6:i * 6, ...] = torch.cat((x_0, x_noised, x, mse, mse_threshold, mask))
+        return output
+
+    def detection_A(self, model, x_0, args, file, mask, total_avg=2):
+        raise NotImplementedError("detection_A writes matplotlib figures (out of scope: plotting driver, SURVEY section 2); "
+                                  "its sampling loop is sample_q + sample_p, see detection_A_fixedT / forward_backward")
+
+    def detection_B(self, model, x_0, args, file, mask, denoise_fn="gauss", total_avg=5):
+        raise NotImplementedError("detection_B writes matplotlib figures / heatmaps (out of scope: plotting driver); "
+                                  "its sampling loop is sample_q + sample_p, see forward_backward")

@@ -1,0 +1,306 @@
+"""Drop-in for the reference module ``UNet`` (reference UNet.py).
+
+``UNetModel`` keeps the reference constructor, attributes, sub-module names and therefore the exact
+``state_dict`` key/shape layout (checkpoints load by key, detection.py:179), but its inference forward
+on a CUDA device is executed by the sm_100a kernels of csrc/ (``engine.UNetEngine``): NHWC activations,
+GroupNorm statistics + fused GN/SiLU/resample, tcgen05 TF32 implicit-GEMM convolutions with the
+timestep-embedding add, skip 1x1 convolution and residual folded in, and a fused attention kernel.
+
+The module classes (ResBlock, AttentionBlock, ...) also define ordinary torch forwards: they document
+the semantics and serve autograd.  The training (autograd) forward is NOT yet native -- it is only taken
+when explicitly enabled with ``UNetModel.allow_autograd_fallback = True`` (or env
+ANODDPM_AUTOGRAD_FALLBACK=1) and is never used by the detection path, the tests' parity checks or bench.py.
+"""
+import math
+import os
+from abc import abstractmethod
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+class TimestepBlock(nn.Module):
+    """A module whose forward takes the timestep embedding as second argument (UNet.py:11-20)."""
+
+    @abstractmethod
+    def forward(self, x, emb):
+        """apply to x given emb"""
+
+
+class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
+    """Sequential that routes ``emb`` to the children that take it (UNet.py:23-35)."""
+
+    def forward(self, x, emb):
+        for layer in self:
+            x = layer(x, emb) if isinstance(layer, TimestepBlock) else layer(x)
+        return x
+
+
+class PositionalEmbedding(nn.Module):
+    """Sinusoidal timestep embedding (UNet.py:38-57)."""
+
+    def __init__(self, dim, scale=1):
+        super().__init__()
+        assert dim % 2 == 0
+        self.dim = dim
+        self.scale = scale
+
+    def forward(self, x):
+        half = self.dim // 2
+        freq = torch.exp(torch.arange(half, device=x.device) * -(np.log(10000) / half))
+        arg = torch.outer(x * self.scale, freq)
+        return torch.cat((arg.sin(), arg.cos()), dim=-1)
+
+
+class Downsample(nn.Module):
+    def __init__(self, in_channels, use_conv, out_channels=None):
+        super().__init__()
+        self.channels = in_channels
+        out_channels = out_channels or in_channels
+        if use_conv:
+            self.downsample = nn.Conv2d(in_channels, out_channels, 3, stride=2, padding=1)
+        else:
+            assert in_channels == out_channels
+            self.downsample = nn.AvgPool2d(kernel_size=2, stride=2)
+
+    def forward(self, x, time_embed=None):
+        assert x.shape[1] == self.channels
+        return self.downsample(x)
+
+
+class Upsample(nn.Module):
+    def __init__(self, in_channels, use_conv, out_channels=None):
+        super().__init__()
+        self.channels = in_channels
+        self.use_conv = use_conv
+        if use_conv:
+            self.conv = nn.Conv2d(in_channels, out_channels, 3, padding=1)
+
+    def forward(self, x, time_embed=None):
+        assert x.shape[1] == self.channels
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+        return self.conv(x) if self.use_conv else x
+
+
+class GroupNorm32(nn.GroupNorm):
+    def forward(self, x):
+        return super().forward(x.float()).type(x.dtype)
+
+
+def zero_module(module):
+    for p in module.parameters():
+        p.detach().zero_()
+    return module
+
+
+class QKVAttention(nn.Module):
+    """Legacy-order QKV attention: channel layout [head][q|k|v][ch] (UNet.py:128-153)."""
+
+    def __init__(self, n_heads):
+        super().__init__()
+        self.n_heads = n_heads
+
+    def forward(self, qkv, time=None):
+        bs, width, length = qkv.shape
+        assert width % (3 * self.n_heads) == 0
+        ch = width // (3 * self.n_heads)
+        q, k, v = qkv.reshape(bs * self.n_heads, ch * 3, length).split(ch, dim=1)
+        scale = 1 / math.sqrt(math.sqrt(ch))
+        weight = torch.einsum("bct,bcs->bts", q * scale, k * scale)
+        weight = torch.softmax(weight.float(), dim=-1).type(weight.dtype)
+        return torch.einsum("bts,bcs->bct", weight, v).reshape(bs, -1, length)
+
+
+class AttentionBlock(nn.Module):
+    """GN -> qkv 1x1 -> attention -> zero-init proj 1x1 -> residual (UNet.py:95-125)."""
+
+    def __init__(self, in_channels, n_heads=1, n_head_channels=-1):
+        super().__init__()
+        self.in_channels = in_channels
+        self.norm = GroupNorm32(32, self.in_channels)
+        if n_head_channels == -1:
+            self.num_heads = n_heads
+        else:
+            assert in_channels % n_head_channels == 0, \
+                f"q,k,v channels {in_channels} is not divisible by num_head_channels {n_head_channels}"
+            self.num_heads = in_channels // n_head_channels
+        self.to_qkv = nn.Conv1d(in_channels, in_channels * 3, 1)
+        self.attention = QKVAttention(self.num_heads)
+        self.proj_out = zero_module(nn.Conv1d(in_channels, in_channels, 1))
+
+    def forward(self, x, time=None):
+        b, c, *spatial = x.shape
+        x = x.reshape(b, c, -1)
+        h = self.proj_out(self.attention(self.to_qkv(self.norm(x))))
+        return (x + h).reshape(b, c, *spatial)
+
+
+class ResBlock(TimestepBlock):
+    """GN-SiLU-conv3x3 (+emb) GN-SiLU-dropout-conv3x3(zero) + skip, optional 2x up/down (UNet.py:156-217)."""
+
+    def __init__(self, in_channels, time_embed_dim, dropout, out_channels=None, use_conv=False, up=False, down=False):
+        super().__init__()
+        out_channels = out_channels or in_channels
+        self.in_layers = nn.Sequential(GroupNorm32(32, in_channels), nn.SiLU(),
+                                       nn.Conv2d(in_channels, out_channels, 3, padding=1))
+        self.updown = up or down
+        if up:
+            self.h_upd, self.x_upd = Upsample(in_channels, False), Upsample(in_channels, False)
+        elif down:
+            self.h_upd, self.x_upd = Downsample(in_channels, False), Downsample(in_channels, False)
+        else:
+            self.h_upd = self.x_upd = nn.Identity()
+        self.embed_layers = nn.Sequential(nn.SiLU(), nn.Linear(time_embed_dim, out_channels))
+        self.out_layers = nn.Sequential(GroupNorm32(32, out_channels), nn.SiLU(), nn.Dropout(p=dropout),
+                                        zero_module(nn.Conv2d(out_channels, out_channels, 3, padding=1)))
+        if out_channels == in_channels:
+            self.skip_connection = nn.Identity()
+        elif use_conv:
+            self.skip_connection = nn.Conv2d(in_channels, out_channels, 3, padding=1)
+        else:
+            self.skip_connection = nn.Conv2d(in_channels, out_channels, 1)
+        self.resample_mode = "up" if up else ("down" if down else "same")
+
+    def forward(self, x, time_embed):
+        if self.updown:
+            h = self.in_layers[:-1](x)
+            h, x = self.h_upd(h), self.x_upd(x)
+            h = self.in_layers[-1](h)
+        else:
+            h = self.in_layers(x)
+        emb_out = self.embed_layers(time_embed).type(h.dtype)
+        while len(emb_out.shape) < len(h.shape):
+            emb_out = emb_out[..., None]
+        h = self.out_layers(h + emb_out)
+        return self.skip_connection(x) + h
+
+
+class UNetModel(nn.Module):
+    """guided-diffusion style UNet; constructor/defaults of reference UNet.py:222-235."""
+
+    allow_autograd_fallback = os.environ.get("ANODDPM_AUTOGRAD_FALLBACK", "0") == "1"
+
+    def __init__(self, img_size, base_channels, conv_resample=True, n_heads=1, n_head_channels=-1, channel_mults="",
+                 num_res_blocks=2, dropout=0, attention_resolutions="32,16,8", biggan_updown=True, in_channels=1):
+        self.dtype = torch.float32
+        super().__init__()
+        if channel_mults == "":
+            table = {512: (0.5, 1, 1, 2, 2, 4, 4), 256: (1, 1, 2, 2, 4, 4), 128: (1, 1, 2, 3, 4), 64: (1, 2, 3, 4),
+                     32: (1, 2, 3, 4)}
+            if img_size not in table:
+                raise ValueError(f"unsupported image size: {img_size}")
+            channel_mults = table[img_size]
+        attention_ds = [img_size // int(res) for res in attention_resolutions.split(",")]
+
+        self.image_size = img_size
+        self.in_channels = in_channels
+        self.model_channels = base_channels
+        self.out_channels = in_channels
+        self.num_res_blocks = num_res_blocks
+        self.attention_resolutions = attention_resolutions
+        self.dropout = dropout
+        self.channel_mult = channel_mults
+        self.conv_resample = conv_resample
+        self.num_heads = n_heads
+        self.num_head_channels = n_head_channels
+
+        E = base_channels * 4
+        self.time_embedding = nn.Sequential(PositionalEmbedding(base_channels, 1), nn.Linear(base_channels, E),
+                                            nn.SiLU(), nn.Linear(E, E))
+
+        def res(cin, cout, **kw):
+            return ResBlock(cin, time_embed_dim=E, out_channels=cout, dropout=dropout, **kw)
+
+        def attn(c):
+            return AttentionBlock(c, n_heads=n_heads, n_head_channels=n_head_channels)
+
+        ch = int(channel_mults[0] * base_channels)
+        self.down = nn.ModuleList([TimestepEmbedSequential(nn.Conv2d(self.in_channels, base_channels, 3, padding=1))])
+        widths = [ch]
+        ds = 1
+        for level, mult in enumerate(channel_mults):
+            for _ in range(num_res_blocks):
+                layers = [res(ch, base_channels * mult)]
+                ch = base_channels * mult
+                if ds in attention_ds:
+                    layers.append(attn(ch))
+                self.down.append(TimestepEmbedSequential(*layers))
+                widths.append(ch)
+            if level != len(channel_mults) - 1:
+                self.down.append(TimestepEmbedSequential(
+                    res(ch, ch, down=True) if biggan_updown else Downsample(ch, conv_resample, out_channels=ch)))
+                ds *= 2
+                widths.append(ch)
+
+        self.middle = TimestepEmbedSequential(res(ch, None), attn(ch), res(ch, None))
+
+        self.up = nn.ModuleList([])
+        for level, mult in reversed(list(enumerate(channel_mults))):
+            for j in range(num_res_blocks + 1):
+                layers = [res(ch + widths.pop(), base_channels * mult)]
+                ch = base_channels * mult
+                if ds in attention_ds:
+                    layers.append(attn(ch))
+                if level and j == num_res_blocks:
+                    layers.append(res(ch, ch, up=True) if biggan_updown else Upsample(ch, conv_resample, out_channels=ch))
+                    ds //= 2
+                self.up.append(TimestepEmbedSequential(*layers))
+
+        self.out = nn.Sequential(GroupNorm32(32, ch), nn.SiLU(),
+                                 zero_module(nn.Conv2d(base_channels * channel_mults[0], self.out_channels, 3, padding=1)))
+        self._engine = None
+        self.conv_impl = os.environ.get("ANODDPM_CONV_IMPL", "tc")  # "tc" (tcgen05 TF32) | "exact" (fp32 CUDA cores)
+
+    # -- native inference path ---------------------------------------------------------------------
+    def engine(self):
+        from .engine import UNetEngine
+        if self._engine is None:
+            object.__setattr__(self, "_engine", UNetEngine(self))  # not a sub-module / not in state_dict
+        return self._engine
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == "_engine" else copy.deepcopy(v, memo)
+        return new
+
+    def forward(self, x, time):
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if not needs_grad:
+            if not x.is_cuda:
+                raise RuntimeError("anoddpm_b200.UNetModel runs on sm_100a only: move the model and inputs to a CUDA "
+                                   "device (no CPU fallback)")
+            return self.engine().forward(x, time)
+        if not UNetModel.allow_autograd_fallback:
+            raise NotImplementedError(
+                "the training (autograd) forward is not native yet; run inference under torch.no_grad(), or opt in "
+                "to the PyTorch autograd fallback with UNetModel.allow_autograd_fallback = True")
+        return self.forward_torch(x, time)
+
+    def forward_torch(self, x, time):
+        """Plain-torch forward (reference UNet.py:390-406): autograd fallback only, see the module docstring."""
+        emb = self.time_embedding(time)
+        skips = []
+        h = x.type(self.dtype)
+        for module in self.down:
+            h = module(h, emb)
+            skips.append(h)
+        h = self.middle(h, emb)
+        for module in self.up:
+            h = module(torch.cat([h, skips.pop()], dim=1), emb)
+        return self.out(h.type(x.dtype))
+
+
+def update_ema_params(target, source, decay_rate=0.9999):
+    """p_target <- decay*p_target + (1-decay)*p_source over named parameters (UNet.py:423-427)."""
+    tgt = dict(target.named_parameters())
+    src = dict(source.named_parameters())
+    with torch.no_grad():
+        keys = list(tgt)
+        torch._foreach_mul_([tgt[k].data for k in keys], decay_rate)
+        torch._foreach_add_([tgt[k].data for k in keys], [src[k].data for k in keys], alpha=1 - decay_rate)

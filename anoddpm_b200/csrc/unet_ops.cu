@@ -1,0 +1,562 @@
+// anoddpm_b200/csrc/unet_ops.cu -- CUDA-core (fp32-exact) kernels of the UNet denoiser:
+// timestep embedding, linear, GroupNorm statistics / apply(+SiLU,+resample), the exact-fp32
+// implicit-GEMM convolution, stem / head convolutions and QKV attention.
+//
+// Activations are NHWC fp32.  The tensor-core convolution (tcgen05, kind::tf32) lives in
+// conv_tc.cu and shares anoddpm_conv_desc with the exact kernel here; the exact kernel is the
+// strict-parity mode (fp32 multiplicands) and the path for shapes the tensor-core tiles do not take.
+#include "common.cuh"
+#include "anoddpm_b200.h"
+#include <math.h>
+
+namespace {
+
+struct alignas(16) F4 { float x, y, z, w; };
+__device__ __forceinline__ F4 ld4(const float* p) { return *reinterpret_cast<const F4*>(p); }
+__device__ __forceinline__ void st4(float* p, F4 v) { *reinterpret_cast<F4*>(p) = v; }
+__device__ __forceinline__ float silu(float y) { return y / (1.0f + expf(-y)); }
+__device__ __forceinline__ float round_tf32(float v) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return __uint_as_float(u);
+}
+
+// ---------------------------------------------------------------- timestep embedding (UNet.py:50-57)
+__global__ void tembed_kernel(float* __restrict__ emb, const long long* __restrict__ t, int B, int dim) {
+    const int half = dim / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    const int b = i / half, j = i - b * half;
+    const float neg = -(float)(9.210340371976184 / (double)half);  // -(ln 1e4)/half, rounded to fp32 like torch
+    const float w = expf((float)j * neg);
+    const float a = (float)t[b] * w;
+    emb[(size_t)b * dim + j] = sinf(a);
+    emb[(size_t)b * dim + half + j] = cosf(a);
+}
+
+// ---------------------------------------------------------------- linear: one warp per (b, n)
+__global__ void __launch_bounds__(256) linear_kernel(float* __restrict__ y, int ldy, const float* __restrict__ x,
+                                                     int ldx, const float* __restrict__ w,
+                                                     const float* __restrict__ bias, int B, int N, int K,
+                                                     int silu_in) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B * N) return;
+    const int b = warp / N, n = warp - b * N;
+    const float* xr = x + (size_t)b * ldx;
+    const float* wr = w + (size_t)n * K;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        float xv = xr[k];
+        if (silu_in) xv = silu(xv);
+        acc = fmaf(xv, wr[k], acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[(size_t)b * ldy + n] = acc + (bias ? bias[n] : 0.f);
+}
+
+// ---------------------------------------------------------------- GroupNorm statistics
+// grid (chunks, B); a CTA reduces a pixel range of one sample; each thread owns a fixed channel
+// vector (so a fixed group), accumulates in fp32, then fp64 shared + global atomics.
+template <int V>
+__global__ void __launch_bounds__(256) gn_stats_kernel(double* __restrict__ stats, const float* __restrict__ x1,
+                                                       int C1, const float* __restrict__ x2, int C2, int HW,
+                                                       int groups, int pix_per_cta) {
+    __shared__ double sh[64][2];
+    const int b = blockIdx.y, C = C1 + C2, gs = C / groups, ncv = C / V;
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i >> 1][i & 1] = 0.0;
+    __syncthreads();
+    const int p0 = blockIdx.x * pix_per_cta;
+    const int p1 = min(HW, p0 + pix_per_cta);
+    int tpr, rows;
+    if (ncv >= 256) { tpr = 256; rows = 1; }
+    else { tpr = ncv; rows = 256 / ncv; }
+    const int r = threadIdx.x / tpr, lane = threadIdx.x - r * tpr;
+    if (r < rows) {
+        for (int cv = lane; cv < ncv; cv += tpr) {
+            const int c = cv * V;
+            const float* src;
+            int cs, cc;
+            if (c < C1) { src = x1; cs = C1; cc = c; }
+            else { src = x2; cs = C2; cc = c - C1; }
+            src += (size_t)b * HW * cs + cc;
+            float s = 0.f, q = 0.f;
+            for (int p = p0 + r; p < p1; p += rows) {
+                if (V == 4) {
+                    const F4 v = ld4(src + (size_t)p * cs);
+                    s += (v.x + v.y) + (v.z + v.w);
+                    q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                } else {
+                    const float v = src[(size_t)p * cs];
+                    s += v;
+                    q += v * v;
+                }
+            }
+            const int g = c / gs;
+            atomicAdd(&sh[g][0], (double)s);
+            atomicAdd(&sh[g][1], (double)q);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
+        atomicAdd(&stats[((size_t)b * groups + (i >> 1)) * 2 + (i & 1)], sh[i >> 1][i & 1]);
+}
+
+// ---------------------------------------------------------------- GroupNorm apply (+SiLU, +resample)
+// grid (chunks, B).  Output NHWC (B, Ho, Wo, C).  mode 0 same, 1 avg-pool 2x2 (of activated values), 2 nearest x2.
+template <int V>
+__global__ void __launch_bounds__(256) gn_apply_kernel(float* __restrict__ out, const float* __restrict__ x1, int C1,
+                                                       const float* __restrict__ x2, int C2,
+                                                       const double* __restrict__ stats,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       int H, int W, int groups, float eps, int do_silu, int mode,
+                                                       int rtf32, long long work_per_cta) {
+    __shared__ float s_mean[64], s_rstd[64];
+    const int b = blockIdx.y, C = C1 + C2, gs = C / groups, ncv = C / V;
+    if (threadIdx.x < groups) {
+        const double n = (double)H * W * gs;
+        const double s = stats[((size_t)b * groups + threadIdx.x) * 2], q = stats[((size_t)b * groups + threadIdx.x) * 2 + 1];
+        const double m = s / n;
+        double var = q / n - m * m;
+        if (var < 0) var = 0;
+        s_mean[threadIdx.x] = (float)m;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const int Ho = mode == 1 ? H / 2 : (mode == 2 ? H * 2 : H);
+    const int Wo = mode == 1 ? W / 2 : (mode == 2 ? W * 2 : W);
+    const long long total = (long long)Ho * Wo * ncv;
+    const long long i0 = blockIdx.x * work_per_cta;
+    const long long i1 = min(total, i0 + work_per_cta);
+    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        const int cv = (int)(i % ncv);
+        const long long po = i / ncv;
+        const int wo = (int)(po % Wo), ho = (int)(po / Wo);
+        const int c = cv * V;
+        const float* src;
+        int cs, cc;
+        if (c < C1) { src = x1; cs = C1; cc = c; }
+        else { src = x2; cs = C2; cc = c - C1; }
+        src += (size_t)b * H * W * cs + cc;
+        float sc[V], bi[V], acc[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const int g = (c + j) / gs;
+            sc[j] = s_rstd[g] * gamma[c + j];
+            bi[j] = beta[c + j] - sc[j] * s_mean[g];
+            acc[j] = 0.f;
+        }
+        const int taps = mode == 1 ? 4 : 1;
+        for (int tp = 0; tp < taps; ++tp) {
+            int hi, wi;
+            if (mode == 1) { hi = 2 * ho + (tp >> 1); wi = 2 * wo + (tp & 1); }
+            else if (mode == 2) { hi = ho >> 1; wi = wo >> 1; }
+            else { hi = ho; wi = wo; }
+            float v[V];
+            if (V == 4) {
+                const F4 t = ld4(src + ((size_t)hi * W + wi) * cs);
+                v[0] = t.x; v[1 % V] = t.y; v[2 % V] = t.z; v[3 % V] = t.w;
+            } else {
+                v[0] = src[((size_t)hi * W + wi) * cs];
+            }
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float y = v[j] * sc[j] + bi[j];
+                if (do_silu) y = silu(y);
+                acc[j] += y;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            if (mode == 1) acc[j] *= 0.25f;
+            if (rtf32) acc[j] = round_tf32(acc[j]);
+        }
+        float* dst = out + (((size_t)b * Ho + ho) * Wo + wo) * C + c;
+        if (V == 4) {
+            F4 o; o.x = acc[0]; o.y = acc[1 % V]; o.z = acc[2 % V]; o.w = acc[3 % V];
+            st4(dst, o);
+        } else {
+            dst[0] = acc[0];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- exact fp32 implicit-GEMM conv
+// CTA tile 64 pixels x 64 output channels, K chunks of 16 input channels of one tap.
+constexpr int CBM = 64, CBN = 64, CBK = 16;
+
+struct ConvArgs {
+    anoddpm_conv_desc d;
+    int M;     // B*H*W
+    int Ktot;  // packed weight row length
+};
+
+__global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs A) {
+    __shared__ float As[CBK][CBM + 4];
+    __shared__ float Bs[CBK][CBN + 4];
+    const anoddpm_conv_desc& d = A.d;
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * CBM, n0 = blockIdx.y * CBN;
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    // loader coordinates
+    const int lp = tid >> 2, lc4 = (tid & 3) * 4;  // A: pixel row lp, channel offset lc4 ; B: cout row lp, k offset lc4
+    const int p = m0 + lp;
+    int pb = 0, ph = 0, pw = 0;
+    const bool pvalid = p < A.M;
+    if (pvalid) { pw = p % d.W; ph = (p / d.W) % d.H; pb = p / (d.W * d.H); }
+    const int nrow = n0 + lp;
+    const bool nvalid = nrow < d.Cout;
+
+    int kbase = 0;  // running offset into the packed K axis
+    for (int seg = 0; seg < 3; ++seg) {
+        const float* src = seg == 0 ? d.a : (seg == 1 ? d.r1 : d.r2);
+        const int Cs = seg == 0 ? d.Ca : (seg == 1 ? d.Cr1 : d.Cr2);
+        if (src == nullptr || Cs == 0) continue;
+        const int ks = seg == 0 ? d.ksize : 1;
+        const int ntaps = ks * ks, padr = ks / 2;
+        for (int tap = 0; tap < ntaps; ++tap) {
+            const int dy = tap / ks - padr, dx = tap % ks - padr;
+            const int hh = ph + dy, ww = pw + dx;
+            const bool inb = pvalid && hh >= 0 && hh < d.H && ww >= 0 && ww < d.W;
+            const float* arow = src + (((size_t)pb * d.H + hh) * d.W + ww) * Cs;
+            for (int c0 = 0; c0 < Cs; c0 += CBK) {
+                F4 av = {0.f, 0.f, 0.f, 0.f};
+                if (inb && c0 + lc4 < Cs) av = ld4(arow + c0 + lc4);
+                F4 bv = {0.f, 0.f, 0.f, 0.f};
+                if (nvalid && c0 + lc4 < Cs) bv = ld4(d.w + (size_t)nrow * A.Ktot + kbase + tap * Cs + c0 + lc4);
+                __syncthreads();
+                As[lc4 + 0][lp] = av.x; As[lc4 + 1][lp] = av.y; As[lc4 + 2][lp] = av.z; As[lc4 + 3][lp] = av.w;
+                Bs[lc4 + 0][lp] = bv.x; Bs[lc4 + 1][lp] = bv.y; Bs[lc4 + 2][lp] = bv.z; Bs[lc4 + 3][lp] = bv.w;
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < CBK; ++k) {
+                    const F4 a4 = ld4(&As[k][ty * 4]);
+                    const F4 b4 = ld4(&Bs[k][tx * 4]);
+                    const float a[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+                }
+            }
+        }
+        kbase += ntaps * Cs;
+    }
+
+    // epilogue
+    const int n = n0 + tx * 4;
+    if (n >= d.Cout) return;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int q = m0 + ty * 4 + i;
+        if (q >= A.M) continue;
+        const int w = q % d.W, h = (q / d.W) % d.H, b = q / (d.W * d.H);
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = acc[i][j];
+            if (d.bias) v[j] += d.bias[n + j];
+            if (d.emb) v[j] += d.emb[(size_t)b * d.emb_stride + n + j];
+        }
+        if (d.res_mode == 1) {
+            const F4 r = ld4(d.res + (size_t)q * d.Cout + n);
+            v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+        } else if (d.res_mode == 2) {
+            const int H2 = d.H * 2, W2 = d.W * 2;
+            const float* rb = d.res + (((size_t)b * H2 + 2 * h) * W2 + 2 * w) * d.Cout + n;
+            const F4 r0 = ld4(rb), r1 = ld4(rb + d.Cout), r2 = ld4(rb + (size_t)W2 * d.Cout),
+                     r3 = ld4(rb + (size_t)W2 * d.Cout + d.Cout);
+            v[0] += (r0.x + r1.x + r2.x + r3.x) * 0.25f;
+            v[1] += (r0.y + r1.y + r2.y + r3.y) * 0.25f;
+            v[2] += (r0.z + r1.z + r2.z + r3.z) * 0.25f;
+            v[3] += (r0.w + r1.w + r2.w + r3.w) * 0.25f;
+        } else if (d.res_mode == 3) {
+            const int Hh = d.H / 2, Wh = d.W / 2;
+            const F4 r = ld4(d.res + (((size_t)b * Hh + (h >> 1)) * Wh + (w >> 1)) * d.Cout + n);
+            v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+        }
+        F4 o; o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = v[3];
+        st4(d.out + (size_t)q * d.Cout + n, o);
+    }
+}
+
+// ---------------------------------------------------------------- stem: NCHW image -> NHWC features
+__global__ void __launch_bounds__(256) conv_stem_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        int B, int Cin, int H, int W, int Cout) {
+    extern __shared__ float sw[];  // [Cout][Cin*9] + bias
+    const int nw = Cout * Cin * 9;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[nw + i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const long long total = (long long)B * H * W * Cout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout);
+        const long long p = i / Cout;
+        const int xw = (int)(p % W), yh = (int)((p / W) % H), b = (int)(p / ((long long)W * H));
+        float acc = 0.f;  // OIHW order: ci, ky, kx (matches a direct convolution loop nest)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int ky = 0; ky < 3; ++ky) {
+                const int yy = yh + ky - 1;
+                if (yy < 0 || yy >= H) continue;
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int xx = xw + kx - 1;
+                    if (xx < 0 || xx >= W) continue;
+                    acc = fmaf(x[(((size_t)b * Cin + ci) * H + yy) * W + xx], sw[(co * Cin + ci) * 9 + ky * 3 + kx], acc);
+                }
+            }
+        out[i] = acc + sw[nw + co];
+    }
+}
+
+// ---------------------------------------------------------------- head: NHWC features -> NCHW image
+// one warp per output pixel, lanes over input channels (coalesced), all Cout (<= 4) at once.
+__global__ void __launch_bounds__(256) conv_head_kernel(float* __restrict__ out, const float* __restrict__ a,
+                                                        const float* __restrict__ w, const float* __restrict__ bias,
+                                                        int B, int Cin, int H, int W, int Cout) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long npix = (long long)B * H * W;
+    if (warp >= npix) return;
+    const int xw = (int)(warp % W), yh = (int)((warp / W) % H), b = (int)(warp / ((long long)W * H));
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int tap = 0; tap < 9; ++tap) {
+        const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        const float* row = a + (((size_t)b * H + yy) * W + xx) * Cin;
+        for (int c = lane; c < Cin; c += 32) {
+            const float v = row[c];
+            for (int co = 0; co < Cout; ++co) acc[co] = fmaf(v, w[(size_t)co * 9 * Cin + tap * Cin + c], acc[co]);
+        }
+    }
+    for (int co = 0; co < Cout; ++co) {
+        float s = acc[co];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) out[(((size_t)b * Cout + co) * H + yh) * W + xw] = s + (bias ? bias[co] : 0.f);
+    }
+}
+
+// ---------------------------------------------------------------- attention (UNet.py:137-153)
+// CTA: one (b, head), QB queries.  smem: q tile [QB][ch] (pre-scaled by 1/sqrt(ch)), scores [QB][T].
+constexpr int QB = 8;
+
+__global__ void __launch_bounds__(128) attention_kernel(float* __restrict__ out, const float* __restrict__ qkv, int T,
+                                                        int C, int heads) {
+    extern __shared__ float sm[];
+    const int ch = C / heads;
+    float* sq = sm;            // QB * ch
+    float* ss = sm + QB * ch;  // QB * T
+    const int b = blockIdx.z, h = blockIdx.y, t0 = blockIdx.x * QB;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t row = (size_t)3 * C;
+    const float* base = qkv + (size_t)b * T * row + (size_t)h * 3 * ch;
+    const float scale = 1.0f / sqrtf((float)ch);
+    for (int i = tid; i < QB * ch; i += blockDim.x) {
+        const int qi = i / ch, c = i - qi * ch;
+        sq[i] = (t0 + qi < T) ? base[(size_t)(t0 + qi) * row + c] * scale : 0.f;
+    }
+    __syncthreads();
+    // scores: warp per key
+    for (int s = warp; s < T; s += 4) {
+        const float* kr = base + (size_t)s * row + ch;
+        float part[QB];
+#pragma unroll
+        for (int qi = 0; qi < QB; ++qi) part[qi] = 0.f;
+        for (int c = lane; c < ch; c += 32) {
+            const float kv = kr[c];
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) part[qi] = fmaf(sq[qi * ch + c], kv, part[qi]);
+        }
+#pragma unroll
+        for (int qi = 0; qi < QB; ++qi) {
+            float v = part[qi];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) ss[qi * T + s] = v;
+        }
+    }
+    __syncthreads();
+    // softmax rows: warp handles rows warp, warp+4
+    for (int qi = warp; qi < QB; qi += 4) {
+        float* r = ss + qi * T;
+        float mx = -INFINITY;
+        for (int s = lane; s < T; s += 32) mx = fmaxf(mx, r[s]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int s = lane; s < T; s += 32) {
+            const float e = expf(r[s] - mx);
+            r[s] = e;
+            sum += e;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.0f / sum;
+        for (int s = lane; s < T; s += 32) r[s] *= inv;
+    }
+    __syncthreads();
+    // out = P . V : thread per channel
+    for (int c = tid; c < ch; c += blockDim.x) {
+        float acc[QB];
+#pragma unroll
+        for (int qi = 0; qi < QB; ++qi) acc[qi] = 0.f;
+        const float* vr = base + 2 * ch + c;
+        for (int s = 0; s < T; ++s) {
+            const float v = vr[(size_t)s * row];
+#pragma unroll
+            for (int qi = 0; qi < QB; ++qi) acc[qi] = fmaf(ss[qi * T + s], v, acc[qi]);
+        }
+#pragma unroll
+        for (int qi = 0; qi < QB; ++qi)
+            if (t0 + qi < T) out[((size_t)b * T + t0 + qi) * C + h * ch + c] = acc[qi];
+    }
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+int anoddpm_conv_tc(const anoddpm_conv_desc* d, void* stream);  // conv_tc.cu
+
+extern "C" int anoddpm_timestep_embedding(float* emb, const int64_t* t, int B, int dim, void* stream) {
+    ADP_REQUIRE(emb && t && B > 0 && dim > 0 && dim % 2 == 0, "anoddpm_timestep_embedding: bad arguments");
+    const int n = B * (dim / 2);
+    tembed_kernel<<<adp_ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(emb, (const long long*)t, B, dim);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}
+
+extern "C" int anoddpm_linear(float* y, int ldy, const float* x, int ldx, const float* w, const float* bias, int B,
+                              int N, int K, int silu_in, void* stream) {
+    ADP_REQUIRE(y && x && w && B > 0 && N > 0 && K > 0, "anoddpm_linear: bad arguments");
+    const long long warps = (long long)B * N;
+    linear_kernel<<<adp_ceil_div(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(y, ldy, x, ldx, w, bias, B, N, K,
+                                                                                   silu_in);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}
+
+static int gn_vec(int C1, int C2, int groups, const void* p1, const void* p2) {
+    const int C = C1 + C2, gs = C / groups;
+    return (gs % 4 == 0 && C1 % 4 == 0 && C2 % 4 == 0 && al16(p1) && (!p2 || al16(p2))) ? 4 : 1;
+}
+
+extern "C" int anoddpm_gn_stats(double* stats, const float* x1, int C1, const float* x2, int C2, int B, int HW,
+                                int groups, void* stream) {
+    ADP_REQUIRE(stats && x1 && B > 0 && B <= 65535 && HW > 0, "anoddpm_gn_stats: bad arguments");
+    ADP_REQUIRE((C2 == 0) == (x2 == nullptr), "anoddpm_gn_stats: x2/C2 mismatch");
+    const int C = C1 + C2;
+    ADP_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0, "anoddpm_gn_stats: C=%d not divisible into %d groups", C,
+                groups);
+    int ppc = 2048;  // pixels per CTA
+    while (ppc > 64 && (long long)adp_ceil_div(HW, ppc) * B < 148 * 2) ppc >>= 1;
+    dim3 grid(adp_ceil_div(HW, ppc), B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (gn_vec(C1, C2, groups, x1, x2) == 4)
+        gn_stats_kernel<4><<<grid, 256, 0, st>>>(stats, x1, C1, x2, C2, HW, groups, ppc);
+    else
+        gn_stats_kernel<1><<<grid, 256, 0, st>>>(stats, x1, C1, x2, C2, HW, groups, ppc);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}
+
+extern "C" int anoddpm_gn_apply(float* out, const float* x1, int C1, const float* x2, int C2, const double* stats,
+                                const float* gamma, const float* beta, int B, int H, int W, int groups, float eps,
+                                int do_silu, int mode, int rtf32, void* stream) {
+    ADP_REQUIRE(out && x1 && stats && gamma && beta && B > 0 && B <= 65535 && H > 0 && W > 0,
+                "anoddpm_gn_apply: bad arguments");
+    ADP_REQUIRE((C2 == 0) == (x2 == nullptr), "anoddpm_gn_apply: x2/C2 mismatch");
+    const int C = C1 + C2;
+    ADP_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0, "anoddpm_gn_apply: bad groups");
+    ADP_REQUIRE(mode >= 0 && mode <= 2, "anoddpm_gn_apply: bad mode %d", mode);
+    ADP_REQUIRE(mode != 1 || (H % 2 == 0 && W % 2 == 0), "anoddpm_gn_apply: avg-pool needs even H, W");
+    const int V = (gn_vec(C1, C2, groups, x1, x2) == 4 && al16(out)) ? 4 : 1;
+    const int Ho = mode == 1 ? H / 2 : (mode == 2 ? H * 2 : H), Wo = mode == 1 ? W / 2 : (mode == 2 ? W * 2 : W);
+    const long long total = (long long)Ho * Wo * (C / V);
+    long long wpc = 256 * 16;
+    while (wpc > 256 && (total + wpc - 1) / wpc * B < 148 * 4) wpc >>= 1;
+    dim3 grid((unsigned)((total + wpc - 1) / wpc), B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (V == 4)
+        gn_apply_kernel<4><<<grid, 256, 0, st>>>(out, x1, C1, x2, C2, stats, gamma, beta, H, W, groups, eps, do_silu,
+                                                 mode, rtf32, wpc);
+    else
+        gn_apply_kernel<1><<<grid, 256, 0, st>>>(out, x1, C1, x2, C2, stats, gamma, beta, H, W, groups, eps, do_silu,
+                                                 mode, rtf32, wpc);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}
+
+extern "C" int anoddpm_conv(const anoddpm_conv_desc* d, void* stream) {
+    ADP_REQUIRE(d && d->out && d->a && d->w, "anoddpm_conv: null pointer");
+    ADP_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cout > 0 && d->Ca > 0, "anoddpm_conv: bad shape");
+    ADP_REQUIRE(d->ksize == 1 || d->ksize == 3, "anoddpm_conv: ksize must be 1 or 3");
+    ADP_REQUIRE((d->Cr1 == 0) == (d->r1 == nullptr) && (d->Cr2 == 0) == (d->r2 == nullptr),
+                "anoddpm_conv: skip source / channel mismatch");
+    ADP_REQUIRE(d->Ca % 4 == 0 && d->Cr1 % 4 == 0 && d->Cr2 % 4 == 0 && d->Cout % 4 == 0,
+                "anoddpm_conv: channel counts must be multiples of 4 (Ca=%d Cr1=%d Cr2=%d Cout=%d)", d->Ca, d->Cr1,
+                d->Cr2, d->Cout);
+    ADP_REQUIRE(d->res_mode >= 0 && d->res_mode <= 3 && ((d->res_mode == 0) == (d->res == nullptr)),
+                "anoddpm_conv: residual mode / pointer mismatch");
+    ADP_REQUIRE(d->res_mode != 3 || (d->H % 2 == 0 && d->W % 2 == 0), "anoddpm_conv: upsampled residual needs even H, W");
+    ADP_REQUIRE(al16(d->out) && al16(d->a) && al16(d->w) && (!d->r1 || al16(d->r1)) && (!d->r2 || al16(d->r2)) &&
+                    (!d->res || al16(d->res)),
+                "anoddpm_conv: pointers must be 16-byte aligned");
+    if (d->impl == 1) return anoddpm_conv_tc(d, stream);
+    ADP_REQUIRE(d->impl == 0, "anoddpm_conv: unknown impl %d", d->impl);
+    ConvArgs A;
+    A.d = *d;
+    A.M = d->B * d->H * d->W;
+    A.Ktot = d->ksize * d->ksize * d->Ca + d->Cr1 + d->Cr2;
+    dim3 grid(adp_ceil_div(A.M, CBM), adp_ceil_div(d->Cout, CBN));
+    conv_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}
+
+extern "C" int anoddpm_conv_stem(float* out, const float* x, const float* w, const float* bias, int B, int Cin, int H,
+                                 int W, int Cout, void* stream) {
+    ADP_REQUIRE(out && x && w && B > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, "anoddpm_conv_stem: bad arguments");
+    const size_t smem = ((size_t)Cout * Cin * 9 + Cout) * sizeof(float);
+    ADP_REQUIRE(smem <= 48 * 1024, "anoddpm_conv_stem: weights (%zu B) exceed shared memory", smem);
+    const long long total = (long long)B * H * W * Cout;
+    int blocks = adp_ceil_div(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    conv_stem_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(out, x, w, bias, B, Cin, H, W, Cout);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}
+
+extern "C" int anoddpm_conv_head(float* out, const float* a, const float* w, const float* bias, int B, int Cin, int H,
+                                 int W, int Cout, void* stream) {
+    ADP_REQUIRE(out && a && w && B > 0 && Cin > 0 && H > 0 && W > 0, "anoddpm_conv_head: bad arguments");
+    ADP_REQUIRE(Cout >= 1 && Cout <= 4, "anoddpm_conv_head: Cout must be 1..4 (got %d)", Cout);
+    const long long npix = (long long)B * H * W;
+    conv_head_kernel<<<adp_ceil_div(npix * 32, 256), 256, 0, (cudaStream_t)stream>>>(out, a, w, bias, B, Cin, H, W, Cout);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}
+
+extern "C" int anoddpm_attention(float* out, const float* qkv, int B, int T, int C, int heads, void* stream) {
+    ADP_REQUIRE(out && qkv && B > 0 && T > 0 && C > 0 && heads > 0 && C % heads == 0, "anoddpm_attention: bad arguments");
+    ADP_REQUIRE(B <= 65535 && heads <= 65535, "anoddpm_attention: batch/heads too large");
+    const int ch = C / heads;
+    const size_t smem = (size_t)QB * (ch + T) * sizeof(float);
+    ADP_REQUIRE(smem <= 200 * 1024, "anoddpm_attention: T=%d ch=%d needs %zu B of shared memory", T, ch, smem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        ADP_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(adp_ceil_div(T, QB), heads, B);
+    attention_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(out, qkv, T, C, heads);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}

@@ -1,0 +1,289 @@
+"""UNet inference engine: walks a ``UNetModel`` module tree once, packs its weights for the kernels and
+executes the forward pass as a sequence of C-ABI calls on the current CUDA stream.
+
+Data layout in HBM: activations NHWC fp32 (pixel-major, channels contiguous = the K axis of the implicit
+GEMM, so a 32-channel K-block is one 128-byte TMA row); conv weights packed [Cout][Ktot] K-major with
+Ktot ordered tap-major / channel-minor followed by the 1x1 skip-connection channels; GroupNorm
+statistics fp64 (sum, sum of squares) per (sample, group).
+
+Fusion map of one ResBlock (reference UNet.py:202-217), 6 launches instead of ~20 library calls:
+    gn_stats(x[,skip]) -> gn_apply(+SiLU,+avgpool/upsample,+concat,+tf32 round)
+    -> conv3x3(+bias,+timestep-embedding row)
+    -> gn_stats -> gn_apply(+SiLU) -> conv3x3(+bias,+1x1 skip conv as extra K-blocks | +identity residual
+       with the x_upd resample folded into the epilogue read)
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, call, ptr, stream
+
+_MODE = {"same": 0, "down": 1, "up": 2}
+_RES_FOR_MODE = {"same": 1, "down": 2, "up": 3}
+
+
+def round_tf32_(w):
+    """In-place round-to-nearest (ties away) of fp32 values to TF32 precision, like cvt.rna.tf32.f32."""
+    i = w.view(torch.int32)
+    i.add_(0x1000).bitwise_and_(-8192)
+    return w
+
+
+def pack_conv_weight(w):
+    """OIHW (or OI1 for Conv1d) -> [Cout][taps*Cin], tap-major / channel-minor."""
+    if w.dim() == 3:
+        w = w.unsqueeze(-1)
+    co, ci, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
+
+
+class _Conv:
+    """One fused convolution site (weights packed lazily per implementation)."""
+
+    def __init__(self, weights, biases, ksize):
+        self.weights = weights      # list of parameter tensors: main conv first, then optional 1x1 skip conv
+        self.biases = biases
+        self.ksize = ksize
+        self.cache = {}
+
+    def packed(self, impl):
+        if impl not in self.cache:
+            parts = [pack_conv_weight(w.detach()) for w in self.weights]
+            w = torch.cat(parts, dim=1).contiguous().float()
+            if impl == 1:
+                round_tf32_(w)
+            b = self.biases[0].detach().float()
+            for extra in self.biases[1:]:
+                b = b + extra.detach().float()
+            self.cache[impl] = (w, b.contiguous())
+        return self.cache[impl]
+
+
+class UNetEngine:
+    def __init__(self, model):
+        self.model = model
+        self._sig = None
+        self.launches = 0           # native kernel launches issued (for bench.py's gpu_launches)
+
+    # ------------------------------------------------------------------ packing
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version, p.device) for p in self.model.parameters())
+
+    def _build(self):
+        from .UNet import AttentionBlock, ResBlock
+        m = self.model
+        self.gn_sites = 0
+        self.emb_w, self.emb_b, self.emb_off = [], [], 0
+
+        def gn_site():
+            self.gn_sites += 1
+            return self.gn_sites - 1
+
+        def build_res(rb):
+            if not isinstance(rb.skip_connection, (torch.nn.Identity, torch.nn.Conv2d)) or (
+                    isinstance(rb.skip_connection, torch.nn.Conv2d) and rb.skip_connection.kernel_size != (1, 1)):
+                raise NotImplementedError("ResBlock(use_conv=True) skip has no native kernel")
+            conv1, conv2 = rb.in_layers[2], rb.out_layers[3]
+            cout = conv1.out_channels
+            e = {"kind": "res", "mode": rb.resample_mode, "cin": conv1.in_channels, "cout": cout,
+                 "gn1": rb.in_layers[0], "gn2": rb.out_layers[0], "s1": gn_site(), "s2": gn_site(),
+                 "conv1": _Conv([conv1.weight], [conv1.bias], 3), "emb_off": self.emb_off}
+            self.emb_w.append(rb.embed_layers[1].weight)
+            self.emb_b.append(rb.embed_layers[1].bias)
+            self.emb_off += cout
+            if isinstance(rb.skip_connection, torch.nn.Conv2d):
+                e["conv2"] = _Conv([conv2.weight, rb.skip_connection.weight], [conv2.bias, rb.skip_connection.bias], 3)
+                e["skip_conv"] = True
+            else:
+                e["conv2"] = _Conv([conv2.weight], [conv2.bias], 3)
+                e["skip_conv"] = False
+            return e
+
+        def build_attn(ab):
+            return {"kind": "attn", "c": ab.in_channels, "heads": ab.num_heads, "gn": ab.norm, "s": gn_site(),
+                    "qkv": _Conv([ab.to_qkv.weight], [ab.to_qkv.bias], 1),
+                    "proj": _Conv([ab.proj_out.weight], [ab.proj_out.bias], 1)}
+
+        def build_entry(seq):
+            out = []
+            for layer in seq:
+                if isinstance(layer, ResBlock):
+                    out.append(build_res(layer))
+                elif isinstance(layer, AttentionBlock):
+                    out.append(build_attn(layer))
+                elif isinstance(layer, torch.nn.Conv2d):
+                    out.append({"kind": "stem", "conv": layer})
+                else:
+                    raise NotImplementedError(f"{type(layer).__name__} has no native kernel "
+                                              "(biggan_updown=False resampling is not on the reference's path)")
+            return out
+
+        self.down = [build_entry(seq) for seq in m.down]
+        self.middle = build_entry(m.middle)
+        self.up = [build_entry(seq) for seq in m.up]
+        self.head = {"gn": m.out[0], "s": gn_site(), "conv": m.out[2]}
+        self.emb_cat_w = torch.cat([w.detach() for w in self.emb_w], dim=0).contiguous().float()
+        self.emb_cat_b = torch.cat([b.detach() for b in self.emb_b], dim=0).contiguous().float()
+        self.head_w = pack_conv_weight(self.head["conv"].weight.detach()).contiguous().float()
+
+    def _refresh(self):
+        sig = self._signature()
+        if sig != self._sig:
+            self._build()
+            self._sig = sig
+
+    # ------------------------------------------------------------------ op wrappers
+    def _gn_stats(self, site, srcs, B, HW):
+        x1 = srcs[0]
+        x2 = srcs[1] if len(srcs) > 1 else None
+        call("anoddpm_gn_stats", ptr(self.stats[site]), ptr(x1), x1.shape[-1], ptr(x2), x2.shape[-1] if x2 is not None else 0,
+             B, HW, 32, stream())
+        self.launches += 1
+
+    def _gn_apply(self, site, srcs, gn, B, H, W, silu, mode, rtf32):
+        x1 = srcs[0]
+        x2 = srcs[1] if len(srcs) > 1 else None
+        C = x1.shape[-1] + (x2.shape[-1] if x2 is not None else 0)
+        Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
+        out = torch.empty((B, Ho, Wo, C), device=x1.device, dtype=torch.float32)
+        call("anoddpm_gn_apply", ptr(out), ptr(x1), x1.shape[-1], ptr(x2), x2.shape[-1] if x2 is not None else 0,
+             ptr(self.stats[site]), ptr(gn.weight), ptr(gn.bias), B, H, W, 32, float(gn.eps), int(silu), mode,
+             int(rtf32), stream())
+        self.launches += 1
+        return out
+
+    def _conv(self, site, a, B, H, W, cout, r=(), emb=None, res=None, res_mode=0):
+        d = ConvDesc()
+        d.B, d.H, d.W = B, H, W
+        d.Ca, d.Cout, d.ksize = a.shape[-1], cout, site.ksize
+        d.Cr1 = r[0].shape[-1] if len(r) > 0 else 0
+        d.Cr2 = r[1].shape[-1] if len(r) > 1 else 0
+        impl = 1 if (self.use_tc and _lib.lib().anoddpm_conv_tc_supported(ctypes.byref(d))) else 0
+        w, b = site.packed(impl)
+        out = torch.empty((B, H, W, cout), device=a.device, dtype=torch.float32)
+        d.out, d.a, d.w, d.bias = out.data_ptr(), a.data_ptr(), w.data_ptr(), b.data_ptr()
+        d.r1 = r[0].data_ptr() if len(r) > 0 else None
+        d.r2 = r[1].data_ptr() if len(r) > 1 else None
+        if emb is not None:
+            d.emb, d.emb_stride = emb.data_ptr(), self.emb_all.shape[1]
+        else:
+            d.emb, d.emb_stride = None, 0
+        d.res = res.data_ptr() if res is not None else None
+        d.res_mode = res_mode
+        d.impl = impl
+        call("anoddpm_conv", ctypes.byref(d), stream())
+        self.launches += 1
+        self.tc_convs += impl
+        return out
+
+    def _tc_ok(self, C, H, W):
+        """Will the conv consuming a (.., H, W, C) activation run on tensor cores? (decides the TF32 rounding)"""
+        if not self.use_tc:
+            return False
+        d = ConvDesc()
+        d.B, d.H, d.W, d.Ca, d.Cr1, d.Cr2, d.Cout, d.ksize = 1, H, W, C, 0, 0, 32, 3
+        return bool(_lib.lib().anoddpm_conv_tc_supported(ctypes.byref(d)))
+
+    # ------------------------------------------------------------------ blocks
+    def _res(self, e, srcs, B, H, W):
+        mode = _MODE[e["mode"]]
+        Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
+        self._gn_stats(e["s1"], srcs, B, H * W)
+        a1 = self._gn_apply(e["s1"], srcs, e["gn1"], B, H, W, True, mode, self._tc_ok(e["cin"], Ho, Wo))
+        emb = self.emb_all[:, e["emb_off"]:]
+        h = self._conv(e["conv1"], a1, B, Ho, Wo, e["cout"], emb=emb)
+        del a1
+        self._gn_stats(e["s2"], [h], B, Ho * Wo)
+        a2 = self._gn_apply(e["s2"], [h], e["gn2"], B, Ho, Wo, True, 0, self._tc_ok(e["cout"], Ho, Wo))
+        del h
+        if e["skip_conv"]:
+            return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], r=srcs), Ho, Wo
+        assert len(srcs) == 1
+        return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], res=srcs[0], res_mode=_RES_FOR_MODE[e["mode"]]), Ho, Wo
+
+    def _attn(self, e, x, B, H, W):
+        C, T = e["c"], H * W
+        self._gn_stats(e["s"], [x], B, T)
+        xn = self._gn_apply(e["s"], [x], e["gn"], B, H, W, False, 0, self._tc_ok(C, H, W))
+        qkv = self._conv(e["qkv"], xn, B, H, W, 3 * C)
+        del xn
+        a = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
+        call("anoddpm_attention", ptr(a), ptr(qkv), B, T, C, e["heads"], stream())
+        self.launches += 1
+        return self._conv(e["proj"], a, B, H, W, C, res=x, res_mode=1)
+
+    def _entry(self, entry, srcs, B, H, W):
+        h = None
+        for e in entry:
+            cur = srcs if h is None else [h]
+            if e["kind"] == "stem":
+                raise RuntimeError("stem handled by forward()")
+            if e["kind"] == "res":
+                h, H, W = self._res(e, cur, B, H, W)
+            else:
+                assert len(cur) == 1
+                h = self._attn(e, cur[0], B, H, W)
+        return h, H, W
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, x, t):
+        m = self.model
+        _lib.require_cuda(x, "UNetModel input")
+        p0 = next(m.parameters())
+        if p0.device != x.device:
+            raise RuntimeError(f"UNetModel parameters are on {p0.device} but the input is on {x.device}")
+        self._refresh()
+        self.use_tc = (m.conv_impl == "tc")
+        self.tc_convs = 0
+        in_dtype = x.dtype
+        x = x.contiguous().float()
+        B, Cin, H, W = x.shape
+        if Cin != m.in_channels:
+            raise RuntimeError(f"expected {m.in_channels} input channels, got {Cin}")
+        t = t.to(device=x.device, dtype=torch.int64).contiguous()
+        if t.numel() != B:
+            raise RuntimeError("time must have one entry per sample")
+        dev = x.device
+        base, E = m.model_channels, m.model_channels * 4
+
+        # timestep embedding MLP + all per-ResBlock projections in three small launches
+        temb = torch.empty((B, base), device=dev, dtype=torch.float32)
+        call("anoddpm_timestep_embedding", ptr(temb), ptr(t), B, base, stream())
+        l1, l2 = m.time_embedding[1], m.time_embedding[3]
+        e1 = torch.empty((B, E), device=dev, dtype=torch.float32)
+        call("anoddpm_linear", ptr(e1), E, ptr(temb), base, ptr(l1.weight), ptr(l1.bias), B, E, base, 0, stream())
+        emb = torch.empty((B, E), device=dev, dtype=torch.float32)
+        call("anoddpm_linear", ptr(emb), E, ptr(e1), E, ptr(l2.weight), ptr(l2.bias), B, E, E, 1, stream())
+        S = self.emb_cat_w.shape[0]
+        self.emb_all = torch.empty((B, S), device=dev, dtype=torch.float32)
+        call("anoddpm_linear", ptr(self.emb_all), S, ptr(emb), E, ptr(self.emb_cat_w), ptr(self.emb_cat_b), B, S, E, 1,
+             stream())
+        self.launches += 4
+        self.stats = torch.zeros((self.gn_sites, B, 32, 2), device=dev, dtype=torch.float64)
+
+        stem = self.down[0][0]["conv"]
+        C0 = stem.out_channels
+        h = torch.empty((B, H, W, C0), device=dev, dtype=torch.float32)
+        call("anoddpm_conv_stem", ptr(h), ptr(x), ptr(stem.weight), ptr(stem.bias), B, Cin, H, W, C0, stream())
+        self.launches += 1
+        skips = [(h, H, W)]
+        for entry in self.down[1:]:
+            h, H, W = self._entry(entry, [h], B, H, W)
+            skips.append((h, H, W))
+        h, H, W = self._entry(self.middle, [h], B, H, W)
+        for entry in self.up:
+            s, sh, sw = skips.pop()
+            assert (sh, sw) == (H, W)
+            h, H, W = self._entry(entry, [h, s], B, H, W)
+        hd = self.head
+        self._gn_stats(hd["s"], [h], B, H * W)
+        a = self._gn_apply(hd["s"], [h], hd["gn"], B, H, W, True, 0, False)
+        out = torch.empty((B, m.out_channels, H, W), device=dev, dtype=torch.float32)
+        call("anoddpm_conv_head", ptr(out), ptr(a), ptr(self.head_w), ptr(hd["conv"].bias), B, a.shape[-1], H, W,
+             m.out_channels, stream())
+        self.launches += 1
+        self.emb_all = None
+        self.stats = None
+        return out.to(in_dtype)

@@ -1,0 +1,142 @@
+/*
+ * include/anoddpm_b200.h -- C ABI of libanoddpm_b200.so (sm_100a kernels for the AnoDDPM hot path).
+ *
+ * The reference (Julian-Wyatt/AnoDDPM) is pure Python and has no FFI of its own; its drop-in
+ * boundary is the Python class API (GaussianDiffusionModel / UNetModel / Simplex_CLASS).  This
+ * header is the boundary BELOW that API: each entry point names the reference code it replaces
+ * (paths relative to the reference tree).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (ANODDPM_ERR_*); the message is in
+ *     anoddpm_last_error() (thread-local).  Nothing throws, exits or allocates persistently.
+ *   - all tensor arguments are DEVICE pointers owned by the caller unless marked [host];
+ *     `stream` is a cudaStream_t passed as void*.  Entry points are asynchronous, re-entrant
+ *     and CUDA-graph capturable (no allocation, no synchronisation, no host reads of device data).
+ *   - activations inside the UNet are NHWC fp32 ("pixels x channels"); images at the API edge
+ *     are NCHW fp32 like the reference.
+ */
+#ifndef ANODDPM_B200_H
+#define ANODDPM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANODDPM_ABI_VERSION 1
+
+int anoddpm_abi_version(void);
+const char* anoddpm_last_error(void);
+/* name of the tensor-core conv path compiled in ("tcgen05-tf32") -- for bench/DESIGN bookkeeping */
+const char* anoddpm_build_info(void);
+
+/* ------------------------------------------------------------------ simplex noise ------------- */
+
+/* [host] Permutation tables of one seed.  tables[0..255] = perm, tables[256..511] = perm_grad_index3.
+ * Replaces simplex.py:166-192 (_init / overflow); integer, bit-exact. */
+int anoddpm_simplex_init(int64_t seed, int16_t* tables /* [host] 512 */);
+int anoddpm_simplex_init_batch(const int64_t* seeds /* [host] n */, int n, int16_t* tables /* [host] n*512 */);
+
+/* Fractal simplex noise written straight into an fp32 (B,C,H,W) tensor:
+ *   out[b,c,y,x] = fp32( sum_o persistence^o * noise3(x*2^o/f, y*2^o/f, t[b]*2^o/f ; tables[b*C+c]) )   (fp64 inside)
+ * = GaussianDiffusion.py:96-137 (generate_simplex_noise) -> simplex.py:75-93 (rand_3d_fixed_T_octaves)
+ *   -> :833-840 (_noise3a) -> :321-830 (_noise3), evaluated per sample (batched semantic of DESIGN.md).
+ * shared_seed != 0: tables holds C table sets (one per channel) shared by all samples. */
+int anoddpm_simplex_noise(float* out, int B, int C, int H, int W, const int16_t* tables, int shared_seed,
+                          const int64_t* t /* B */, int octaves, double persistence, double frequency, void* stream);
+
+/* Volume / slice fields for the Simplex_CLASS numpy API: out[d,y,x] (fp64 if out_f64 else fp32),
+ * z coordinate of slice d = z[d] (NULL -> d).  simplex.py:37-54 (rand_3d_octaves), :75-93. */
+int anoddpm_simplex_octaves(void* out, int out_f64, int D, int H, int W, const int16_t* tables /* 512 */,
+                            const double* z /* D or NULL */, int octaves, double persistence, double frequency,
+                            void* stream);
+
+/* out[z][y][x] = noise3(X[x], Y[y], Z[z])   -- simplex.py:833-840 (_noise3a / noise3array) */
+int anoddpm_simplex_grid3(double* out, const double* X, int nx, const double* Y, int ny, const double* Z, int nz,
+                          const int16_t* tables, void* stream);
+/* out[i][j] = noise2(X[j], Y[i])            -- simplex.py:211-318 (_noise2 / _noise2a, square case) */
+int anoddpm_simplex_grid2(double* out, const double* X, int nx, const double* Y, int ny, const int16_t* tables,
+                          void* stream);
+
+/* ------------------------------------------------------------------ diffusion elementwise ----- */
+
+/* out = coef_a[t_b]*x + coef_b[t_b]*noise, per sample b.  GaussianDiffusion.py:361-371 (sample_q, with
+ * sqrt_alphas_cumprod / sqrt_one_minus_alphas_cumprod) and :373-382 (sample_q_gradual, sqrt_alphas / sqrt_betas).
+ * coef_* are fp32 tables of length T (= extract(), :32-36, done once). */
+int anoddpm_q_sample(float* out, const float* x, const float* noise, const int64_t* t, const float* coef_a,
+                     const float* coef_b, int B, int64_t per_sample, void* stream);
+
+/* One reverse step given eps = model(x_t, t):  GaussianDiffusion.py:298-318 (sample_p) with :269-296
+ * (p_mean_variance), :228-230, :253-267 fused.  tables = 5 rows of length T:
+ *   [sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1, posterior_mean_coef2,
+ *    sigma0 = (t!=0)*exp(0.5*log(model_var))].   pred_x0 may be NULL. */
+int anoddpm_p_sample(float* sample, float* pred_x0, const float* x_t, const float* eps, const float* noise,
+                     const int64_t* t, const float* tables, int T, int B, int64_t per_sample, void* stream);
+
+/* ------------------------------------------------------------------ UNet denoiser ops --------- */
+
+/* emb[b, :] = cat(sin(t_b*w), cos(t_b*w)), w_i = exp(-i*ln(1e4)/half).  UNet.py:38-57. */
+int anoddpm_timestep_embedding(float* emb /* B x dim */, const int64_t* t, int B, int dim, void* stream);
+
+/* y[b, n] = sum_k act(x[b,k]) * w[n,k] + bias[n], act = SiLU if silu_in.  UNet.py:271-276, :185-188 (nn.Linear).
+ * ldx / ldy: row strides of x / y (elements). */
+int anoddpm_linear(float* y, int ldy, const float* x, int ldx, const float* w, const float* bias, int B, int N, int K,
+                   int silu_in, void* stream);
+
+/* GroupNorm statistics of a (possibly channel-concatenated) NHWC tensor: for sample b, group g
+ * accumulates (sum, sum of squares) in fp64 into stats[b][g][2] (+=; caller zeroes).  UNet.py:409-411.
+ * x2 may be NULL (C2 = 0): channels [0,C1) come from x1, [C1,C1+C2) from x2 (torch.cat, UNet.py:402). */
+int anoddpm_gn_stats(double* stats /* B x groups x 2 */, const float* x1, int C1, const float* x2, int C2, int B,
+                     int HW, int groups, void* stream);
+
+/* out = resample(act(GroupNorm(x))) on NHWC: act = SiLU if silu; mode 0 same, 1 avg-pool 2x2, 2 nearest x2
+ * (UNet.py:202-210: GN -> SiLU -> h_upd, in that order).  stats from anoddpm_gn_stats over n = HW*(C/groups).
+ * round_tf32: round results to TF32 (rna) for the tensor-core conv that consumes them. */
+int anoddpm_gn_apply(float* out, const float* x1, int C1, const float* x2, int C2, const double* stats,
+                     const float* gamma, const float* beta, int B, int H, int W, int groups, float eps, int silu,
+                     int mode, int round_tf32, void* stream);
+
+/* Convolution as implicit GEMM over NHWC pixels.  out[b,y,x,:] =
+ *     conv_k(a)[..] (k = ksize 3 pad 1, or 1)  +  r1 . W_r1  +  r2 . W_r2      (1x1 "skip" sources, optional)
+ *   + bias  +  emb[b, :] (optional)  +  residual (optional)
+ * w is packed [Cout][Ktot] with Ktot = ksize^2*Ca + Cr1 + Cr2 ordered (tap-major, channel-minor), then r1, r2.
+ * Replaces nn.Conv2d 3x3/1x1 + skip_connection + the adds of ResBlock.forward (UNet.py:202-217) and the
+ * Conv1d 1x1 qkv/proj of AttentionBlock (UNet.py:115-125).
+ * res_mode: 0 none, 1 same resolution, 2 res is 2H x 2W and is avg-pooled 2x2, 3 res is H/2 x W/2 nearest-upsampled
+ * (x_upd of UNet.py:206-207).  impl: 0 = exact fp32 CUDA-core kernel, 1 = tcgen05 kind::tf32 tensor-core kernel. */
+typedef struct anoddpm_conv_desc {
+    float* out;
+    const float* a;
+    const float* r1;
+    const float* r2;
+    const float* w;
+    const float* bias;
+    const float* emb;
+    const float* res;
+    int B, H, W;
+    int Ca, Cr1, Cr2, Cout;
+    int ksize;
+    int emb_stride;
+    int res_mode;
+    int impl;
+} anoddpm_conv_desc;
+int anoddpm_conv(const anoddpm_conv_desc* d /* [host] */, void* stream);
+/* 1 if impl=1 (tcgen05 tiles: channels % 32, Cout % 16, power-of-two W) covers the problem, else 0. */
+int anoddpm_conv_tc_supported(const anoddpm_conv_desc* d /* [host] */);
+
+/* Stem: NCHW image (Cin small) -> NHWC features, 3x3 pad 1, w is OIHW.  UNet.py:279-281. */
+int anoddpm_conv_stem(float* out_nhwc, const float* x_nchw, const float* w_oihw, const float* bias, int B, int Cin,
+                      int H, int W, int Cout, void* stream);
+/* Head: NHWC activated features -> NCHW image (Cout small), 3x3 pad 1, w packed [Cout][9*Cin] tap-major. UNet.py:384-388 */
+int anoddpm_conv_head(float* out_nchw, const float* a_nhwc, const float* w_packed, const float* bias, int B, int Cin,
+                      int H, int W, int Cout, void* stream);
+
+/* QKV attention on qkv[B][T][3*C] (channel layout [head][q|k|v][ch], UNet.py:146-147):
+ * out[b][t][h*ch + c] = sum_s softmax_s( (q_t . k_s) / sqrt(ch) ) v_s[c].   UNet.py:137-153. */
+int anoddpm_attention(float* out /* B x T x C */, const float* qkv, int B, int T, int C, int heads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANODDPM_B200_H */

@@ -1,0 +1,122 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol the header declares, host logic of the
+drop-in modules (no GPU compute calls)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import ROOT
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "anoddpm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(anoddpm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    from anoddpm_b200 import _lib
+    L = _lib.lib()
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/anoddpm_b200.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(syms)
+    assert L.anoddpm_abi_version() == 1
+    assert b"tcgen05" in L.anoddpm_build_info()
+
+
+def test_error_channel_without_gpu():
+    from anoddpm_b200 import _lib
+    L = _lib.lib()
+    rc = L.anoddpm_q_sample(None, None, None, None, None, None, 1, 16, None)
+    assert rc < 0 and b"null pointer" in L.anoddpm_last_error()
+    with pytest.raises(RuntimeError):
+        _lib.check(rc)
+
+
+def test_host_permutation_tables_match_golden(golden):
+    from anoddpm_b200.simplex import _init, init_tables, overflow
+    g = golden("simplex")
+    for i, s in enumerate(g["seeds"]):
+        perm, pgi3 = _init(int(s))
+        assert perm.dtype == np.int64 and np.array_equal(perm, g["perm"][i].astype(np.int64))
+        assert np.array_equal(pgi3, g["pgi3"][i].astype(np.int64))
+    assert init_tables([3, 12345]).shape == (2, 512)
+    assert overflow(2 ** 63) == -2 ** 63
+
+
+def test_simplex_class_host_state_and_rng_stream(golden):
+    from anoddpm_b200.simplex import Simplex_CLASS
+    g = golden("simplex")
+    np.random.seed(0)
+    S = Simplex_CLASS()                       # consumes one draw, like the reference constructor
+    p0, _ = __import__("anoddpm_b200.simplex", fromlist=["_init"])._init(int(g["np_seed0_draws"][0]))
+    assert np.array_equal(S._perm, p0)
+    S.newSeed()                               # second draw
+    assert int(np.random.randint(-10000000000, 10000000000)) == int(g["np_seed0_draws"][2])
+    S.newSeed(12345)
+    assert list(S._perm[:8]) == [33, 182, 149, 37, 26, 75, 1, 19]
+
+
+def test_diffusion_tables_and_schedule_match_golden(golden):
+    from anoddpm_b200.GaussianDiffusion import GaussianDiffusionModel, get_beta_schedule
+    g = golden("diffusion")
+    for T, name in [(100, "linear"), (1000, "linear"), (100, "cosine"), (1000, "cosine")]:
+        D = GaussianDiffusionModel([64, 64], get_beta_schedule(T, name))
+        for n in ("betas", "sqrt_alphas", "sqrt_betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod",
+                  "sqrt_one_minus_alphas_cumprod", "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod",
+                  "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped",
+                  "posterior_mean_coef1", "posterior_mean_coef2"):
+            assert np.array_equal(getattr(D, n), g[f"{name}{T}/{n}"]), n
+        assert D.num_timesteps == T
+    with pytest.raises(NotImplementedError):
+        get_beta_schedule(10, "sqrt")
+    D = GaussianDiffusionModel([64, 64], get_beta_schedule(10, "linear"), loss_weight="prop-t")
+    assert list(D.weights) == list(range(10, 0, -1))
+
+
+def test_unet_state_dict_layout_matches_reference(golden):
+    import hashlib
+    from anoddpm_b200.UNet import UNetModel
+    g = golden("unet")
+    cases = {"c1_64_b32_h2": dict(img_size=64, base_channels=32, n_heads=2),
+             "s32_b32_attn168": dict(img_size=32, base_channels=32, attention_resolutions="16,8"),
+             "s64_b64_hc32_rgb": dict(img_size=64, base_channels=64, n_head_channels=32, in_channels=3),
+             "s128_b32_h4": dict(img_size=128, base_channels=32, n_heads=4)}
+    for name, kw in cases.items():
+        m = UNetModel(**kw)
+        sd = m.state_dict()
+        h = hashlib.sha1("\n".join(f"{k}:{tuple(v.shape)}" for k, v in sd.items()).encode()).hexdigest()
+        assert h == str(g[f"{name}/keys_sha1"]), name
+        assert sum(p.numel() for p in m.parameters()) == int(g[f"{name}/n_params"])
+    with pytest.raises(ValueError):
+        UNetModel(100, 32)
+    m = UNetModel(64, 32)
+    assert float(m.out[2].weight.abs().max()) == 0.0      # zero-initialised head like the reference
+    assert m.attention_resolutions == "32,16,8" and m.num_heads == 1
+
+
+def test_unet_fails_loudly_without_cuda_or_native_autograd():
+    from anoddpm_b200.UNet import UNetModel
+    m = UNetModel(32, 32)
+    x, t = torch.zeros(1, 1, 32, 32), torch.zeros(1, dtype=torch.long)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(x, t)
+    with pytest.raises(NotImplementedError, match="not native"):
+        m(x, t)
+
+
+def test_ema_update():
+    from anoddpm_b200.UNet import UNetModel, update_ema_params
+    import copy
+    a = UNetModel(32, 32)
+    b = copy.deepcopy(a)
+    for p in b.parameters():
+        p.data.add_(1.0)
+    update_ema_params(a, b, 0.9)
+    w0 = UNetModel(32, 32).out[0].weight      # GroupNorm weight = 1 at init
+    assert torch.allclose(a.out[0].weight, 0.9 * w0 + 0.1 * (w0 + 1))
