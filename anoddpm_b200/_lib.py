@@ -34,16 +34,16 @@ SIGNATURES = {
     "anoddpm_simplex_grid2": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
     "anoddpm_q_sample": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp]),
     "anoddpm_p_sample": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
-    "anoddpm_timestep_embedding": (c_int, [c_vp, c_vp, c_int, c_int, c_vp]),
+    "anoddpm_timestep_embedding": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
     "anoddpm_linear": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "anoddpm_gn_stats": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp]),
-    "anoddpm_gn_apply": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32,
+    "anoddpm_gn_apply": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32,
                                  c_int, c_int, c_int, c_vp]),
     "anoddpm_conv": (c_int, [ctypes.POINTER(ConvDesc), c_vp]),
     "anoddpm_conv_tc_supported": (c_int, [ctypes.POINTER(ConvDesc)]),
     "anoddpm_conv_stem": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "anoddpm_conv_head": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
-    "anoddpm_attention": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
+    "anoddpm_attention": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
 }
 
 _lib = None

@@ -22,14 +22,13 @@ __device__ __forceinline__ float round_tf32(float v) {
 }
 
 // ---------------------------------------------------------------- timestep embedding (UNet.py:50-57)
-__global__ void tembed_kernel(float* __restrict__ emb, const long long* __restrict__ t, int B, int dim) {
+__global__ void tembed_kernel(float* __restrict__ emb, const long long* __restrict__ t,
+                              const float* __restrict__ freq, int B, int dim) {
     const int half = dim / 2;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
     const int b = i / half, j = i - b * half;
-    const float neg = -(float)(9.210340371976184 / (double)half);  // -(ln 1e4)/half, rounded to fp32 like torch
-    const float w = expf((float)j * neg);
-    const float a = (float)t[b] * w;
+    const float a = (float)t[b] * freq[j];
     emb[(size_t)b * dim + j] = sinf(a);
     emb[(size_t)b * dim + half + j] = cosf(a);
 }
@@ -105,7 +104,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(double* __restrict__ stat
 // ---------------------------------------------------------------- GroupNorm apply (+SiLU, +resample)
 // grid (chunks, B).  Output NHWC (B, Ho, Wo, C).  mode 0 same, 1 avg-pool 2x2 (of activated values), 2 nearest x2.
 template <int V>
-__global__ void __launch_bounds__(256) gn_apply_kernel(float* __restrict__ out, const float* __restrict__ x1, int C1,
+__global__ void __launch_bounds__(256) gn_apply_kernel(float* __restrict__ out, float* __restrict__ raw_out,
+                                                       const float* __restrict__ x1, int C1,
                                                        const float* __restrict__ x2, int C2,
                                                        const double* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -164,6 +164,15 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(float* __restrict__ out, 
                 float y = v[j] * sc[j] + bi[j];
                 if (do_silu) y = silu(y);
                 acc[j] += y;
+            }
+            if (raw_out) {  // mode 0 only: TF32-rounded concatenated copy of the input for the fused skip conv
+                float* rd = raw_out + (((size_t)b * H + hi) * W + wi) * C + c;
+                if (V == 4) {
+                    F4 o; o.x = round_tf32(v[0]); o.y = round_tf32(v[1 % V]); o.z = round_tf32(v[2 % V]); o.w = round_tf32(v[3 % V]);
+                    st4(rd, o);
+                } else {
+                    rd[0] = round_tf32(v[0]);
+                }
             }
         }
 #pragma unroll
@@ -348,7 +357,7 @@ __global__ void __launch_bounds__(256) conv_head_kernel(float* __restrict__ out,
 constexpr int QB = 8;
 
 __global__ void __launch_bounds__(128) attention_kernel(float* __restrict__ out, const float* __restrict__ qkv, int T,
-                                                        int C, int heads) {
+                                                        int C, int heads, int rtf32) {
     extern __shared__ float sm[];
     const int ch = C / heads;
     float* sq = sm;            // QB * ch
@@ -415,7 +424,7 @@ __global__ void __launch_bounds__(128) attention_kernel(float* __restrict__ out,
         }
 #pragma unroll
         for (int qi = 0; qi < QB; ++qi)
-            if (t0 + qi < T) out[((size_t)b * T + t0 + qi) * C + h * ch + c] = acc[qi];
+            if (t0 + qi < T) out[((size_t)b * T + t0 + qi) * C + h * ch + c] = rtf32 ? round_tf32(acc[qi]) : acc[qi];
     }
 }
 
@@ -425,10 +434,11 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 
 int anoddpm_conv_tc(const anoddpm_conv_desc* d, void* stream);  // conv_tc.cu
 
-extern "C" int anoddpm_timestep_embedding(float* emb, const int64_t* t, int B, int dim, void* stream) {
-    ADP_REQUIRE(emb && t && B > 0 && dim > 0 && dim % 2 == 0, "anoddpm_timestep_embedding: bad arguments");
+extern "C" int anoddpm_timestep_embedding(float* emb, const int64_t* t, const float* freq, int B, int dim,
+                                          void* stream) {
+    ADP_REQUIRE(emb && t && freq && B > 0 && dim > 0 && dim % 2 == 0, "anoddpm_timestep_embedding: bad arguments");
     const int n = B * (dim / 2);
-    tembed_kernel<<<adp_ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(emb, (const long long*)t, B, dim);
+    tembed_kernel<<<adp_ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(emb, (const long long*)t, freq, B, dim);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }
@@ -467,9 +477,9 @@ extern "C" int anoddpm_gn_stats(double* stats, const float* x1, int C1, const fl
     return ANODDPM_OK;
 }
 
-extern "C" int anoddpm_gn_apply(float* out, const float* x1, int C1, const float* x2, int C2, const double* stats,
-                                const float* gamma, const float* beta, int B, int H, int W, int groups, float eps,
-                                int do_silu, int mode, int rtf32, void* stream) {
+extern "C" int anoddpm_gn_apply(float* out, float* raw_out, const float* x1, int C1, const float* x2, int C2,
+                                const double* stats, const float* gamma, const float* beta, int B, int H, int W,
+                                int groups, float eps, int do_silu, int mode, int rtf32, void* stream) {
     ADP_REQUIRE(out && x1 && stats && gamma && beta && B > 0 && B <= 65535 && H > 0 && W > 0,
                 "anoddpm_gn_apply: bad arguments");
     ADP_REQUIRE((C2 == 0) == (x2 == nullptr), "anoddpm_gn_apply: x2/C2 mismatch");
@@ -477,7 +487,8 @@ extern "C" int anoddpm_gn_apply(float* out, const float* x1, int C1, const float
     ADP_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0, "anoddpm_gn_apply: bad groups");
     ADP_REQUIRE(mode >= 0 && mode <= 2, "anoddpm_gn_apply: bad mode %d", mode);
     ADP_REQUIRE(mode != 1 || (H % 2 == 0 && W % 2 == 0), "anoddpm_gn_apply: avg-pool needs even H, W");
-    const int V = (gn_vec(C1, C2, groups, x1, x2) == 4 && al16(out)) ? 4 : 1;
+    ADP_REQUIRE(raw_out == nullptr || mode == 0, "anoddpm_gn_apply: raw_out needs mode 0");
+    const int V = (gn_vec(C1, C2, groups, x1, x2) == 4 && al16(out) && (!raw_out || al16(raw_out))) ? 4 : 1;
     const int Ho = mode == 1 ? H / 2 : (mode == 2 ? H * 2 : H), Wo = mode == 1 ? W / 2 : (mode == 2 ? W * 2 : W);
     const long long total = (long long)Ho * Wo * (C / V);
     long long wpc = 256 * 16;
@@ -485,10 +496,10 @@ extern "C" int anoddpm_gn_apply(float* out, const float* x1, int C1, const float
     dim3 grid((unsigned)((total + wpc - 1) / wpc), B);
     cudaStream_t st = (cudaStream_t)stream;
     if (V == 4)
-        gn_apply_kernel<4><<<grid, 256, 0, st>>>(out, x1, C1, x2, C2, stats, gamma, beta, H, W, groups, eps, do_silu,
+        gn_apply_kernel<4><<<grid, 256, 0, st>>>(out, raw_out, x1, C1, x2, C2, stats, gamma, beta, H, W, groups, eps, do_silu,
                                                  mode, rtf32, wpc);
     else
-        gn_apply_kernel<1><<<grid, 256, 0, st>>>(out, x1, C1, x2, C2, stats, gamma, beta, H, W, groups, eps, do_silu,
+        gn_apply_kernel<1><<<grid, 256, 0, st>>>(out, raw_out, x1, C1, x2, C2, stats, gamma, beta, H, W, groups, eps, do_silu,
                                                  mode, rtf32, wpc);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
@@ -544,7 +555,8 @@ extern "C" int anoddpm_conv_head(float* out, const float* a, const float* w, con
     return ANODDPM_OK;
 }
 
-extern "C" int anoddpm_attention(float* out, const float* qkv, int B, int T, int C, int heads, void* stream) {
+extern "C" int anoddpm_attention(float* out, const float* qkv, int B, int T, int C, int heads, int rtf32,
+                                 void* stream) {
     ADP_REQUIRE(out && qkv && B > 0 && T > 0 && C > 0 && heads > 0 && C % heads == 0, "anoddpm_attention: bad arguments");
     ADP_REQUIRE(B <= 65535 && heads <= 65535, "anoddpm_attention: batch/heads too large");
     const int ch = C / heads;
@@ -556,7 +568,7 @@ extern "C" int anoddpm_attention(float* out, const float* qkv, int B, int T, int
         attr_set = true;
     }
     dim3 grid(adp_ceil_div(T, QB), heads, B);
-    attention_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(out, qkv, T, C, heads);
+    attention_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(out, qkv, T, C, heads, rtf32);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }

@@ -133,6 +133,16 @@ class UNetEngine:
             self._build()
             self._sig = sig
 
+    def _freq(self, dim, dev):
+        key = (dim, str(dev))
+        if getattr(self, "_freq_cache", None) is None:
+            self._freq_cache = {}
+        if key not in self._freq_cache:
+            import numpy as np
+            half = dim // 2     # same expression as the reference (UNet.py:52-54), evaluated on the host once
+            self._freq_cache[key] = torch.exp(torch.arange(half) * -(np.log(10000) / half)).float().to(dev)
+        return self._freq_cache[key]
+
     # ------------------------------------------------------------------ op wrappers
     def _gn_stats(self, site, srcs, B, HW):
         x1 = srcs[0]
@@ -141,17 +151,18 @@ class UNetEngine:
              B, HW, 32, stream())
         self.launches += 1
 
-    def _gn_apply(self, site, srcs, gn, B, H, W, silu, mode, rtf32):
+    def _gn_apply(self, site, srcs, gn, B, H, W, silu, mode, rtf32, want_raw=False):
         x1 = srcs[0]
         x2 = srcs[1] if len(srcs) > 1 else None
         C = x1.shape[-1] + (x2.shape[-1] if x2 is not None else 0)
         Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
         out = torch.empty((B, Ho, Wo, C), device=x1.device, dtype=torch.float32)
-        call("anoddpm_gn_apply", ptr(out), ptr(x1), x1.shape[-1], ptr(x2), x2.shape[-1] if x2 is not None else 0,
+        raw = torch.empty((B, H, W, C), device=x1.device, dtype=torch.float32) if want_raw else None
+        call("anoddpm_gn_apply", ptr(out), ptr(raw), ptr(x1), x1.shape[-1], ptr(x2), x2.shape[-1] if x2 is not None else 0,
              ptr(self.stats[site]), ptr(gn.weight), ptr(gn.bias), B, H, W, 32, float(gn.eps), int(silu), mode,
              int(rtf32), stream())
         self.launches += 1
-        return out
+        return (out, raw) if want_raw else out
 
     def _conv(self, site, a, B, H, W, cout, r=(), emb=None, res=None, res_mode=0):
         d = ConvDesc()
@@ -190,7 +201,14 @@ class UNetEngine:
         mode = _MODE[e["mode"]]
         Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
         self._gn_stats(e["s1"], srcs, B, H * W)
-        a1 = self._gn_apply(e["s1"], srcs, e["gn1"], B, H, W, True, mode, self._tc_ok(e["cin"], Ho, Wo))
+        tc1 = self._tc_ok(e["cin"], Ho, Wo)
+        # tensor-core path: the fused 1x1 skip conv reads a TF32-rounded, concatenated copy of x written by the same
+        # pass that normalises x (rounding to nearest instead of the MMA's operand truncation)
+        raw = None
+        if e["skip_conv"] and tc1 and self._tc_ok(e["cout"], Ho, Wo):
+            a1, raw = self._gn_apply(e["s1"], srcs, e["gn1"], B, H, W, True, mode, tc1, want_raw=True)
+        else:
+            a1 = self._gn_apply(e["s1"], srcs, e["gn1"], B, H, W, True, mode, tc1)
         emb = self.emb_all[:, e["emb_off"]:]
         h = self._conv(e["conv1"], a1, B, Ho, Wo, e["cout"], emb=emb)
         del a1
@@ -198,7 +216,7 @@ class UNetEngine:
         a2 = self._gn_apply(e["s2"], [h], e["gn2"], B, Ho, Wo, True, 0, self._tc_ok(e["cout"], Ho, Wo))
         del h
         if e["skip_conv"]:
-            return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], r=srcs), Ho, Wo
+            return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], r=([raw] if raw is not None else srcs)), Ho, Wo
         assert len(srcs) == 1
         return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], res=srcs[0], res_mode=_RES_FOR_MODE[e["mode"]]), Ho, Wo
 
@@ -209,7 +227,7 @@ class UNetEngine:
         qkv = self._conv(e["qkv"], xn, B, H, W, 3 * C)
         del xn
         a = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
-        call("anoddpm_attention", ptr(a), ptr(qkv), B, T, C, e["heads"], stream())
+        call("anoddpm_attention", ptr(a), ptr(qkv), B, T, C, e["heads"], int(self._tc_ok(C, H, W)), stream())
         self.launches += 1
         return self._conv(e["proj"], a, B, H, W, C, res=x, res_mode=1)
 
@@ -250,7 +268,7 @@ class UNetEngine:
 
         # timestep embedding MLP + all per-ResBlock projections in three small launches
         temb = torch.empty((B, base), device=dev, dtype=torch.float32)
-        call("anoddpm_timestep_embedding", ptr(temb), ptr(t), B, base, stream())
+        call("anoddpm_timestep_embedding", ptr(temb), ptr(t), ptr(self._freq(base, dev)), B, base, stream())
         l1, l2 = m.time_embedding[1], m.time_embedding[3]
         e1 = torch.empty((B, E), device=dev, dtype=torch.float32)
         call("anoddpm_linear", ptr(e1), E, ptr(temb), base, ptr(l1.weight), ptr(l1.bias), B, E, base, 0, stream())

@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- detection throughput of the AnoDDPM hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], per GPU): GaussianDiffusionModel.forward_backward on a synthetic
+(32,1,256,256) batch, T=1000 linear schedule, t_distance=800, simplex noise (6 octaves, 0.8, 64), UNet
+256/base 128/attn "16,8"/2 heads with random-init weights (reference zero-inits re-drawn).
+A STEP is one reverse-diffusion step of that chain -- `sample_p` = UNet forward + batched simplex noise +
+fused posterior kernel -- over the whole batch; the K timed steps are K consecutive iterations of a real
+chain (t = 799, 798, ...).  One image costs t_distance = 800 steps, so
+    images/s = n_gpus * B / (800 * seconds_per_step).
+N > 1: 32 images per GPU (weak scaling, configs[3] = 256 images over 8 GPUs), no data-path collective.
+`--full-chain` times whole 800-step chains instead (one chain = one step) to confirm the same number.
+
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+Working set per step (activations, GBs) is far larger than the 126 MB L2, so no explicit L2 flush.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+T_DISTANCE = 800
+UNET_KW = dict(img_size=256, base_channels=128, n_heads=2, attention_resolutions="16,8")
+GFLOP_PER_IMAGE_FWD = 554.5          # BASELINE.md section 3 (277.26 GMAC)
+METRIC = "detection images/sec (256x256, T=1000 partial reverse t_distance=800, simplex)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.rows = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_unet(device):
+    from anoddpm_b200 import UNetModel
+    from oracle.unet_oracle import fill_state_dict   # deterministic synthetic weights only (no oracle compute)
+    m = UNetModel(**UNET_KW).eval()
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed=1))
+    return m.to(device)
+
+
+# ------------------------------------------------------------------------------------------------ native arm
+def run_native(args):
+    from anoddpm_b200 import GaussianDiffusionModel, dist as D, get_beta_schedule
+    from anoddpm_b200.GaussianDiffusion import simplex_noise_from_seeds
+    rank, world, local = D.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the native arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = args.batch
+    model = build_unet(dev)
+    if args.conv_impl:
+        model.conv_impl = args.conv_impl
+    diff = GaussianDiffusionModel([256, 256], get_beta_schedule(1000, "linear"), noise="simplex")
+    lo = rank * B
+    gidx = range(lo, lo + B)
+    launches = {"n": 0}
+    step_counter = {"s": 0}
+
+    def noise_fn(x, t):   # batched simplex noise, per-image seeds by GLOBAL index (world-size invariant)
+        seeds = D.seeds_for_step(args.seed, step_counter["s"], gidx)
+        step_counter["s"] += 1
+        launches["n"] += 1
+        return simplex_noise_from_seeds(seeds, tuple(x.shape), t)
+
+    diff.noise_fn = noise_fn
+    g = torch.Generator().manual_seed(1000 + rank)
+    x_host = (torch.rand(B, 1, 256, 256, generator=g) * 2 - 1).pin_memory()
+    eng = model.engine()
+
+    @torch.no_grad()
+    def reverse_steps(x, t_hi, n):
+        for t in range(t_hi, t_hi - n, -1):
+            tb = torch.full((B,), t, device=dev, dtype=torch.int64)
+            x = diff.sample_p(model, x, tb, "noise_fn")["sample"]
+            launches["n"] += 1
+        return x
+
+    def chain(x_h, td):   # the public API call, host buffers in, host buffer out
+        y = diff.forward_backward(model, x_h.to(dev, non_blocking=True), None, td, "noise_fn")
+        return y.cpu()
+
+    clocks = ClockSampler(local)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.full_chain:
+        for _ in range(args.warmup):
+            chain(x_host, T_DISTANCE)
+        torch.cuda.synchronize(); D.barrier()
+        clocks.start(); l0, e0 = launches["n"], eng.launches
+        ev0.record()
+        for _ in range(args.steps):
+            chain(x_host, T_DISTANCE)
+        ev1.record(); torch.cuda.synchronize(); D.barrier()
+        ms = ev0.elapsed_time(ev1)
+        steps_per_image = 1.0
+    else:
+        t_start = torch.full((B,), T_DISTANCE - 1, device=dev, dtype=torch.int64)
+        x = diff.sample_q(x_host.to(dev), t_start, noise_fn(x_host.to(dev), t_start))
+        launches["n"] += 1
+        x = reverse_steps(x, T_DISTANCE - 1, args.warmup)
+        torch.cuda.synchronize(); D.barrier()
+        clocks.start(); l0, e0 = launches["n"], eng.launches
+        ev0.record()
+        x = reverse_steps(x, T_DISTANCE - 1 - args.warmup, args.steps)
+        ev1.record(); torch.cuda.synchronize(); D.barrier()
+        ms = ev0.elapsed_time(ev1)
+        steps_per_image = float(T_DISTANCE)
+    clk = clocks.stop()
+    n_launch = (launches["n"] - l0) + (eng.launches - e0)
+    ms = D.max_over_ranks(ms, dev)
+    ms_per_step = ms / args.steps
+    value = world * B / (steps_per_image * ms_per_step / 1e3)
+
+    # ---- end-to-end through the public API with host buffers (H2D of the batch + D2H of the result inside the timed region)
+    k_e2e = max(2, min(args.steps, 25))
+    chain(x_host, 2)
+    torch.cuda.synchronize(); D.barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    y = chain(x_host, k_e2e)
+    ev1.record(); torch.cuda.synchronize()
+    e2e_ms = D.max_over_ranks(ev0.elapsed_time(ev1), dev) / k_e2e
+    wall_ms = (time.perf_counter() - t0) * 1e3 / k_e2e
+    e2e_ms = max(e2e_ms, D.max_over_ranks(wall_ms, dev))     # .cpu() completes after the last event; take the slower clock
+    img_bytes = B * 256 * 256 * 4
+    e2e = {"value": world * B / (T_DISTANCE * e2e_ms / 1e3), "unit": "images/s",
+           "h2d_bytes_per_step": int(img_bytes / k_e2e + B * 1024), "d2h_bytes_per_step": int(img_bytes / k_e2e),
+           "api": f"GaussianDiffusionModel.forward_backward(unet, x_host->cuda, None, t_distance={k_e2e}, 'noise_fn').cpu(); "
+                  f"per-step time x 800 steps/image", "finite": bool(torch.isfinite(y).all())}
+
+    out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "tf32" if model.conv_impl == "tc" else "f32", "data": "synthetic",
+           "config": {"workload": "BASELINE configs[2] per GPU: forward_backward 256x256x1 bs=32 T=1000 t_distance=800 "
+                                  "simplex(6,0.8,64), UNet 256/base128/attn16,8/2 heads (554.5 GFLOP/image/step); "
+                                  + ("step = one full 800-step chain" if args.full_chain else
+                                     "step = one reverse step (sample_p: UNet fwd + simplex noise + fused posterior) of the chain; "
+                                     "images/s = n_gpus*B/(800*s_per_step)"),
+                      "global_batch": world * B, "per_gpu_batch": B, "t_distance": T_DISTANCE,
+                      "parallelism": f"dp{world} (images sharded by index, no collective in the loop)",
+                      "l2": "working set per step >> 126 MB L2 (no explicit flush)", "conv_impl": model.conv_impl},
+           "e2e": e2e, "gpu_launches": int(n_launch), "clocks": clk, "tc_convs_per_forward": eng.tc_convs}
+
+    if rank == 0:
+        out["roofline"] = roofline(model, dev, B)
+        out["cpu_baseline"] = cpu_baseline(sample_steps=2) if world == 1 and not args.no_cpu_baseline else None
+        print(json.dumps(out))
+    D.barrier()
+
+
+def roofline(model, dev, B):
+    """Dominant kernel = conv_tc_kernel (tcgen05 kind::tf32).  Live CUDA-event timing of the three conv shapes that
+    carry 61% of the UNet MACs, through the same C-ABI entry point the engine uses."""
+    import ctypes
+    from anoddpm_b200 import _lib
+    from anoddpm_b200.engine import round_tf32_
+    pk = peaks()
+    res = []
+    tot_flop, tot_ms = 0.0, 0.0
+    impl = 1 if model.conv_impl == "tc" else 0
+    for (Ci, Co, HW, count) in ((128, 128, 256, 9), (256, 128, 256, 3), (128, 128, 128, 9)):
+        a = round_tf32_(torch.randn(B, HW, HW, Ci, device=dev))
+        w = round_tf32_(torch.randn(Co, 9 * Ci, device=dev) * 0.03)
+        bias = torch.zeros(Co, device=dev)
+        out = torch.empty(B, HW, HW, Co, device=dev)
+        d = _lib.ConvDesc()
+        d.out, d.a, d.w, d.bias = out.data_ptr(), a.data_ptr(), w.data_ptr(), bias.data_ptr()
+        d.B, d.H, d.W, d.Ca, d.Cout, d.ksize, d.impl = B, HW, HW, Ci, Co, 3, impl
+        for _ in range(3):
+            _lib.call("anoddpm_conv", ctypes.byref(d), _lib.stream())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 10
+        e0.record()
+        for _ in range(n):
+            _lib.call("anoddpm_conv", ctypes.byref(d), _lib.stream())
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        flop = 2.0 * B * HW * HW * Co * 9 * Ci
+        res.append({"shape": f"conv3x3 {Ci}->{Co} @{HW}^2 bs{B}", "ms": ms, "tflops": flop / ms / 1e9, "count_per_forward": count})
+        tot_flop += flop * count
+        tot_ms += ms * count
+        del a, w, out
+    achieved = tot_flop / tot_ms / 1e9
+    return {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05.mma kind::tf32, TMA-fed implicit GEMM)" if impl else "conv_simt_kernel",
+            "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+            "peak_note": f"dense bf16 cuBLAS sustained, {pk['src']} (MEASURED_PEAKS.json); kind::tf32 issues at half the bf16 rate, "
+                         f"so frac of the tf32 rate = {achieved / (pk['bf16_sustained'] / 2):.3f}",
+            "traffic": None, "per_shape": res,
+            "algorithmic": "2*M*N*K flop per launch, M=B*H*W, N=Cout, K=9*Cin; weighted by launches per forward"}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_reverse_step_seconds(steps, threads):
+    """The oracle port of ONE reverse step at bs 1 (UNet fwd fp32 on torch CPU + C simplex + posterior), timed."""
+    from oracle import diffusion_oracle as DO, unet_oracle as UO
+    from oracle.simplex_oracle import OracleSimplex
+    from tests.util_unet import empty_state_dict
+    torch.set_num_threads(threads)
+    kw = dict(UNET_KW)
+    sd = UO.fill_state_dict(empty_state_dict(img_size=256, base_channels=128, attention_resolutions="16,8"), seed=1)
+    tab = DO.Tables(DO.beta_schedule(1000, "linear"))
+    x = torch.rand(1, 1, 256, 256, generator=torch.Generator().manual_seed(0)) * 2 - 1
+    times = []
+    with torch.no_grad():
+        for i in range(steps + 1):
+            t = torch.tensor([T_DISTANCE - 1 - i])
+            t0 = time.perf_counter()
+            eps = UO.forward(sd, x, t, **kw)
+            z = torch.from_numpy(OracleSimplex(1000 + i, threads=threads).rand_3d_fixed_T_octaves(
+                (256, 256), np.array([int(t)]), 6, 0.8, 64).astype(np.float32))[None]
+            x = DO.sample_p(tab, x, t, eps, z)["sample"]
+            if i > 0:                      # first iteration = warm-up
+                times.append(time.perf_counter() - t0)
+    return float(np.mean(times))
+
+
+def cpu_baseline(sample_steps=2):
+    threads = os.cpu_count() or 1
+    s = cpu_reverse_step_seconds(sample_steps, threads)
+    return {"value": 1.0 / (T_DISTANCE * s), "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": f"{sample_steps} reverse steps at bs 1 (256x256, same UNet) after 1 warm-up step, "
+                      f"{s:.3f} s/step, extrapolated x800 steps/image", "s_per_step": s}
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path.  The reference is Python and cannot
+    travel to the GPU box, so this times the oracle port (pinned bit-identical to it on CPU) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 3))
+    s = cpu_reverse_step_seconds(steps, threads)
+    v = 1.0 / (T_DISTANCE * s)
+    cb = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+          "sample": f"{steps} reverse steps at bs 1 after 1 warm-up, {s:.3f} s/step, x800 steps/image"}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
+                      "steps": steps, "warmup": 1, "ms_per_step": s * 1e3, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "same chain as the native arm, oracle port on host CPU, bs 1 sample", "t_distance": T_DISTANCE},
+                      "cpu_baseline": cb,
+                      "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU (BASELINE: 32)")
+    ap.add_argument("--seed", type=int, default=2024)
+    ap.add_argument("--full-chain", action="store_true", help="a step = one whole 800-step chain")
+    ap.add_argument("--conv-impl", default=None, choices=[None, "tc", "exact"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

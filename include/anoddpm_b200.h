@@ -76,8 +76,10 @@ int anoddpm_p_sample(float* sample, float* pred_x0, const float* x_t, const floa
 
 /* ------------------------------------------------------------------ UNet denoiser ops --------- */
 
-/* emb[b, :] = cat(sin(t_b*w), cos(t_b*w)), w_i = exp(-i*ln(1e4)/half).  UNet.py:38-57. */
-int anoddpm_timestep_embedding(float* emb /* B x dim */, const int64_t* t, int B, int dim, void* stream);
+/* emb[b, :] = cat(sin(t_b*w), cos(t_b*w)), w = freq[0..dim/2) = exp(-i*ln(1e4)/half) (built once by the caller
+ * exactly as UNet.py:50-55 builds it, so the argument t*w is bit-identical to the reference).  UNet.py:38-57. */
+int anoddpm_timestep_embedding(float* emb /* B x dim */, const int64_t* t, const float* freq /* dim/2 */, int B,
+                               int dim, void* stream);
 
 /* y[b, n] = sum_k act(x[b,k]) * w[n,k] + bias[n], act = SiLU if silu_in.  UNet.py:271-276, :185-188 (nn.Linear).
  * ldx / ldy: row strides of x / y (elements). */
@@ -92,10 +94,12 @@ int anoddpm_gn_stats(double* stats /* B x groups x 2 */, const float* x1, int C1
 
 /* out = resample(act(GroupNorm(x))) on NHWC: act = SiLU if silu; mode 0 same, 1 avg-pool 2x2, 2 nearest x2
  * (UNet.py:202-210: GN -> SiLU -> h_upd, in that order).  stats from anoddpm_gn_stats over n = HW*(C/groups).
- * round_tf32: round results to TF32 (rna) for the tensor-core conv that consumes them. */
-int anoddpm_gn_apply(float* out, const float* x1, int C1, const float* x2, int C2, const double* stats,
-                     const float* gamma, const float* beta, int B, int H, int W, int groups, float eps, int silu,
-                     int mode, int round_tf32, void* stream);
+ * round_tf32: round results to TF32 (rna) for the tensor-core conv that consumes them.
+ * raw_out (optional, mode 0 only): also writes the TF32-rounded, channel-concatenated copy of the INPUT, which the
+ * fused 1x1 skip convolution of the same ResBlock reads as its K-major operand (one pass over x for both). */
+int anoddpm_gn_apply(float* out, float* raw_out, const float* x1, int C1, const float* x2, int C2,
+                     const double* stats, const float* gamma, const float* beta, int B, int H, int W, int groups,
+                     float eps, int silu, int mode, int round_tf32, void* stream);
 
 /* Convolution as implicit GEMM over NHWC pixels.  out[b,y,x,:] =
  *     conv_k(a)[..] (k = ksize 3 pad 1, or 1)  +  r1 . W_r1  +  r2 . W_r2      (1x1 "skip" sources, optional)
@@ -134,7 +138,8 @@ int anoddpm_conv_head(float* out_nchw, const float* a_nhwc, const float* w_packe
 
 /* QKV attention on qkv[B][T][3*C] (channel layout [head][q|k|v][ch], UNet.py:146-147):
  * out[b][t][h*ch + c] = sum_s softmax_s( (q_t . k_s) / sqrt(ch) ) v_s[c].   UNet.py:137-153. */
-int anoddpm_attention(float* out /* B x T x C */, const float* qkv, int B, int T, int C, int heads, void* stream);
+int anoddpm_attention(float* out /* B x T x C */, const float* qkv, int B, int T, int C, int heads, int round_tf32,
+                      void* stream);
 
 #ifdef __cplusplus
 }

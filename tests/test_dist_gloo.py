@@ -1,0 +1,42 @@
+"""N>1 host logic on CPU: world_size-2 gloo processes shard 256 images, derive world-size-independent
+simplex seeds and reduce timings -- no data-path collective (detection is embarrassingly parallel)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+from tests.conftest import ROOT
+
+WORKER = textwrap.dedent("""
+    import json, os, sys
+    sys.path.insert(0, %r)
+    import torch
+    from anoddpm_b200 import dist as D
+    rank, world, local = D.init_from_env(backend="gloo")
+    lo, hi = D.shard_range(256, rank, world)
+    seeds = D.seeds_for_step(1234, 5, range(lo, hi))
+    mx = D.max_over_ranks(10.0 + rank, torch.device("cpu"))
+    sm = D.sum_over_ranks(hi - lo, torch.device("cpu"))
+    D.barrier()
+    print(json.dumps({"rank": rank, "lo": lo, "hi": hi, "seeds": seeds[:4], "max": mx, "sum": sm}))
+""") % ROOT
+
+
+def test_two_rank_sharding_and_reduction(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(WORKER)
+    port = 29500 + os.getpid() % 2000
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    rows = sorted((json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")), key=lambda r: r["rank"])
+    assert [(r["lo"], r["hi"]) for r in rows] == [(0, 128), (128, 256)]
+    assert all(r["max"] == 11.0 and r["sum"] == 256.0 for r in rows)
+    # seeds depend on the global image index only, not on the world size / owner
+    from anoddpm_b200.dist import seeds_for_step, shard_range
+    assert rows[1]["seeds"] == seeds_for_step(1234, 5, range(128, 132))
+    assert rows[0]["seeds"] == seeds_for_step(1234, 5, range(0, 4))
+    assert [shard_range(10, r, 3) for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
+    assert all(-10000000000 <= s < 10000000000 and s != 0 for s in seeds_for_step(7, 0, range(100)))
