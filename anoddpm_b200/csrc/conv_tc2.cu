@@ -1,0 +1,426 @@
+// anoddpm_b200/csrc/conv_tc2.cu -- persistent, CTA-pair tensor-core convolution for sm_100a (impl = 2).
+//
+// Same contract and operand layouts as conv_tc.cu (implicit GEMM, NHWC activations via 4-D TMA boxes at
+// tap-shifted coordinates, packed K-major weights, kind::tf32, fp32 accumulators in TMEM), restructured for
+// tensor-pipe utilisation:
+//   * a cluster of 2 CTAs (one per SM of a TPC) computes a 256-pixel x BN tile with
+//     tcgen05.mma.cta_group::2 (UMMA M = 256): each CTA stages its own 128 pixel rows of A and only HALF of
+//     the weight tile, so shared-memory operand bandwidth per SM drops from 128 to 96 (BN=128) / 64 (BN=256)
+//     bytes per clock -- the single-CTA M=128,N=128 shape is pinned at the 128 B/clk smem limit;
+//   * persistent: grid = min(#tiles, 74) clusters, static round-robin tile schedule, deep smem ring shared
+//     across tiles, so the TMA pipeline never drains between tiles;
+//   * two TMEM accumulator stages: the epilogue of tile i (TMEM -> registers -> +bias/+emb/+residual ->
+//     global) overlaps the MMAs of tile i+1.
+// Warp roles per CTA (256 threads): 0 = TMA producer, 1 = MMA issuer (leader CTA only), 2 = TMEM allocator,
+// 4..7 = epilogue.  Barrier protocol follows the canonical sm_100 2-CTA GEMM: `full` barriers live in the
+// leader CTA (both producers signal it), `empty` / `tmem_full` are multicast to both CTAs by tcgen05.commit,
+// `tmem_empty` lives in the leader and collects all 2 x 128 epilogue threads.
+#include "common.cuh"
+#include "anoddpm_b200.h"
+#include <cuda.h>
+
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 32;
+constexpr int kUmmaK = 8;
+constexpr int kThreads = 256;
+constexpr int kABytes = kBM * kBK * 4;
+constexpr int kAccStages = 2;
+constexpr int kMaxStages = 8;
+
+struct Tc2Args {
+    float* out;
+    const float* bias;
+    const float* emb;
+    const float* res;
+    int M, H, W, Cout;
+    int emb_stride, res_mode;
+    int nkb_a, chunks_a, ks;
+    int nkb_r1, nkb_r2;
+    int BN;            // pair-tile N (UMMA N); each CTA stages BN/2 weight rows
+    int tmem_cols;
+    int stages;
+    int n_tiles_n, n_tiles;   // tiles along N, total pair tiles
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// arrive (no tx) on the barrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// 2-CTA TMA loads: data lands in THIS CTA's smem, the transaction bytes are signalled on the LEADER's barrier
+// (peer bit of the barrier address cleared).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma2_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                             int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// commit all prior MMAs of this thread; arrive on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_r1,
+                const __grid_constant__ CUtensorMap map_r2, const __grid_constant__ CUtensorMap map_w,
+                const Tc2Args P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_bytes = (P.BN / 2) * kBK * 4;
+    const int S = P.stages;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + S * kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + S * b_bytes);
+    uint64_t* full = bars;                       // [S]   leader only
+    uint64_t* empty = bars + kMaxStages;         // [S]   both CTAs (multicast commit)
+    uint64_t* tmem_full = bars + 2 * kMaxStages; // [2]   both CTAs (multicast commit)
+    uint64_t* tmem_empty = tmem_full + kAccStages;  // [2] leader only, 2 x 128 arrivals
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int nkb = P.nkb_a + P.nkb_r1 + P.nkb_r2;
+
+    cluster_sync_all();   // both CTAs resident before the pair-wide TMEM allocation
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)P.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer (both CTAs; own A rows + own half of the weight tile) ----------------
+        if (elect_one()) {
+            const int pad = P.ks / 2;
+            int kbc = 0;
+            for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters) {
+                const int mp = tile / P.n_tiles_n, nt = tile - mp * P.n_tiles_n;
+                const int m0 = (mp * 2 + (int)rank) * kBM;
+                const int n0 = nt * P.BN + (int)rank * (P.BN / 2);
+                const int w0 = m0 % P.W, h0 = (m0 / P.W) % P.H, b0 = m0 / (P.W * P.H);
+                for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+                    const int s = kbc % S;
+                    mbar_wait(&empty[s], ((kbc / S) & 1) ^ 1);
+                    if (leader) mbar_expect_tx(&full[s], (uint32_t)(2 * (kABytes + b_bytes)));
+                    else mbar_arrive_remote(&full[s], 0);
+                    const CUtensorMap* am;
+                    int c0, dy = 0, dx = 0;
+                    if (kb < P.nkb_a) {
+                        const int tap = kb / P.chunks_a;
+                        c0 = (kb - tap * P.chunks_a) * kBK;
+                        dy = tap / P.ks - pad;
+                        dx = tap % P.ks - pad;
+                        am = &map_a;
+                    } else if (kb < P.nkb_a + P.nkb_r1) {
+                        c0 = (kb - P.nkb_a) * kBK;
+                        am = &map_r1;
+                    } else {
+                        c0 = (kb - P.nkb_a - P.nkb_r1) * kBK;
+                        am = &map_r2;
+                    }
+                    tma2_load_4d(sA + s * kABytes, am, &full[s], c0, w0 + dx, h0 + dy, b0);
+                    tma2_load_2d(sB + s * b_bytes, &map_w, &full[s], kb * kBK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer (leader CTA only) ----------------
+        if (leader) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.BN >> 3) << 17) |
+                                   ((uint32_t)(256 >> 4) << 24);
+            int kbc = 0, it = 0;
+            for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * P.BN);
+                for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+                    const int s = kbc % S;
+                    mbar_wait(&full[s], (kbc / S) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const uint64_t ad = make_sdesc(smem_u32(sA + s * kABytes));
+                        const uint64_t bd = make_sdesc(smem_u32(sB + s * b_bytes));
+#pragma unroll
+                        for (int k = 0; k < kBK / kUmmaK; ++k)
+                            umma2_tf32(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        umma2_commit(&empty[s]);
+                        if (kb == nkb - 1) umma2_commit(&tmem_full[acc]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue (both CTAs): TMEM -> registers -> global (NHWC) ----------------
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        int it = 0;
+        for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters, ++it) {
+            const int acc = it & 1;
+            const int mp = tile / P.n_tiles_n, nt = tile - mp * P.n_tiles_n;
+            const int m0 = (mp * 2 + (int)rank) * kBM;
+            const int n0 = nt * P.BN;
+            const int q = m0 + row;
+            const bool valid = q < P.M;
+            int w = 0, h = 0, b = 0;
+            if (valid) { w = q % P.W; h = (q / P.W) % P.H; b = q / (P.W * P.H); }
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int cb = 0; cb < P.BN; cb += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.BN + cb);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+                      "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+                      "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+                      "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cb + 32 >= P.BN) {
+                    // accumulator fully read: hand the TMEM stage back to the MMA issuer (leader's barrier)
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive_remote(&tmem_empty[acc], 0);
+                }
+                if (!valid) continue;
+                const int nb = n0 + cb;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = nb + j;
+                    if (n >= P.Cout) break;
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        v[e] = __uint_as_float(r[j + e]);
+                        if (P.bias) v[e] += P.bias[n + e];
+                        if (P.emb) v[e] += P.emb[(size_t)b * P.emb_stride + n + e];
+                    }
+                    if (P.res_mode == 1) {
+                        const float4 t = *reinterpret_cast<const float4*>(P.res + (size_t)q * P.Cout + n);
+                        v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                    } else if (P.res_mode == 2) {
+                        const int H2 = P.H * 2, W2 = P.W * 2;
+                        const float* rb = P.res + (((size_t)b * H2 + 2 * h) * W2 + 2 * w) * P.Cout + n;
+                        const float4 r0 = *reinterpret_cast<const float4*>(rb);
+                        const float4 r1 = *reinterpret_cast<const float4*>(rb + P.Cout);
+                        const float4 r2 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout);
+                        const float4 r3 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout + P.Cout);
+                        v[0] += (r0.x + r1.x + r2.x + r3.x) * 0.25f;
+                        v[1] += (r0.y + r1.y + r2.y + r3.y) * 0.25f;
+                        v[2] += (r0.z + r1.z + r2.z + r3.z) * 0.25f;
+                        v[3] += (r0.w + r1.w + r2.w + r3.w) * 0.25f;
+                    } else if (P.res_mode == 3) {
+                        const int Hh = P.H / 2, Wh = P.W / 2;
+                        const float4 t = *reinterpret_cast<const float4*>(
+                            P.res + (((size_t)b * Hh + (h >> 1)) * Wh + (w >> 1)) * P.Cout + n);
+                        v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                    }
+                    *reinterpret_cast<float4*>(P.out + (size_t)q * P.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();   // all MMAs committed + all remote barrier arrivals landed before either CTA tears down
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols)
+                     : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode2() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_act_map2(CUtensorMap* m, const float* p, int C, int W, int H, int B, int TW, int TH, int TB) {
+    EncodeTiledFn enc = get_encode2();
+    if (!enc) { anoddpm_set_error("cuTensorMapEncodeTiled entry point not available"); return ANODDPM_ERR_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        anoddpm_set_error("cuTensorMapEncodeTiled(act C=%d W=%d H=%d B=%d box %d,%d,%d) failed: %d", C, W, H, B, TW, TH,
+                          TB, (int)r);
+        return ANODDPM_ERR_CUDA;
+    }
+    return ANODDPM_OK;
+}
+
+int make_w_map2(CUtensorMap* m, const float* p, int Ktot, int Cout, int rows) {
+    EncodeTiledFn enc = get_encode2();
+    if (!enc) { anoddpm_set_error("cuTensorMapEncodeTiled entry point not available"); return ANODDPM_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        anoddpm_set_error("cuTensorMapEncodeTiled(weights K=%d Cout=%d rows=%d) failed: %d", Ktot, Cout, rows, (int)r);
+        return ANODDPM_ERR_CUDA;
+    }
+    return ANODDPM_OK;
+}
+
+}  // namespace
+
+extern "C" int anoddpm_conv_tc_supported(const anoddpm_conv_desc* d);
+
+int anoddpm_conv_tc2(const anoddpm_conv_desc* d, void* stream) {
+    ADP_REQUIRE(anoddpm_conv_tc_supported(d), "anoddpm_conv(impl=2): shape not covered by the tensor-core tiling "
+                "(Ca=%d Cr1=%d Cr2=%d Cout=%d H=%d W=%d); use impl=0", d->Ca, d->Cr1, d->Cr2, d->Cout, d->H, d->W);
+    Tc2Args P;
+    P.out = d->out; P.bias = d->bias; P.emb = d->emb; P.res = d->res;
+    P.M = d->B * d->H * d->W; P.H = d->H; P.W = d->W; P.Cout = d->Cout;
+    P.emb_stride = d->emb_stride; P.res_mode = d->res_mode;
+    const int TW = d->W < 128 ? d->W : 128;
+    int TH = 128 / TW; if (TH > d->H) TH = d->H;
+    const int TB = 128 / (TW * TH);
+    P.ks = d->ksize;
+    P.chunks_a = d->Ca / kBK;
+    P.nkb_a = d->ksize * d->ksize * P.chunks_a;
+    P.nkb_r1 = d->Cr1 / kBK;
+    P.nkb_r2 = d->Cr2 / kBK;
+    P.BN = (d->Cout % 256 == 0) ? 256 : (d->Cout < 128 ? d->Cout : 128);
+    const int acc_cols = kAccStages * P.BN;
+    P.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
+    const int Ktot = (P.nkb_a + P.nkb_r1 + P.nkb_r2) * kBK;
+    const int b_bytes = (P.BN / 2) * kBK * 4;
+    int stages = (196 * 1024) / (kABytes + b_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    P.stages = stages;
+    P.n_tiles_n = adp_ceil_div(d->Cout, P.BN);
+    const int m_pairs = adp_ceil_div(P.M, 2 * kBM);
+    P.n_tiles = m_pairs * P.n_tiles_n;
+
+    CUtensorMap ma, m1, m2, mw;
+    int rc;
+    if ((rc = make_act_map2(&ma, d->a, d->Ca, d->W, d->H, d->B, TW, TH, TB))) return rc;
+    m1 = ma; m2 = ma;
+    if (d->r1 && (rc = make_act_map2(&m1, d->r1, d->Cr1, d->W, d->H, d->B, TW, TH, TB))) return rc;
+    if (d->r2 && (rc = make_act_map2(&m2, d->r2, d->Cr2, d->W, d->H, d->B, TW, TH, TB))) return rc;
+    if ((rc = make_w_map2(&mw, d->w, Ktot, d->Cout, P.BN / 2))) return rc;
+
+    const size_t smem = (size_t)stages * (kABytes + b_bytes) + (2 * kMaxStages + 2 * kAccStages) * 8 + 16 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    int sms = 148;
+    int n_clusters = P.n_tiles < sms / 2 ? P.n_tiles : sms / 2;
+    conv_tc2_kernel<<<dim3(2 * n_clusters), kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, P);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}

@@ -102,15 +102,36 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(double* __restrict__ stat
 }
 
 // ---------------------------------------------------------------- GroupNorm apply (+SiLU, +resample)
-// grid (chunks, B).  Output NHWC (B, Ho, Wo, C).  mode 0 same, 1 avg-pool 2x2 (of activated values), 2 nearest x2.
+// grid (pixel chunks, B).  Output NHWC (B, Ho, Wo, C).  mode 0 same, 1 avg-pool 2x2 (of activated values),
+// 2 nearest x2.  Like gn_stats, a thread owns a fixed channel vector (scale/shift computed once, no per-element
+// integer division) and walks output pixels; 4 pixels are in flight per thread for memory-level parallelism.
 template <int V>
+__device__ __forceinline__ void gn_load(float (&v)[V], const float* p) {
+    if (V == 4) {
+        const F4 t = ld4(p);
+        v[0] = t.x; v[1 % V] = t.y; v[2 % V] = t.z; v[3 % V] = t.w;
+    } else {
+        v[0] = p[0];
+    }
+}
+template <int V>
+__device__ __forceinline__ void gn_store(float* p, const float (&v)[V]) {
+    if (V == 4) {
+        F4 o; o.x = v[0]; o.y = v[1 % V]; o.z = v[2 % V]; o.w = v[3 % V];
+        st4(p, o);
+    } else {
+        p[0] = v[0];
+    }
+}
+
+template <int V, int NT>   // NT = taps per output pixel: 4 for the avg-pool mode, else 1
 __global__ void __launch_bounds__(256) gn_apply_kernel(float* __restrict__ out, float* __restrict__ raw_out,
                                                        const float* __restrict__ x1, int C1,
                                                        const float* __restrict__ x2, int C2,
                                                        const double* __restrict__ stats,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int H, int W, int groups, float eps, int do_silu, int mode,
-                                                       int rtf32, long long work_per_cta) {
+                                                       int rtf32, int pix_per_cta) {
     __shared__ float s_mean[64], s_rstd[64];
     const int b = blockIdx.y, C = C1 + C2, gs = C / groups, ncv = C / V;
     if (threadIdx.x < groups) {
@@ -125,67 +146,84 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(float* __restrict__ out, 
     __syncthreads();
     const int Ho = mode == 1 ? H / 2 : (mode == 2 ? H * 2 : H);
     const int Wo = mode == 1 ? W / 2 : (mode == 2 ? W * 2 : W);
-    const long long total = (long long)Ho * Wo * ncv;
-    const long long i0 = blockIdx.x * work_per_cta;
-    const long long i1 = min(total, i0 + work_per_cta);
-    for (long long i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-        const int cv = (int)(i % ncv);
-        const long long po = i / ncv;
-        const int wo = (int)(po % Wo), ho = (int)(po / Wo);
+    const int npo = Ho * Wo;
+    const int p0 = blockIdx.x * pix_per_cta;
+    const int p1 = min(npo, p0 + pix_per_cta);
+    int tpr, rows;
+    if (ncv >= 256) { tpr = 256; rows = 1; }
+    else { tpr = ncv; rows = 256 / ncv; }
+    const int r = threadIdx.x / tpr, lane = threadIdx.x - r * tpr;
+    if (r >= rows) return;
+    for (int cv = lane; cv < ncv; cv += tpr) {
         const int c = cv * V;
         const float* src;
         int cs, cc;
         if (c < C1) { src = x1; cs = C1; cc = c; }
         else { src = x2; cs = C2; cc = c - C1; }
         src += (size_t)b * H * W * cs + cc;
-        float sc[V], bi[V], acc[V];
+        float sc[V], bi[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             const int g = (c + j) / gs;
             sc[j] = s_rstd[g] * gamma[c + j];
             bi[j] = beta[c + j] - sc[j] * s_mean[g];
-            acc[j] = 0.f;
         }
-        const int taps = mode == 1 ? 4 : 1;
-        for (int tp = 0; tp < taps; ++tp) {
-            int hi, wi;
-            if (mode == 1) { hi = 2 * ho + (tp >> 1); wi = 2 * wo + (tp & 1); }
-            else if (mode == 2) { hi = ho >> 1; wi = wo >> 1; }
-            else { hi = ho; wi = wo; }
-            float v[V];
-            if (V == 4) {
-                const F4 t = ld4(src + ((size_t)hi * W + wi) * cs);
-                v[0] = t.x; v[1 % V] = t.y; v[2 % V] = t.z; v[3 % V] = t.w;
-            } else {
-                v[0] = src[((size_t)hi * W + wi) * cs];
-            }
+        float* dst = out + (size_t)b * npo * C + c;
+        float* rdst = raw_out ? raw_out + (size_t)b * npo * C + c : nullptr;
+        constexpr int U = NT == 4 ? 1 : 4;
+        for (int pb = p0 + r; pb < p1; pb += rows * U) {
+            float v[U][NT][V];   // [pixel in flight][tap][channel]
+            constexpr int ntap = NT;
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                float y = v[j] * sc[j] + bi[j];
-                if (do_silu) y = silu(y);
-                acc[j] += y;
-            }
-            if (raw_out) {  // mode 0 only: TF32-rounded concatenated copy of the input for the fused skip conv
-                float* rd = raw_out + (((size_t)b * H + hi) * W + wi) * C + c;
-                if (V == 4) {
-                    F4 o; o.x = round_tf32(v[0]); o.y = round_tf32(v[1 % V]); o.z = round_tf32(v[2 % V]); o.w = round_tf32(v[3 % V]);
-                    st4(rd, o);
-                } else {
-                    rd[0] = round_tf32(v[0]);
+            for (int u = 0; u < U; ++u) {
+                const int po = pb + u * rows;
+                if (po < p1) {
+                    if (mode == 0) {
+                        gn_load<V>(v[u][0], src + (size_t)po * cs);
+                    } else {
+                        const int ho = po / Wo, wo = po - ho * Wo;
+                        if (NT == 1) {
+                            gn_load<V>(v[u][0], src + ((size_t)(ho >> 1) * W + (wo >> 1)) * cs);
+                        } else {
+                            const float* q = src + ((size_t)(2 * ho) * W + 2 * wo) * cs;
+                            gn_load<V>(v[u][0], q);
+                            gn_load<V>(v[u][1 % NT], q + cs);
+                            gn_load<V>(v[u][2 % NT], q + (size_t)W * cs);
+                            gn_load<V>(v[u][3 % NT], q + (size_t)W * cs + cs);
+                        }
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            if (mode == 1) acc[j] *= 0.25f;
-            if (rtf32) acc[j] = round_tf32(acc[j]);
-        }
-        float* dst = out + (((size_t)b * Ho + ho) * Wo + wo) * C + c;
-        if (V == 4) {
-            F4 o; o.x = acc[0]; o.y = acc[1 % V]; o.z = acc[2 % V]; o.w = acc[3 % V];
-            st4(dst, o);
-        } else {
-            dst[0] = acc[0];
+            for (int u = 0; u < U; ++u) {
+                const int po = pb + u * rows;
+                if (po < p1) {
+                    float acc[V];
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+#pragma unroll
+                    for (int tp = 0; tp < ntap; ++tp) {
+#pragma unroll
+                        for (int j = 0; j < V; ++j) {
+                            float y = v[u][tp][j] * sc[j] + bi[j];
+                            if (do_silu) y = silu(y);
+                            acc[j] += y;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        if (mode == 1) acc[j] *= 0.25f;
+                        if (rtf32) acc[j] = round_tf32(acc[j]);
+                    }
+                    gn_store<V>(dst + (size_t)po * C, acc);
+                    if (rdst) {   // mode 0 only: TF32-rounded concatenated copy of the input for the fused skip conv
+                        float rv[V];
+#pragma unroll
+                        for (int j = 0; j < V; ++j) rv[j] = round_tf32(v[u][0][j]);
+                        gn_store<V>(rdst + (size_t)po * C, rv);
+                    }
+                }
+            }
         }
     }
 }
@@ -296,60 +334,97 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs A) {
 }
 
 // ---------------------------------------------------------------- stem: NCHW image -> NHWC features
+// thread = (pixel, 4 output channels): the 9*Cin inputs are warp-broadcast loads, weights sit in shared memory
+// as [tap*Cin][Cout] (conflict-free float4 reads), one coalesced float4 store per thread.  HBM-bound on the store.
 __global__ void __launch_bounds__(256) conv_stem_kernel(float* __restrict__ out, const float* __restrict__ x,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         int B, int Cin, int H, int W, int Cout) {
-    extern __shared__ float sw[];  // [Cout][Cin*9] + bias
-    const int nw = Cout * Cin * 9;
-    for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
-    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[nw + i] = bias ? bias[i] : 0.f;
+    extern __shared__ float sw[];  // [Cin*9][Cout] then bias[Cout]
+    const int K = Cin * 9;
+    for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+        const int co = i / K, k = i - co * K;      // OIHW: w[co][ci][ky][kx], k = ci*9 + ky*3 + kx
+        sw[k * Cout + co] = w[i];
+    }
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[K * Cout + i] = bias ? bias[i] : 0.f;
     __syncthreads();
-    const long long total = (long long)B * H * W * Cout;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int co = (int)(i % Cout);
-        const long long p = i / Cout;
-        const int xw = (int)(p % W), yh = (int)((p / W) % H), b = (int)(p / ((long long)W * H));
-        float acc = 0.f;  // OIHW order: ci, ky, kx (matches a direct convolution loop nest)
-        for (int ci = 0; ci < Cin; ++ci)
+    const int nc4 = Cout >> 2;
+    const int ppb = blockDim.x / nc4;              // pixels per block iteration
+    const int pl = threadIdx.x / nc4, c4 = (threadIdx.x - pl * nc4) * 4;
+    if (pl >= ppb) return;
+    const int npix = B * H * W;
+    for (int p = blockIdx.x * ppb + pl; p < npix; p += gridDim.x * ppb) {
+        const int xw = p % W, yh = (p / W) % H, b = p / (W * H);
+        float a0 = sw[K * Cout + c4], a1 = sw[K * Cout + c4 + 1], a2 = sw[K * Cout + c4 + 2], a3 = sw[K * Cout + c4 + 3];
+        // bias first, then (ci, ky, kx) accumulation
+        for (int ci = 0; ci < Cin; ++ci) {
+            const float* xp = x + ((size_t)b * Cin + ci) * H * W;
+#pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
                 const int yy = yh + ky - 1;
                 if (yy < 0 || yy >= H) continue;
+#pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
                     const int xx = xw + kx - 1;
                     if (xx < 0 || xx >= W) continue;
-                    acc = fmaf(x[(((size_t)b * Cin + ci) * H + yy) * W + xx], sw[(co * Cin + ci) * 9 + ky * 3 + kx], acc);
+                    const float v = xp[(size_t)yy * W + xx];
+                    const F4 wv = ld4(&sw[(ci * 9 + ky * 3 + kx) * Cout + c4]);
+                    a0 = fmaf(v, wv.x, a0); a1 = fmaf(v, wv.y, a1); a2 = fmaf(v, wv.z, a2); a3 = fmaf(v, wv.w, a3);
                 }
             }
-        out[i] = acc + sw[nw + co];
+        }
+        F4 o; o.x = a0; o.y = a1; o.z = a2; o.w = a3;
+        st4(out + (size_t)p * Cout + c4, o);
     }
 }
 
 // ---------------------------------------------------------------- head: NHWC features -> NCHW image
-// one warp per output pixel, lanes over input channels (coalesced), all Cout (<= 4) at once.
+// CTA = 8x32 output pixels; per 32-channel chunk the (10 x 34)-pixel halo tile is staged in shared memory
+// ([pixel][33] padding: conflict-free for pixel-consecutive lanes), weights of the chunk as [co][tap][32].
+// Each thread owns one output pixel (all Cout <= 4 channels).  Reads the input exactly once from HBM.
+constexpr int HT_H = 8, HT_W = 32, HT_C = 16;
 __global__ void __launch_bounds__(256) conv_head_kernel(float* __restrict__ out, const float* __restrict__ a,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
                                                         int B, int Cin, int H, int W, int Cout) {
-    const int lane = threadIdx.x & 31;
-    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    const long long npix = (long long)B * H * W;
-    if (warp >= npix) return;
-    const int xw = (int)(warp % W), yh = (int)((warp / W) % H), b = (int)(warp / ((long long)W * H));
+    __shared__ float st[(HT_H + 2) * (HT_W + 2) * (HT_C + 1)];
+    __shared__ float swt[4 * 9 * HT_C];
+    const int tiles_x = (W + HT_W - 1) / HT_W, tiles_y = (H + HT_H - 1) / HT_H;
+    const int tile = blockIdx.x;
+    const int b = tile / (tiles_x * tiles_y), tr = tile - b * tiles_x * tiles_y;
+    const int y0 = (tr / tiles_x) * HT_H, x0 = (tr % tiles_x) * HT_W;
+    const int py = threadIdx.x / HT_W, px = threadIdx.x % HT_W;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int tap = 0; tap < 9; ++tap) {
-        const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-        const float* row = a + (((size_t)b * H + yy) * W + xx) * Cin;
-        for (int c = lane; c < Cin; c += 32) {
-            const float v = row[c];
-            for (int co = 0; co < Cout; ++co) acc[co] = fmaf(v, w[(size_t)co * 9 * Cin + tap * Cin + c], acc[co]);
+    for (int c0 = 0; c0 < Cin; c0 += HT_C) {
+        __syncthreads();
+        // stage halo tile: 340 pixels x HT_C channels, HT_C/4 lanes (float4) per pixel
+        for (int i = threadIdx.x; i < (HT_H + 2) * (HT_W + 2) * (HT_C / 4); i += blockDim.x) {
+            const int pix = i / (HT_C / 4), q = (i % (HT_C / 4)) * 4;
+            const int ly = pix / (HT_W + 2), lx = pix - ly * (HT_W + 2);
+            const int gy = y0 + ly - 1, gx = x0 + lx - 1;
+            F4 v = {0.f, 0.f, 0.f, 0.f};
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W && c0 + q < Cin)
+                v = ld4(a + (((size_t)b * H + gy) * W + gx) * Cin + c0 + q);
+            float* d = &st[pix * (HT_C + 1) + q];
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        for (int i = threadIdx.x; i < Cout * 9 * HT_C; i += blockDim.x) {
+            const int co = i / (9 * HT_C), r = i - co * 9 * HT_C, tap = r / HT_C, c = r - tap * HT_C;
+            swt[i] = (c0 + c < Cin) ? w[(size_t)co * 9 * Cin + tap * Cin + c0 + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const float* sp = &st[((py + tap / 3) * (HT_W + 2) + px + tap % 3) * (HT_C + 1)];
+#pragma unroll 8
+            for (int c = 0; c < HT_C; ++c) {
+                const float v = sp[c];
+                for (int co = 0; co < Cout; ++co) acc[co] = fmaf(v, swt[(co * 9 + tap) * HT_C + c], acc[co]);
+            }
         }
     }
-    for (int co = 0; co < Cout; ++co) {
-        float s = acc[co];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) out[(((size_t)b * Cout + co) * H + yh) * W + xw] = s + (bias ? bias[co] : 0.f);
-    }
+    const int gy = y0 + py, gx = x0 + px;
+    if (gy < H && gx < W)
+        for (int co = 0; co < Cout; ++co)
+            out[(((size_t)b * Cout + co) * H + gy) * W + gx] = acc[co] + (bias ? bias[co] : 0.f);
 }
 
 // ---------------------------------------------------------------- attention (UNet.py:137-153)
@@ -432,7 +507,8 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 
 }  // namespace
 
-int anoddpm_conv_tc(const anoddpm_conv_desc* d, void* stream);  // conv_tc.cu
+int anoddpm_conv_tc(const anoddpm_conv_desc* d, void* stream);   // conv_tc.cu  (impl 1)
+int anoddpm_conv_tc2(const anoddpm_conv_desc* d, void* stream);  // conv_tc2.cu (impl 2)
 
 extern "C" int anoddpm_timestep_embedding(float* emb, const int64_t* t, const float* freq, int B, int dim,
                                           void* stream) {
@@ -490,17 +566,17 @@ extern "C" int anoddpm_gn_apply(float* out, float* raw_out, const float* x1, int
     ADP_REQUIRE(raw_out == nullptr || mode == 0, "anoddpm_gn_apply: raw_out needs mode 0");
     const int V = (gn_vec(C1, C2, groups, x1, x2) == 4 && al16(out) && (!raw_out || al16(raw_out))) ? 4 : 1;
     const int Ho = mode == 1 ? H / 2 : (mode == 2 ? H * 2 : H), Wo = mode == 1 ? W / 2 : (mode == 2 ? W * 2 : W);
-    const long long total = (long long)Ho * Wo * (C / V);
-    long long wpc = 256 * 16;
-    while (wpc > 256 && (total + wpc - 1) / wpc * B < 148 * 4) wpc >>= 1;
-    dim3 grid((unsigned)((total + wpc - 1) / wpc), B);
+    const int npo = Ho * Wo;
+    int wpc = 1024;  // output pixels per CTA
+    while (wpc > 32 && (long long)adp_ceil_div(npo, wpc) * B < 148 * 4) wpc >>= 1;
+    dim3 grid((unsigned)adp_ceil_div(npo, wpc), B);
     cudaStream_t st = (cudaStream_t)stream;
-    if (V == 4)
-        gn_apply_kernel<4><<<grid, 256, 0, st>>>(out, raw_out, x1, C1, x2, C2, stats, gamma, beta, H, W, groups, eps, do_silu,
-                                                 mode, rtf32, wpc);
-    else
-        gn_apply_kernel<1><<<grid, 256, 0, st>>>(out, raw_out, x1, C1, x2, C2, stats, gamma, beta, H, W, groups, eps, do_silu,
-                                                 mode, rtf32, wpc);
+#define ADP_GN_APPLY(VV, NN)                                                                                       \
+    gn_apply_kernel<VV, NN><<<grid, 256, 0, st>>>(out, raw_out, x1, C1, x2, C2, stats, gamma, beta, H, W, groups, eps, \
+                                                  do_silu, mode, rtf32, wpc)
+    if (V == 4) { if (mode == 1) ADP_GN_APPLY(4, 4); else ADP_GN_APPLY(4, 1); }
+    else { if (mode == 1) ADP_GN_APPLY(1, 4); else ADP_GN_APPLY(1, 1); }
+#undef ADP_GN_APPLY
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }
@@ -521,6 +597,7 @@ extern "C" int anoddpm_conv(const anoddpm_conv_desc* d, void* stream) {
                     (!d->res || al16(d->res)),
                 "anoddpm_conv: pointers must be 16-byte aligned");
     if (d->impl == 1) return anoddpm_conv_tc(d, stream);
+    if (d->impl == 2) return anoddpm_conv_tc2(d, stream);
     ADP_REQUIRE(d->impl == 0, "anoddpm_conv: unknown impl %d", d->impl);
     ConvArgs A;
     A.d = *d;
@@ -535,11 +612,13 @@ extern "C" int anoddpm_conv(const anoddpm_conv_desc* d, void* stream) {
 extern "C" int anoddpm_conv_stem(float* out, const float* x, const float* w, const float* bias, int B, int Cin, int H,
                                  int W, int Cout, void* stream) {
     ADP_REQUIRE(out && x && w && B > 0 && Cin > 0 && H > 0 && W > 0 && Cout > 0, "anoddpm_conv_stem: bad arguments");
+    ADP_REQUIRE(Cout % 4 == 0 && Cout <= 1024 && al16(out), "anoddpm_conv_stem: Cout must be a multiple of 4 (<= 1024)");
+    ADP_REQUIRE((long long)B * H * W < (1LL << 31), "anoddpm_conv_stem: too many pixels");
     const size_t smem = ((size_t)Cout * Cin * 9 + Cout) * sizeof(float);
     ADP_REQUIRE(smem <= 48 * 1024, "anoddpm_conv_stem: weights (%zu B) exceed shared memory", smem);
-    const long long total = (long long)B * H * W * Cout;
-    int blocks = adp_ceil_div(total, 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    const int ppb = 256 / (Cout / 4) > 0 ? 256 / (Cout / 4) : 1;
+    int blocks = adp_ceil_div((long long)B * H * W, ppb);
+    if (blocks > 148 * 32) blocks = 148 * 32;
     conv_stem_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(out, x, w, bias, B, Cin, H, W, Cout);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
@@ -549,8 +628,10 @@ extern "C" int anoddpm_conv_head(float* out, const float* a, const float* w, con
                                  int W, int Cout, void* stream) {
     ADP_REQUIRE(out && a && w && B > 0 && Cin > 0 && H > 0 && W > 0, "anoddpm_conv_head: bad arguments");
     ADP_REQUIRE(Cout >= 1 && Cout <= 4, "anoddpm_conv_head: Cout must be 1..4 (got %d)", Cout);
-    const long long npix = (long long)B * H * W;
-    conv_head_kernel<<<adp_ceil_div(npix * 32, 256), 256, 0, (cudaStream_t)stream>>>(out, a, w, bias, B, Cin, H, W, Cout);
+    ADP_REQUIRE(Cin % 4 == 0 && al16(a), "anoddpm_conv_head: Cin must be a multiple of 4");
+    const long long tiles = (long long)B * adp_ceil_div(H, HT_H) * adp_ceil_div(W, HT_W);
+    ADP_REQUIRE(tiles < (1LL << 31), "anoddpm_conv_head: too many tiles");
+    conv_head_kernel<<<(unsigned)tiles, 256, 0, (cudaStream_t)stream>>>(out, a, w, bias, B, Cin, H, W, Cout);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }

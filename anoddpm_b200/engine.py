@@ -51,7 +51,7 @@ class _Conv:
         if impl not in self.cache:
             parts = [pack_conv_weight(w.detach()) for w in self.weights]
             w = torch.cat(parts, dim=1).contiguous().float()
-            if impl == 1:
+            if impl >= 1:
                 round_tf32_(w)
             b = self.biases[0].detach().float()
             for extra in self.biases[1:]:
@@ -170,7 +170,7 @@ class UNetEngine:
         d.Ca, d.Cout, d.ksize = a.shape[-1], cout, site.ksize
         d.Cr1 = r[0].shape[-1] if len(r) > 0 else 0
         d.Cr2 = r[1].shape[-1] if len(r) > 1 else 0
-        impl = 1 if (self.use_tc and _lib.lib().anoddpm_conv_tc_supported(ctypes.byref(d))) else 0
+        impl = self.tc_impl if (self.use_tc and _lib.lib().anoddpm_conv_tc_supported(ctypes.byref(d))) else 0
         w, b = site.packed(impl)
         out = torch.empty((B, H, W, cout), device=a.device, dtype=torch.float32)
         d.out, d.a, d.w, d.bias = out.data_ptr(), a.data_ptr(), w.data_ptr(), b.data_ptr()
@@ -185,7 +185,7 @@ class UNetEngine:
         d.impl = impl
         call("anoddpm_conv", ctypes.byref(d), stream())
         self.launches += 1
-        self.tc_convs += impl
+        self.tc_convs += 1 if impl else 0
         return out
 
     def _tc_ok(self, C, H, W):
@@ -253,7 +253,10 @@ class UNetEngine:
         if p0.device != x.device:
             raise RuntimeError(f"UNetModel parameters are on {p0.device} but the input is on {x.device}")
         self._refresh()
-        self.use_tc = (m.conv_impl == "tc")
+        if m.conv_impl not in ("tc", "tc1", "exact"):
+            raise ValueError(f"conv_impl must be 'tc', 'tc1' or 'exact', got {m.conv_impl!r}")
+        self.use_tc = m.conv_impl in ("tc", "tc1")
+        self.tc_impl = 2 if m.conv_impl == "tc" else 1   # tc: persistent CTA-pair kernel; tc1: single-CTA tiles
         self.tc_convs = 0
         in_dtype = x.dtype
         x = x.contiguous().float()

@@ -108,7 +108,8 @@ int anoddpm_gn_apply(float* out, float* raw_out, const float* x1, int C1, const 
  * Replaces nn.Conv2d 3x3/1x1 + skip_connection + the adds of ResBlock.forward (UNet.py:202-217) and the
  * Conv1d 1x1 qkv/proj of AttentionBlock (UNet.py:115-125).
  * res_mode: 0 none, 1 same resolution, 2 res is 2H x 2W and is avg-pooled 2x2, 3 res is H/2 x W/2 nearest-upsampled
- * (x_upd of UNet.py:206-207).  impl: 0 = exact fp32 CUDA-core kernel, 1 = tcgen05 kind::tf32 tensor-core kernel. */
+ * (x_upd of UNet.py:206-207).  impl: 0 = exact fp32 CUDA-core kernel; 1 = tcgen05 kind::tf32, one CTA per 128x128 tile;
+ * 2 = tcgen05 kind::tf32 cta_group::2, persistent CTA pairs (256 x BN tiles, double-buffered TMEM) -- the fast path. */
 typedef struct anoddpm_conv_desc {
     float* out;
     const float* a;
@@ -126,7 +127,7 @@ typedef struct anoddpm_conv_desc {
     int impl;
 } anoddpm_conv_desc;
 int anoddpm_conv(const anoddpm_conv_desc* d /* [host] */, void* stream);
-/* 1 if impl=1 (tcgen05 tiles: channels % 32, Cout % 16, power-of-two W) covers the problem, else 0. */
+/* 1 if impl=1/2 (tcgen05 tiles: channels % 32, Cout % 16, power-of-two W) covers the problem, else 0. */
 int anoddpm_conv_tc_supported(const anoddpm_conv_desc* d /* [host] */);
 
 /* Stem: NCHW image (Cin small) -> NHWC features, 3x3 pad 1, w is OIHW.  UNet.py:279-281. */
