@@ -1,0 +1,487 @@
+// anoddpm_b200/csrc/conv_tc3.cu -- halo-reuse tensor-core 3x3 convolution for sm_100a (impl = 3).
+//
+// conv_tc2 is L2-bandwidth bound: every filter tap re-reads its own 128-pixel A tile and every tile re-reads the
+// weights, ~96 B/clk/SM against a measured L2->SM ceiling of ~40-48 B/clk/SM (ncu: profiles/).  This kernel cuts the
+// operand traffic per MMA cycle to ~39 B/clk/SM:
+//   * spatial tiling: an M-subtile is 16 rows x 8 pixels of one image.  For each 32-channel chunk and each
+//     horizontal tap dx, ONE TMA box (32 ch, 8 px, 18 rows) is loaded; the three vertical taps dy are UMMA
+//     descriptors into the same box advanced by dy*8 rows (= dy*1024 B, swizzle-atom aligned) -> A traffic / 3;
+//   * each CTA owns TWO subtiles (a 16x16 region) that share every weight tile -> B traffic / 2 per flop;
+//   * CTA pairs (tcgen05.mma.cta_group::2, UMMA M = 256) split the weight tile in halves, persistent clusters,
+//     3-stage smem ring (60 KB/stage), 2 TMEM accumulator stages x 2 subtiles x BN columns (512 columns).
+// 1x1 "skip" sources (raw ResBlock input, centre tap only) are extra stages with a (32, 8, 16) box.
+// Epilogue: as conv_tc2 (bias + timestep embedding + residual), plus optional GroupNorm statistics of the OUTPUT
+// (sum, sum of squares per (sample, group), fp32 per warp -> fp64 atomics) so the next GroupNorm needs no stats pass.
+// Contract: ksize == 3, H % 16 == 0, W % 16 == 0, channels % 32 == 0, Cout % 16 == 0 (anoddpm_conv_tc3_supported).
+#include "common.cuh"
+#include "anoddpm_b200.h"
+#include <cuda.h>
+
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 32;
+constexpr int kUmmaK = 8;
+constexpr int kThreads = 256;
+constexpr int kSubRows = 18;                        // 16 output rows + 1 halo row above and below
+constexpr int kSubBytes = kSubRows * 8 * kBK * 4;   // one (32 ch, 8 px, 18 rows) box = 18432 B
+constexpr int kABytes = 2 * kSubBytes;              // two subtiles per CTA
+constexpr int kAccStages = 2;
+constexpr int kMaxStages = 4;
+
+struct Tc3Args {
+    float* out;
+    const float* bias;
+    const float* emb;
+    const float* res;
+    int M, H, W, Cout;
+    int emb_stride, res_mode;
+    int Ca, chunks_a;          // main 3x3 source: channels, 32-channel chunks
+    int chunks_r1, chunks_r2;  // 1x1 skip sources
+    int BN;                    // pair-tile N (UMMA N); each CTA stages BN/2 weight rows per tap
+    int tmem_cols;
+    int stages;
+    int n_tiles_n, n_tiles;    // tiles along N, total pair tiles
+    int regions_x, regions_per_img, n_regions;   // 16x16 regions
+    double* gn_stats;          // optional [B][32][2] accumulation of the output's GroupNorm statistics
+    int gn_gs;                 // channels per group (Cout / 32)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// arrive (no tx) on the barrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// 2-CTA TMA loads: data lands in THIS CTA's smem, the transaction bytes are signalled on the LEADER's barrier
+// (peer bit of the barrier address cleared).
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma2_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                             int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// commit all prior MMAs of this thread; arrive on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_r1,
+                const __grid_constant__ CUtensorMap map_r2, const __grid_constant__ CUtensorMap map_w,
+                const Tc3Args P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int b_bytes = (P.BN / 2) * kBK * 4;      // one weight tile (this CTA's half of the N rows)
+    const int S = P.stages;
+    uint8_t* sA = smem;                            // [S][2 subtiles][kSubBytes]
+    uint8_t* sB = smem + S * kABytes;              // [S][3 taps][b_bytes]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + S * 3 * b_bytes);
+    uint64_t* full = bars;                         // [S]   leader only
+    uint64_t* empty = bars + kMaxStages;           // [S]   both CTAs (multicast commit)
+    uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]   both CTAs (multicast commit)
+    uint64_t* tmem_empty = tmem_full + kAccStages; // [2]   leader only, 2 x 128 arrivals
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int nst_a = P.chunks_a * 3;                       // (chunk, dx) stages of the 3x3 source
+    const int nst = nst_a + P.chunks_r1 + P.chunks_r2;      // + centre-tap stages of the 1x1 skip sources
+
+    cluster_sync_all();
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)P.tmem_cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer (both CTAs) ----------------
+        if (elect_one()) {
+            int kbc = 0;
+            for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters) {
+                const int pair = tile / P.n_tiles_n, nt = tile - pair * P.n_tiles_n;
+                const int R = pair * 2 + (int)rank;                 // this CTA's 16x16 region (may be past the end)
+                const int b0 = R / P.regions_per_img, rr = R - b0 * P.regions_per_img;
+                const int y0 = (rr / P.regions_x) * 16, x0 = (rr % P.regions_x) * 16;
+                const int n0 = nt * P.BN + (int)rank * (P.BN / 2);
+                for (int st = 0; st < nst; ++st, ++kbc) {
+                    const int s = kbc % S;
+                    mbar_wait(&empty[s], ((kbc / S) & 1) ^ 1);
+                    uint8_t* a_dst = sA + s * kABytes;
+                    uint8_t* b_dst = sB + s * 3 * b_bytes;
+                    if (st < nst_a) {
+                        const int chunk = st / 3, dx = st - chunk * 3;
+                        const uint32_t bytes = 2u * kSubBytes + 3u * (uint32_t)b_bytes;
+                        if (leader) mbar_expect_tx(&full[s], 2u * bytes);
+                        else mbar_arrive_remote(&full[s], 0);
+                        tma2_load_4d(a_dst, &map_a, &full[s], chunk * kBK, x0 + dx - 1, y0 - 1, b0);
+                        tma2_load_4d(a_dst + kSubBytes, &map_a, &full[s], chunk * kBK, x0 + 8 + dx - 1, y0 - 1, b0);
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy)
+                            tma2_load_2d(b_dst + dy * b_bytes, &map_w, &full[s], (dy * 3 + dx) * P.Ca + chunk * kBK, n0);
+                    } else {
+                        const int cs = st - nst_a;
+                        const bool first = cs < P.chunks_r1;
+                        const CUtensorMap* am = first ? &map_r1 : &map_r2;
+                        const int c0 = (first ? cs : cs - P.chunks_r1) * kBK;
+                        const uint32_t bytes = 2u * (16 * 8 * kBK * 4) + (uint32_t)b_bytes;
+                        if (leader) mbar_expect_tx(&full[s], 2u * bytes);
+                        else mbar_arrive_remote(&full[s], 0);
+                        tma2_load_4d(a_dst, am, &full[s], c0, x0, y0, b0);
+                        tma2_load_4d(a_dst + kSubBytes, am, &full[s], c0, x0 + 8, y0, b0);
+                        tma2_load_2d(b_dst, &map_w, &full[s], 9 * P.Ca + cs * kBK, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer (leader CTA only) ----------------
+        if (leader) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.BN >> 3) << 17) |
+                                   ((uint32_t)(256 >> 4) << 24);
+            int kbc = 0, it = 0;
+            for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters, ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d0 = tmem_base + (uint32_t)((acc * 2 + 0) * P.BN);
+                const uint32_t tmem_d1 = tmem_base + (uint32_t)((acc * 2 + 1) * P.BN);
+                for (int st = 0; st < nst; ++st, ++kbc) {
+                    const int s = kbc % S;
+                    mbar_wait(&full[s], (kbc / S) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const uint64_t a0 = make_sdesc(smem_u32(sA + s * kABytes));
+                        const uint64_t a1 = make_sdesc(smem_u32(sA + s * kABytes + kSubBytes));
+                        const uint32_t b_addr = smem_u32(sB + s * 3 * b_bytes);
+                        const int ntap = st < nst_a ? 3 : 1;
+                        for (int dy = 0; dy < ntap; ++dy) {
+                            // vertical tap = the same box advanced by dy rows of 8 pixels = dy * 1024 B (atom aligned)
+                            const uint64_t bd = make_sdesc(b_addr + dy * b_bytes);
+                            const uint64_t ad0 = a0 + (uint64_t)(dy * 64), ad1 = a1 + (uint64_t)(dy * 64);
+#pragma unroll
+                            for (int k = 0; k < kBK / kUmmaK; ++k) {
+                                const uint32_t accum = (st | dy | k) ? 1u : 0u;
+                                umma2_tf32(tmem_d0, ad0 + 2 * k, bd + 2 * k, idesc, accum);
+                                umma2_tf32(tmem_d1, ad1 + 2 * k, bd + 2 * k, idesc, accum);
+                            }
+                        }
+                        umma2_commit(&empty[s]);
+                        if (st == nst - 1) umma2_commit(&tmem_full[acc]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ---------------- epilogue (both CTAs) ----------------
+        const int quarter = warp & 3;
+        const int m = quarter * 32 + lane;            // row of the subtile: pixel (m / 8, m % 8)
+        int it = 0;
+        for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters, ++it) {
+            const int acc = it & 1;
+            const int pair = tile / P.n_tiles_n, nt = tile - pair * P.n_tiles_n;
+            const int R = pair * 2 + (int)rank;
+            const bool valid = R < P.n_regions;
+            const int b = R / P.regions_per_img, rr = R - b * P.regions_per_img;
+            const int y = (rr / P.regions_x) * 16 + (m >> 3), xb = (rr % P.regions_x) * 16 + (m & 7);
+            const int n0 = nt * P.BN;
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int cb = 0; cb < P.BN; cb += 32) {
+                float gsum[8], gsq[8];
+#pragma unroll
+                for (int g = 0; g < 8; ++g) { gsum[g] = 0.f; gsq[g] = 0.f; }
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                           (uint32_t)((acc * 2 + sub) * P.BN + cb);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+                          "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+                          "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+                          "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (sub == 1 && cb + 32 >= P.BN) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        mbar_arrive_remote(&tmem_empty[acc], 0);   // accumulators fully read
+                    }
+                    if (!valid) continue;
+                    const int x = xb + sub * 8;
+                    const size_t q = ((size_t)b * P.H + y) * P.W + x;
+                    const int nb = n0 + cb;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int n = nb + j;
+                        if (n >= P.Cout) break;
+                        float v[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            v[e] = __uint_as_float(r[j + e]);
+                            if (P.bias) v[e] += P.bias[n + e];
+                            if (P.emb) v[e] += P.emb[(size_t)b * P.emb_stride + n + e];
+                        }
+                        if (P.res_mode == 1) {
+                            const float4 t = *reinterpret_cast<const float4*>(P.res + q * P.Cout + n);
+                            v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                        } else if (P.res_mode == 2) {
+                            const int W2 = P.W * 2;
+                            const float* rb = P.res + (((size_t)b * P.H * 2 + 2 * y) * W2 + 2 * x) * P.Cout + n;
+                            const float4 r0 = *reinterpret_cast<const float4*>(rb);
+                            const float4 r1 = *reinterpret_cast<const float4*>(rb + P.Cout);
+                            const float4 r2 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout);
+                            const float4 r3 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout + P.Cout);
+                            v[0] += (r0.x + r1.x + r2.x + r3.x) * 0.25f;
+                            v[1] += (r0.y + r1.y + r2.y + r3.y) * 0.25f;
+                            v[2] += (r0.z + r1.z + r2.z + r3.z) * 0.25f;
+                            v[3] += (r0.w + r1.w + r2.w + r3.w) * 0.25f;
+                        } else if (P.res_mode == 3) {
+                            const int Hh = P.H / 2, Wh = P.W / 2;
+                            const float4 t = *reinterpret_cast<const float4*>(
+                                P.res + (((size_t)b * Hh + (y >> 1)) * Wh + (x >> 1)) * P.Cout + n);
+                            v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                        }
+                        *reinterpret_cast<float4*>(P.out + q * P.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
+                        if (P.gn_stats) {   // gn_gs in {4, 8, 16, 32}: a float4 never straddles a group
+                            const int g = j / P.gn_gs;
+                            gsum[g] += (v[0] + v[1]) + (v[2] + v[3]);
+                            gsq[g] += (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+                        }
+                    }
+                }
+                if (P.gn_stats) {   // warp-uniform branch; all 32 lanes hold pixels of the same sample b
+                    const int ng = 32 / P.gn_gs;
+                    for (int g = 0; g < ng; ++g) {
+                        float s1 = valid ? gsum[g] : 0.f, s2 = valid ? gsq[g] : 0.f;
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                        }
+                        const int grp = (n0 + cb) / P.gn_gs + g;
+                        if (valid && lane == g && n0 + cb + g * P.gn_gs < P.Cout) {
+                            atomicAdd(&P.gn_stats[((size_t)b * 32 + grp) * 2], (double)s1);
+                            atomicAdd(&P.gn_stats[((size_t)b * 32 + grp) * 2 + 1], (double)s2);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)P.tmem_cols)
+                     : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode3() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// NHWC activation map: dims (C, W, H, B), box (32 ch, 8 px, rows, 1)
+int make_act_map3(CUtensorMap* m, const float* p, int C, int W, int H, int B, int rows) {
+    EncodeTiledFn enc = get_encode3();
+    if (!enc) { anoddpm_set_error("cuTensorMapEncodeTiled entry point not available"); return ANODDPM_ERR_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kBK, 8u, (cuuint32_t)rows, 1u};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        anoddpm_set_error("cuTensorMapEncodeTiled(act C=%d W=%d H=%d B=%d rows=%d) failed: %d", C, W, H, B, rows, (int)r);
+        return ANODDPM_ERR_CUDA;
+    }
+    return ANODDPM_OK;
+}
+
+int make_w_map3(CUtensorMap* m, const float* p, int Ktot, int Cout, int rows) {
+    EncodeTiledFn enc = get_encode3();
+    if (!enc) { anoddpm_set_error("cuTensorMapEncodeTiled entry point not available"); return ANODDPM_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        anoddpm_set_error("cuTensorMapEncodeTiled(weights K=%d Cout=%d rows=%d) failed: %d", Ktot, Cout, rows, (int)r);
+        return ANODDPM_ERR_CUDA;
+    }
+    return ANODDPM_OK;
+}
+
+}  // namespace
+
+// 1 if the halo-reuse kernel covers the problem (3x3, 16x16 regions, 32-channel chunks).
+extern "C" int anoddpm_conv_tc3_supported(const anoddpm_conv_desc* d) {
+    if (!d) return 0;
+    if (d->ksize != 3) return 0;
+    if (d->H % 16 || d->W % 16) return 0;
+    if (d->Ca % kBK || d->Cr1 % kBK || d->Cr2 % kBK) return 0;
+    if (d->Cout % 16) return 0;
+    if (d->Cout > 128 && d->Cout % 128) return 0;
+    return 1;
+}
+
+int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
+    ADP_REQUIRE(anoddpm_conv_tc3_supported(d), "anoddpm_conv(impl=3): needs ksize 3, H,W %% 16 == 0, channels %% 32 == 0 "
+                "(Ca=%d Cr1=%d Cr2=%d Cout=%d H=%d W=%d)", d->Ca, d->Cr1, d->Cr2, d->Cout, d->H, d->W);
+    Tc3Args P;
+    P.out = d->out; P.bias = d->bias; P.emb = d->emb; P.res = d->res;
+    P.M = d->B * d->H * d->W; P.H = d->H; P.W = d->W; P.Cout = d->Cout;
+    P.emb_stride = d->emb_stride; P.res_mode = d->res_mode;
+    P.Ca = d->Ca;
+    P.chunks_a = d->Ca / kBK;
+    P.chunks_r1 = d->Cr1 / kBK;
+    P.chunks_r2 = d->Cr2 / kBK;
+    P.BN = d->Cout < 128 ? d->Cout : 128;
+    const int acc_cols = kAccStages * 2 * P.BN;
+    P.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
+    const int Ktot = 9 * d->Ca + d->Cr1 + d->Cr2;
+    const int b_bytes = (P.BN / 2) * kBK * 4;
+    int stages = (200 * 1024) / (kABytes + 3 * b_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    P.stages = stages;
+    P.n_tiles_n = adp_ceil_div(d->Cout, P.BN);
+    P.regions_x = d->W / 16;
+    P.regions_per_img = (d->H / 16) * (d->W / 16);
+    P.n_regions = d->B * P.regions_per_img;
+    P.n_tiles = adp_ceil_div(P.n_regions, 2) * P.n_tiles_n;
+    P.gn_stats = d->gn_stats;
+    P.gn_gs = d->Cout / 32;
+    if (d->gn_stats) {
+        ADP_REQUIRE(d->Cout % 32 == 0 && (P.gn_gs == 4 || P.gn_gs == 8 || P.gn_gs == 16 || P.gn_gs == 32),
+                    "anoddpm_conv(impl=3): fused GroupNorm statistics need Cout in {128, 256, 512, 1024} (got %d)", d->Cout);
+    }
+
+    CUtensorMap ma, m1, m2, mw;
+    int rc;
+    if ((rc = make_act_map3(&ma, d->a, d->Ca, d->W, d->H, d->B, kSubRows))) return rc;
+    m1 = ma; m2 = ma;
+    if (d->r1 && (rc = make_act_map3(&m1, d->r1, d->Cr1, d->W, d->H, d->B, 16))) return rc;
+    if (d->r2 && (rc = make_act_map3(&m2, d->r2, d->Cr2, d->W, d->H, d->B, 16))) return rc;
+    if ((rc = make_w_map3(&mw, d->w, Ktot, d->Cout, P.BN / 2))) return rc;
+
+    const size_t smem = (size_t)stages * (kABytes + 3 * b_bytes) + (2 * kMaxStages + 2 * kAccStages) * 8 + 16 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int sms = 148;
+    const int n_clusters = P.n_tiles < sms / 2 ? P.n_tiles : sms / 2;
+    conv_tc3_kernel<<<dim3(2 * n_clusters), kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, P);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}

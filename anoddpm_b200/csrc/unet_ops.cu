@@ -378,53 +378,64 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(float* __restrict__ out,
 }
 
 // ---------------------------------------------------------------- head: NHWC features -> NCHW image
-// CTA = 8x32 output pixels; per 32-channel chunk the (10 x 34)-pixel halo tile is staged in shared memory
-// ([pixel][33] padding: conflict-free for pixel-consecutive lanes), weights of the chunk as [co][tap][32].
-// Each thread owns one output pixel (all Cout <= 4 channels).  Reads the input exactly once from HBM.
-constexpr int HT_H = 8, HT_W = 32, HT_C = 16;
+// CTA = 8x32 output pixels; per 16-channel chunk the (10 x 34)-pixel halo tile is staged in shared memory as
+// [pixel][20] floats (stride 20: 128-bit reads by 8 pixel-consecutive lanes touch all 32 banks once), weights of the
+// chunk as [co][tap][16].  Each thread owns one output pixel (all COUT <= 4 channels, compile-time).  The input is
+// read once from HBM (+33% halo); inner loop = 2 LDS.128 + 4*COUT FFMA per 4 channels.
+constexpr int HT_H = 8, HT_W = 32, HT_C = 16, HT_P = 20;
+template <int COUT>
 __global__ void __launch_bounds__(256) conv_head_kernel(float* __restrict__ out, const float* __restrict__ a,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
-                                                        int B, int Cin, int H, int W, int Cout) {
-    __shared__ float st[(HT_H + 2) * (HT_W + 2) * (HT_C + 1)];
-    __shared__ float swt[4 * 9 * HT_C];
+                                                        int B, int Cin, int H, int W) {
+    __shared__ __align__(16) float st[(HT_H + 2) * (HT_W + 2) * HT_P];
+    __shared__ __align__(16) float swt[COUT * 9 * HT_C];
     const int tiles_x = (W + HT_W - 1) / HT_W, tiles_y = (H + HT_H - 1) / HT_H;
     const int tile = blockIdx.x;
     const int b = tile / (tiles_x * tiles_y), tr = tile - b * tiles_x * tiles_y;
     const int y0 = (tr / tiles_x) * HT_H, x0 = (tr % tiles_x) * HT_W;
     const int py = threadIdx.x / HT_W, px = threadIdx.x % HT_W;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
     for (int c0 = 0; c0 < Cin; c0 += HT_C) {
         __syncthreads();
-        // stage halo tile: 340 pixels x HT_C channels, HT_C/4 lanes (float4) per pixel
         for (int i = threadIdx.x; i < (HT_H + 2) * (HT_W + 2) * (HT_C / 4); i += blockDim.x) {
-            const int pix = i / (HT_C / 4), q = (i % (HT_C / 4)) * 4;
+            const int pix = i >> 2, q = (i & 3) * 4;
             const int ly = pix / (HT_W + 2), lx = pix - ly * (HT_W + 2);
             const int gy = y0 + ly - 1, gx = x0 + lx - 1;
             F4 v = {0.f, 0.f, 0.f, 0.f};
             if (gy >= 0 && gy < H && gx >= 0 && gx < W && c0 + q < Cin)
                 v = ld4(a + (((size_t)b * H + gy) * W + gx) * Cin + c0 + q);
-            float* d = &st[pix * (HT_C + 1) + q];
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            st4(&st[pix * HT_P + q], v);
         }
-        for (int i = threadIdx.x; i < Cout * 9 * HT_C; i += blockDim.x) {
+        for (int i = threadIdx.x; i < COUT * 9 * HT_C; i += blockDim.x) {
             const int co = i / (9 * HT_C), r = i - co * 9 * HT_C, tap = r / HT_C, c = r - tap * HT_C;
             swt[i] = (c0 + c < Cin) ? w[(size_t)co * 9 * Cin + tap * Cin + c0 + c] : 0.f;
         }
         __syncthreads();
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-            const float* sp = &st[((py + tap / 3) * (HT_W + 2) + px + tap % 3) * (HT_C + 1)];
-#pragma unroll 8
-            for (int c = 0; c < HT_C; ++c) {
-                const float v = sp[c];
-                for (int co = 0; co < Cout; ++co) acc[co] = fmaf(v, swt[(co * 9 + tap) * HT_C + c], acc[co]);
+            const float* sp = &st[((py + tap / 3) * (HT_W + 2) + px + tap % 3) * HT_P];
+#pragma unroll
+            for (int c = 0; c < HT_C; c += 4) {
+                const F4 v = ld4(sp + c);
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+                    const F4 ww = ld4(&swt[(co * 9 + tap) * HT_C + c]);
+                    acc[co] = fmaf(v.x, ww.x, acc[co]);
+                    acc[co] = fmaf(v.y, ww.y, acc[co]);
+                    acc[co] = fmaf(v.z, ww.z, acc[co]);
+                    acc[co] = fmaf(v.w, ww.w, acc[co]);
+                }
             }
         }
     }
     const int gy = y0 + py, gx = x0 + px;
-    if (gy < H && gx < W)
-        for (int co = 0; co < Cout; ++co)
-            out[(((size_t)b * Cout + co) * H + gy) * W + gx] = acc[co] + (bias ? bias[co] : 0.f);
+    if (gy < H && gx < W) {
+#pragma unroll
+        for (int co = 0; co < COUT; ++co)
+            out[(((size_t)b * COUT + co) * H + gy) * W + gx] = acc[co] + (bias ? bias[co] : 0.f);
+    }
 }
 
 // ---------------------------------------------------------------- attention (UNet.py:137-153)
@@ -509,6 +520,7 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 
 int anoddpm_conv_tc(const anoddpm_conv_desc* d, void* stream);   // conv_tc.cu  (impl 1)
 int anoddpm_conv_tc2(const anoddpm_conv_desc* d, void* stream);  // conv_tc2.cu (impl 2)
+int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream);  // conv_tc3.cu (impl 3)
 
 extern "C" int anoddpm_timestep_embedding(float* emb, const int64_t* t, const float* freq, int B, int dim,
                                           void* stream) {
@@ -596,6 +608,8 @@ extern "C" int anoddpm_conv(const anoddpm_conv_desc* d, void* stream) {
     ADP_REQUIRE(al16(d->out) && al16(d->a) && al16(d->w) && (!d->r1 || al16(d->r1)) && (!d->r2 || al16(d->r2)) &&
                     (!d->res || al16(d->res)),
                 "anoddpm_conv: pointers must be 16-byte aligned");
+    if (d->impl == 3) return anoddpm_conv_tc3(d, stream);
+    ADP_REQUIRE(d->gn_stats == nullptr, "anoddpm_conv: fused GroupNorm statistics need impl 3");
     if (d->impl == 1) return anoddpm_conv_tc(d, stream);
     if (d->impl == 2) return anoddpm_conv_tc2(d, stream);
     ADP_REQUIRE(d->impl == 0, "anoddpm_conv: unknown impl %d", d->impl);
@@ -631,7 +645,13 @@ extern "C" int anoddpm_conv_head(float* out, const float* a, const float* w, con
     ADP_REQUIRE(Cin % 4 == 0 && al16(a), "anoddpm_conv_head: Cin must be a multiple of 4");
     const long long tiles = (long long)B * adp_ceil_div(H, HT_H) * adp_ceil_div(W, HT_W);
     ADP_REQUIRE(tiles < (1LL << 31), "anoddpm_conv_head: too many tiles");
-    conv_head_kernel<<<(unsigned)tiles, 256, 0, (cudaStream_t)stream>>>(out, a, w, bias, B, Cin, H, W, Cout);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (Cout) {
+        case 1: conv_head_kernel<1><<<(unsigned)tiles, 256, 0, st>>>(out, a, w, bias, B, Cin, H, W); break;
+        case 2: conv_head_kernel<2><<<(unsigned)tiles, 256, 0, st>>>(out, a, w, bias, B, Cin, H, W); break;
+        case 3: conv_head_kernel<3><<<(unsigned)tiles, 256, 0, st>>>(out, a, w, bias, B, Cin, H, W); break;
+        default: conv_head_kernel<4><<<(unsigned)tiles, 256, 0, st>>>(out, a, w, bias, B, Cin, H, W); break;
+    }
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }

@@ -145,6 +145,9 @@ class UNetEngine:
 
     # ------------------------------------------------------------------ op wrappers
     def _gn_stats(self, site, srcs, B, HW):
+        if site in self.stats_ready:       # already produced by the conv that wrote srcs[0]
+            assert len(srcs) == 1
+            return
         x1 = srcs[0]
         x2 = srcs[1] if len(srcs) > 1 else None
         call("anoddpm_gn_stats", ptr(self.stats[site]), ptr(x1), x1.shape[-1], ptr(x2), x2.shape[-1] if x2 is not None else 0,
@@ -164,13 +167,13 @@ class UNetEngine:
         self.launches += 1
         return (out, raw) if want_raw else out
 
-    def _conv(self, site, a, B, H, W, cout, r=(), emb=None, res=None, res_mode=0):
+    def _conv(self, site, a, B, H, W, cout, r=(), emb=None, res=None, res_mode=0, stats_site=None):
         d = ConvDesc()
         d.B, d.H, d.W = B, H, W
         d.Ca, d.Cout, d.ksize = a.shape[-1], cout, site.ksize
         d.Cr1 = r[0].shape[-1] if len(r) > 0 else 0
         d.Cr2 = r[1].shape[-1] if len(r) > 1 else 0
-        impl = self.tc_impl if (self.use_tc and _lib.lib().anoddpm_conv_tc_supported(ctypes.byref(d))) else 0
+        impl = self._pick_impl(d)
         w, b = site.packed(impl)
         out = torch.empty((B, H, W, cout), device=a.device, dtype=torch.float32)
         d.out, d.a, d.w, d.bias = out.data_ptr(), a.data_ptr(), w.data_ptr(), b.data_ptr()
@@ -183,10 +186,26 @@ class UNetEngine:
         d.res = res.data_ptr() if res is not None else None
         d.res_mode = res_mode
         d.impl = impl
+        d.gn_stats = None
+        if stats_site is not None and impl == 3 and cout in (128, 256, 512, 1024):
+            # the epilogue also accumulates the GroupNorm statistics of its output: the consumer skips its stats pass
+            d.gn_stats = self.stats[stats_site].data_ptr()
+            self.stats_ready.add(stats_site)
+            self.fused_stats += 1
         call("anoddpm_conv", ctypes.byref(d), stream())
         self.launches += 1
         self.tc_convs += 1 if impl else 0
         return out
+
+    def _pick_impl(self, d):
+        L = _lib.lib()
+        if not self.use_tc:
+            return 0
+        if self.tc_impl == 3 and L.anoddpm_conv_tc3_supported(ctypes.byref(d)):
+            return 3
+        if L.anoddpm_conv_tc_supported(ctypes.byref(d)):
+            return min(self.tc_impl, 2)
+        return 0
 
     def _tc_ok(self, C, H, W):
         """Will the conv consuming a (.., H, W, C) activation run on tensor cores? (decides the TF32 rounding)"""
@@ -197,7 +216,7 @@ class UNetEngine:
         return bool(_lib.lib().anoddpm_conv_tc_supported(ctypes.byref(d)))
 
     # ------------------------------------------------------------------ blocks
-    def _res(self, e, srcs, B, H, W):
+    def _res(self, e, srcs, B, H, W, next_site=None):
         mode = _MODE[e["mode"]]
         Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
         self._gn_stats(e["s1"], srcs, B, H * W)
@@ -210,15 +229,17 @@ class UNetEngine:
         else:
             a1 = self._gn_apply(e["s1"], srcs, e["gn1"], B, H, W, True, mode, tc1)
         emb = self.emb_all[:, e["emb_off"]:]
-        h = self._conv(e["conv1"], a1, B, Ho, Wo, e["cout"], emb=emb)
+        h = self._conv(e["conv1"], a1, B, Ho, Wo, e["cout"], emb=emb, stats_site=e["s2"])
         del a1
         self._gn_stats(e["s2"], [h], B, Ho * Wo)
         a2 = self._gn_apply(e["s2"], [h], e["gn2"], B, Ho, Wo, True, 0, self._tc_ok(e["cout"], Ho, Wo))
         del h
         if e["skip_conv"]:
-            return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], r=([raw] if raw is not None else srcs)), Ho, Wo
+            return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], r=([raw] if raw is not None else srcs),
+                              stats_site=next_site), Ho, Wo
         assert len(srcs) == 1
-        return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], res=srcs[0], res_mode=_RES_FOR_MODE[e["mode"]]), Ho, Wo
+        return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], res=srcs[0], res_mode=_RES_FOR_MODE[e["mode"]],
+                          stats_site=next_site), Ho, Wo
 
     def _attn(self, e, x, B, H, W):
         C, T = e["c"], H * W
@@ -231,17 +252,25 @@ class UNetEngine:
         self.launches += 1
         return self._conv(e["proj"], a, B, H, W, C, res=x, res_mode=1)
 
-    def _entry(self, entry, srcs, B, H, W):
+    @staticmethod
+    def _first_site(entry):
+        e = entry[0]
+        return e["s1"] if e["kind"] == "res" else e["s"]
+
+    def _entry(self, entry, srcs, B, H, W, next_site=None):
+        """next_site: GroupNorm site that consumes this entry's output as a SINGLE source (None if the consumer
+        concatenates it with a skip tensor, whose statistics need both sources)."""
         h = None
-        for e in entry:
+        for i, e in enumerate(entry):
             cur = srcs if h is None else [h]
+            nxt = self._first_site(entry[i + 1:]) if i + 1 < len(entry) else next_site
             if e["kind"] == "stem":
                 raise RuntimeError("stem handled by forward()")
             if e["kind"] == "res":
-                h, H, W = self._res(e, cur, B, H, W)
+                h, H, W = self._res(e, cur, B, H, W, nxt)
             else:
                 assert len(cur) == 1
-                h = self._attn(e, cur[0], B, H, W)
+                h = self._attn(e, cur[0], B, H, W)   # 1x1 proj conv: no fused statistics
         return h, H, W
 
     # ------------------------------------------------------------------ forward
@@ -253,10 +282,13 @@ class UNetEngine:
         if p0.device != x.device:
             raise RuntimeError(f"UNetModel parameters are on {p0.device} but the input is on {x.device}")
         self._refresh()
-        if m.conv_impl not in ("tc", "tc1", "exact"):
-            raise ValueError(f"conv_impl must be 'tc', 'tc1' or 'exact', got {m.conv_impl!r}")
-        self.use_tc = m.conv_impl in ("tc", "tc1")
-        self.tc_impl = 2 if m.conv_impl == "tc" else 1   # tc: persistent CTA-pair kernel; tc1: single-CTA tiles
+        if m.conv_impl not in ("tc", "tc2", "tc1", "exact"):
+            raise ValueError(f"conv_impl must be 'tc', 'tc2', 'tc1' or 'exact', got {m.conv_impl!r}")
+        self.use_tc = m.conv_impl != "exact"
+        # tc: halo-reuse CTA-pair kernel (impl 3) where it applies, else impl 2; tc2: persistent CTA pairs; tc1: single-CTA tiles
+        self.tc_impl = {"tc": 3, "tc2": 2, "tc1": 1, "exact": 0}[m.conv_impl]
+        self.stats_ready = set()
+        self.fused_stats = 0
         self.tc_convs = 0
         in_dtype = x.dtype
         x = x.contiguous().float()
@@ -290,14 +322,16 @@ class UNetEngine:
         call("anoddpm_conv_stem", ptr(h), ptr(x), ptr(stem.weight), ptr(stem.bias), B, Cin, H, W, C0, stream())
         self.launches += 1
         skips = [(h, H, W)]
-        for entry in self.down[1:]:
-            h, H, W = self._entry(entry, [h], B, H, W)
+        downs = self.down[1:]
+        for i, entry in enumerate(downs):
+            nxt = self._first_site(downs[i + 1]) if i + 1 < len(downs) else self._first_site(self.middle)
+            h, H, W = self._entry(entry, [h], B, H, W, nxt)
             skips.append((h, H, W))
-        h, H, W = self._entry(self.middle, [h], B, H, W)
-        for entry in self.up:
+        h, H, W = self._entry(self.middle, [h], B, H, W, None)
+        for i, entry in enumerate(self.up):
             s, sh, sw = skips.pop()
             assert (sh, sw) == (H, W)
-            h, H, W = self._entry(entry, [h, s], B, H, W)
+            h, H, W = self._entry(entry, [h, s], B, H, W, self.head["s"] if i + 1 == len(self.up) else None)
         hd = self.head
         self._gn_stats(hd["s"], [h], B, H * W)
         a = self._gn_apply(hd["s"], [h], hd["gn"], B, H, W, True, 0, False)

@@ -191,7 +191,7 @@ def run_native(args):
 
     out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "tf32" if model.conv_impl in ("tc", "tc1") else "f32", "data": "synthetic",
+           "vs_baseline": None, "dtype": "tf32" if model.conv_impl != "exact" else "f32", "data": "synthetic",
            "config": {"workload": "BASELINE configs[2] per GPU: forward_backward 256x256x1 bs=32 T=1000 t_distance=800 "
                                   "simplex(6,0.8,64), UNet 256/base128/attn16,8/2 heads (554.5 GFLOP/image/step); "
                                   + ("step = one full 800-step chain" if args.full_chain else
@@ -218,7 +218,7 @@ def roofline(model, dev, B):
     pk = peaks()
     res = []
     tot_flop, tot_ms = 0.0, 0.0
-    impl = {"tc": 2, "tc1": 1}.get(model.conv_impl, 0)
+    impl = {"tc": 3, "tc2": 2, "tc1": 1}.get(model.conv_impl, 0)
     for (Ci, Co, HW, count) in ((128, 128, 256, 9), (256, 128, 256, 3), (128, 128, 128, 9)):
         a = round_tf32_(torch.randn(B, HW, HW, Ci, device=dev))
         w = round_tf32_(torch.randn(Co, 9 * Ci, device=dev) * 0.03)
@@ -227,6 +227,7 @@ def roofline(model, dev, B):
         d = _lib.ConvDesc()
         d.out, d.a, d.w, d.bias = out.data_ptr(), a.data_ptr(), w.data_ptr(), bias.data_ptr()
         d.B, d.H, d.W, d.Ca, d.Cout, d.ksize, d.impl = B, HW, HW, Ci, Co, 3, impl
+        d.gn_stats = None
         for _ in range(3):
             _lib.call("anoddpm_conv", ctypes.byref(d), _lib.stream())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -242,7 +243,7 @@ def roofline(model, dev, B):
         tot_ms += ms * count
         del a, w, out
     achieved = tot_flop / tot_ms / 1e9
-    return {"bound": "tensor", "kernel": {2: "conv_tc2_kernel (tcgen05.mma.cta_group::2 kind::tf32, persistent CTA pairs, TMA-fed implicit GEMM)", 1: "conv_tc_kernel (tcgen05.mma kind::tf32, TMA-fed implicit GEMM)", 0: "conv_simt_kernel"}[impl],
+    return {"bound": "tensor", "kernel": {3: "conv_tc3_kernel (tcgen05.mma.cta_group::2 kind::tf32, halo-reuse persistent CTA pairs, TMA-fed implicit GEMM)", 2: "conv_tc2_kernel (tcgen05.mma.cta_group::2 kind::tf32, persistent CTA pairs, TMA-fed implicit GEMM)", 1: "conv_tc_kernel (tcgen05.mma kind::tf32, TMA-fed implicit GEMM)", 0: "conv_simt_kernel"}[impl],
             "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
             "peak_note": f"dense bf16 cuBLAS sustained, {pk['src']} (MEASURED_PEAKS.json); kind::tf32 issues at half the bf16 rate, "
                          f"so frac of the tf32 rate = {achieved / (pk['bf16_sustained'] / 2):.3f}",
@@ -312,7 +313,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU (BASELINE: 32)")
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--full-chain", action="store_true", help="a step = one whole 800-step chain")
-    ap.add_argument("--conv-impl", default=None, choices=[None, "tc", "tc1", "exact"])
+    ap.add_argument("--conv-impl", default=None, choices=[None, "tc", "tc2", "tc1", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":

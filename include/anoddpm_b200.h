@@ -109,7 +109,9 @@ int anoddpm_gn_apply(float* out, float* raw_out, const float* x1, int C1, const 
  * Conv1d 1x1 qkv/proj of AttentionBlock (UNet.py:115-125).
  * res_mode: 0 none, 1 same resolution, 2 res is 2H x 2W and is avg-pooled 2x2, 3 res is H/2 x W/2 nearest-upsampled
  * (x_upd of UNet.py:206-207).  impl: 0 = exact fp32 CUDA-core kernel; 1 = tcgen05 kind::tf32, one CTA per 128x128 tile;
- * 2 = tcgen05 kind::tf32 cta_group::2, persistent CTA pairs (256 x BN tiles, double-buffered TMEM) -- the fast path. */
+ * 2 = tcgen05 kind::tf32 cta_group::2, persistent CTA pairs (256 x BN tiles, double-buffered TMEM);
+ * 3 = as 2 with halo reuse (16x16 spatial regions, vertical taps share one TMA box, two M-subtiles share each weight
+ *     tile) -- 3x3 convs with H, W % 16 == 0; cuts L2->SM operand traffic ~2.5x.  The fast path. */
 typedef struct anoddpm_conv_desc {
     float* out;
     const float* a;
@@ -125,10 +127,14 @@ typedef struct anoddpm_conv_desc {
     int emb_stride;
     int res_mode;
     int impl;
+    double* gn_stats;   /* optional, impl 3 only: += (sum, sum of squares) of the OUTPUT per (sample, group of Cout/32
+                           channels), layout [B][32][2] fp64 = the input anoddpm_gn_apply expects for the next GroupNorm */
 } anoddpm_conv_desc;
 int anoddpm_conv(const anoddpm_conv_desc* d /* [host] */, void* stream);
 /* 1 if impl=1/2 (tcgen05 tiles: channels % 32, Cout % 16, power-of-two W) covers the problem, else 0. */
 int anoddpm_conv_tc_supported(const anoddpm_conv_desc* d /* [host] */);
+/* 1 if impl=3 covers the problem (ksize 3, H % 16 == W % 16 == 0, channels % 32 == 0, Cout % 16 == 0). */
+int anoddpm_conv_tc3_supported(const anoddpm_conv_desc* d /* [host] */);
 
 /* Stem: NCHW image (Cin small) -> NHWC features, 3x3 pad 1, w is OIHW.  UNet.py:279-281. */
 int anoddpm_conv_stem(float* out_nhwc, const float* x_nchw, const float* w_oihw, const float* bias, int B, int Cin,
