@@ -251,8 +251,9 @@ class UNetModel(nn.Module):
         self.out = nn.Sequential(GroupNorm32(32, ch), nn.SiLU(),
                                  zero_module(nn.Conv2d(base_channels * channel_mults[0], self.out_channels, 3, padding=1)))
         self._engine = None
-        # "tc" (tcgen05 TF32: halo-reuse CTA-pair kernel, falling back to "tc2" shapes) | "tc2" (persistent CTA pairs) |
-        # "tc1" (single-CTA tiles) | "exact" (fp32 CUDA cores)
+        # "tc" (tcgen05, halo-reuse CTA-pair kernel; fp16 operands where channels % 64 == 0, else TF32) |
+        # "tc_tf32" (same kernels, TF32 operands only) | "tc2" (persistent CTA pairs, TF32) | "tc1" (single-CTA tiles, TF32) |
+        # "exact" (fp32 CUDA cores)
         self.conv_impl = os.environ.get("ANODDPM_CONV_IMPL", "tc")
 
     # -- native inference path ---------------------------------------------------------------------

@@ -18,7 +18,7 @@ class ConvDesc(ctypes.Structure):
     """Mirror of ``anoddpm_conv_desc`` (include/anoddpm_b200.h)."""
     _fields_ = [("out", c_vp), ("a", c_vp), ("r1", c_vp), ("r2", c_vp), ("w", c_vp), ("bias", c_vp), ("emb", c_vp),
                 ("res", c_vp), ("B", c_int), ("H", c_int), ("W", c_int), ("Ca", c_int), ("Cr1", c_int), ("Cr2", c_int),
-                ("Cout", c_int), ("ksize", c_int), ("emb_stride", c_int), ("res_mode", c_int), ("impl", c_int), ("gn_stats", c_vp)]
+                ("Cout", c_int), ("ksize", c_int), ("emb_stride", c_int), ("res_mode", c_int), ("impl", c_int), ("operand_f16", c_int), ("gn_stats", c_vp)]
 
 
 # name -> (restype, argtypes); every symbol of include/anoddpm_b200.h

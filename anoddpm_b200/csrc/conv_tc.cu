@@ -352,11 +352,11 @@ int anoddpm_conv_tc(const anoddpm_conv_desc* d, void* stream) {
 
     CUtensorMap ma, m1, m2, mw;
     int rc;
-    if ((rc = make_act_map(&ma, d->a, d->Ca, d->W, d->H, d->B, P.TW, P.TH, TB))) return rc;
+    if ((rc = make_act_map(&ma, static_cast<const float*>(d->a), d->Ca, d->W, d->H, d->B, P.TW, P.TH, TB))) return rc;
     m1 = ma; m2 = ma;
-    if (d->r1 && (rc = make_act_map(&m1, d->r1, d->Cr1, d->W, d->H, d->B, P.TW, P.TH, TB))) return rc;
-    if (d->r2 && (rc = make_act_map(&m2, d->r2, d->Cr2, d->W, d->H, d->B, P.TW, P.TH, TB))) return rc;
-    if ((rc = make_w_map(&mw, d->w, Ktot, d->Cout, P.BN))) return rc;
+    if (d->r1 && (rc = make_act_map(&m1, static_cast<const float*>(d->r1), d->Cr1, d->W, d->H, d->B, P.TW, P.TH, TB))) return rc;
+    if (d->r2 && (rc = make_act_map(&m2, static_cast<const float*>(d->r2), d->Cr2, d->W, d->H, d->B, P.TW, P.TH, TB))) return rc;
+    if ((rc = make_w_map(&mw, static_cast<const float*>(d->w), Ktot, d->Cout, P.BN))) return rc;
 
     const size_t smem = (size_t)kStages * (kABytes + P.BN * kBK * 4) + (2 * kStages + 1) * 8 + 16 + 1024;
     static bool attr_set = false;

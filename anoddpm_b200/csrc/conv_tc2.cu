@@ -22,10 +22,10 @@
 namespace {
 
 constexpr int kBM = 128;
-constexpr int kBK = 32;
-constexpr int kUmmaK = 8;
+constexpr int kRowBytes = 128;   // one K-block row: 32 fp32 (TF32 MMA) or 64 fp16 elements
+constexpr int kKSteps = 4;       // MMAs per K-block: 32 B of K each (8 tf32 / 16 f16 elements)
 constexpr int kThreads = 256;
-constexpr int kABytes = kBM * kBK * 4;
+constexpr int kABytes = kBM * kRowBytes;
 constexpr int kAccStages = 2;
 constexpr int kMaxStages = 8;
 
@@ -41,6 +41,7 @@ struct Tc2Args {
     int BN;            // pair-tile N (UMMA N); each CTA stages BN/2 weight rows
     int tmem_cols;
     int stages;
+    int ke;                    // elements per 128-byte K-block row: 32 (fp32 operands) or 64 (fp16 operands)
     int n_tiles_n, n_tiles;   // tiles along N, total pair tiles
 };
 
@@ -111,16 +112,28 @@ __device__ __forceinline__ void tma2_load_2d(void* smem, const CUtensorMap* map,
         ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+template <bool F16>
+__device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                      uint32_t accumulate) {
+    if (F16) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 // commit all prior MMAs of this thread; arrive on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
@@ -134,13 +147,14 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
+template <bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_r1,
                 const __grid_constant__ CUtensorMap map_r2, const __grid_constant__ CUtensorMap map_w,
                 const Tc2Args P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_bytes = (P.BN / 2) * kBK * 4;
+    const int b_bytes = (P.BN / 2) * kRowBytes;
     const int S = P.stages;
     uint8_t* sA = smem;
     uint8_t* sB = smem + S * kABytes;
@@ -197,26 +211,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     int c0, dy = 0, dx = 0;
                     if (kb < P.nkb_a) {
                         const int tap = kb / P.chunks_a;
-                        c0 = (kb - tap * P.chunks_a) * kBK;
+                        c0 = (kb - tap * P.chunks_a) * P.ke;
                         dy = tap / P.ks - pad;
                         dx = tap % P.ks - pad;
                         am = &map_a;
                     } else if (kb < P.nkb_a + P.nkb_r1) {
-                        c0 = (kb - P.nkb_a) * kBK;
+                        c0 = (kb - P.nkb_a) * P.ke;
                         am = &map_r1;
                     } else {
-                        c0 = (kb - P.nkb_a - P.nkb_r1) * kBK;
+                        c0 = (kb - P.nkb_a - P.nkb_r1) * P.ke;
                         am = &map_r2;
                     }
                     tma2_load_4d(sA + s * kABytes, am, &full[s], c0, w0 + dx, h0 + dy, b0);
-                    tma2_load_2d(sB + s * b_bytes, &map_w, &full[s], kb * kBK, n0);
+                    tma2_load_2d(sB + s * b_bytes, &map_w, &full[s], kb * P.ke, n0);
                 }
             }
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer (leader CTA only) ----------------
         if (leader) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.BN >> 3) << 17) |
+            constexpr uint32_t fmt = F16 ? 0u : 2u;   // a/b format: F16 = 0, TF32 = 2 ; c format F32 = 1
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.BN >> 3) << 17) |
                                    ((uint32_t)(256 >> 4) << 24);
             int kbc = 0, it = 0;
             for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters, ++it) {
@@ -232,8 +247,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         const uint64_t ad = make_sdesc(smem_u32(sA + s * kABytes));
                         const uint64_t bd = make_sdesc(smem_u32(sB + s * b_bytes));
 #pragma unroll
-                        for (int k = 0; k < kBK / kUmmaK; ++k)
-                            umma2_tf32(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < kKSteps; ++k)
+                            umma2<F16>(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
                         umma2_commit(&empty[s]);
                         if (kb == nkb - 1) umma2_commit(&tmem_full[acc]);
                     }
@@ -338,14 +353,15 @@ EncodeTiledFn get_encode2() {
     return fn;
 }
 
-int make_act_map2(CUtensorMap* m, const float* p, int C, int W, int H, int B, int TW, int TH, int TB) {
+int make_act_map2(CUtensorMap* m, const void* p, int f16, int C, int W, int H, int B, int TW, int TH, int TB) {
     EncodeTiledFn enc = get_encode2();
     if (!enc) { anoddpm_set_error("cuTensorMapEncodeTiled entry point not available"); return ANODDPM_ERR_CUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+    const cuuint64_t es = f16 ? 2 : 4;
+    cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+    cuuint32_t box[4] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p), dims, strides, box, estr,
+    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(p), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -356,14 +372,15 @@ int make_act_map2(CUtensorMap* m, const float* p, int C, int W, int H, int B, in
     return ANODDPM_OK;
 }
 
-int make_w_map2(CUtensorMap* m, const float* p, int Ktot, int Cout, int rows) {
+int make_w_map2(CUtensorMap* m, const void* p, int f16, int Ktot, int Cout, int rows) {
     EncodeTiledFn enc = get_encode2();
     if (!enc) { anoddpm_set_error("cuTensorMapEncodeTiled entry point not available"); return ANODDPM_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
-    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)rows};
+    const cuuint64_t es = f16 ? 2 : 4;
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * es};
+    cuuint32_t box[2] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
+    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(p), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -388,15 +405,19 @@ int anoddpm_conv_tc2(const anoddpm_conv_desc* d, void* stream) {
     int TH = 128 / TW; if (TH > d->H) TH = d->H;
     const int TB = 128 / (TW * TH);
     P.ks = d->ksize;
-    P.chunks_a = d->Ca / kBK;
+    const int f16 = d->operand_f16 ? 1 : 0;
+    P.ke = f16 ? 64 : 32;
+    ADP_REQUIRE(d->Ca % P.ke == 0 && d->Cr1 % P.ke == 0 && d->Cr2 % P.ke == 0,
+                "anoddpm_conv(impl=2): fp16 operands need channel counts that are multiples of 64");
+    P.chunks_a = d->Ca / P.ke;
     P.nkb_a = d->ksize * d->ksize * P.chunks_a;
-    P.nkb_r1 = d->Cr1 / kBK;
-    P.nkb_r2 = d->Cr2 / kBK;
+    P.nkb_r1 = d->Cr1 / P.ke;
+    P.nkb_r2 = d->Cr2 / P.ke;
     P.BN = (d->Cout % 256 == 0) ? 256 : (d->Cout < 128 ? d->Cout : 128);
     const int acc_cols = kAccStages * P.BN;
     P.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
-    const int Ktot = (P.nkb_a + P.nkb_r1 + P.nkb_r2) * kBK;
-    const int b_bytes = (P.BN / 2) * kBK * 4;
+    const int Ktot = (P.nkb_a + P.nkb_r1 + P.nkb_r2) * P.ke;
+    const int b_bytes = (P.BN / 2) * kRowBytes;
     int stages = (196 * 1024) / (kABytes + b_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     P.stages = stages;
@@ -406,21 +427,23 @@ int anoddpm_conv_tc2(const anoddpm_conv_desc* d, void* stream) {
 
     CUtensorMap ma, m1, m2, mw;
     int rc;
-    if ((rc = make_act_map2(&ma, d->a, d->Ca, d->W, d->H, d->B, TW, TH, TB))) return rc;
+    if ((rc = make_act_map2(&ma, d->a, f16, d->Ca, d->W, d->H, d->B, TW, TH, TB))) return rc;
     m1 = ma; m2 = ma;
-    if (d->r1 && (rc = make_act_map2(&m1, d->r1, d->Cr1, d->W, d->H, d->B, TW, TH, TB))) return rc;
-    if (d->r2 && (rc = make_act_map2(&m2, d->r2, d->Cr2, d->W, d->H, d->B, TW, TH, TB))) return rc;
-    if ((rc = make_w_map2(&mw, d->w, Ktot, d->Cout, P.BN / 2))) return rc;
+    if (d->r1 && (rc = make_act_map2(&m1, d->r1, f16, d->Cr1, d->W, d->H, d->B, TW, TH, TB))) return rc;
+    if (d->r2 && (rc = make_act_map2(&m2, d->r2, f16, d->Cr2, d->W, d->H, d->B, TW, TH, TB))) return rc;
+    if ((rc = make_w_map2(&mw, d->w, f16, Ktot, d->Cout, P.BN / 2))) return rc;
 
     const size_t smem = (size_t)stages * (kABytes + b_bytes) + (2 * kMaxStages + 2 * kAccStages) * 8 + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        ADP_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     int sms = 148;
     int n_clusters = P.n_tiles < sms / 2 ? P.n_tiles : sms / 2;
-    conv_tc2_kernel<<<dim3(2 * n_clusters), kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, P);
+    if (f16) conv_tc2_kernel<true><<<dim3(2 * n_clusters), kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, P);
+    else conv_tc2_kernel<false><<<dim3(2 * n_clusters), kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, P);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }

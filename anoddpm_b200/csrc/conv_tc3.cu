@@ -20,14 +20,15 @@
 namespace {
 
 constexpr int kBM = 128;
-constexpr int kBK = 32;
-constexpr int kUmmaK = 8;
+constexpr int kRowBytes = 128;   // one K-block row: 32 fp32 (TF32 MMA) or 64 fp16 elements
+constexpr int kKSteps = 4;       // MMAs per K-block: 32 B of K each (8 tf32 / 16 f16 elements)
 constexpr int kThreads = 256;
 constexpr int kSubRows = 18;                        // 16 output rows + 1 halo row above and below
-constexpr int kSubBytes = kSubRows * 8 * kBK * 4;   // one (32 ch, 8 px, 18 rows) box = 18432 B
+constexpr int kSubBytes = kSubRows * 8 * kRowBytes;   // one (32 ch, 8 px, 18 rows) box = 18432 B
 constexpr int kABytes = 2 * kSubBytes;              // two subtiles per CTA
 constexpr int kAccStages = 2;
 constexpr int kMaxStages = 4;
+constexpr int kStgPitch = 36;                       // floats per staged epilogue row (32 + 4: conflict-free 128-bit access)
 
 struct Tc3Args {
     float* out;
@@ -41,6 +42,7 @@ struct Tc3Args {
     int BN;                    // pair-tile N (UMMA N); each CTA stages BN/2 weight rows per tap
     int tmem_cols;
     int stages;
+    int ke;                    // elements per 128-byte K-block row: 32 (fp32 operands) or 64 (fp16 operands)
     int n_tiles_n, n_tiles;    // tiles along N, total pair tiles
     int regions_x, regions_per_img, n_regions;   // 16x16 regions
     double* gn_stats;          // optional [B][32][2] accumulation of the output's GroupNorm statistics
@@ -114,16 +116,28 @@ __device__ __forceinline__ void tma2_load_2d(void* smem, const CUtensorMap* map,
         ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
         : "memory");
 }
-__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+template <bool F16>
+__device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                      uint32_t accumulate) {
+    if (F16) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+            "}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 // commit all prior MMAs of this thread; arrive on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
@@ -137,13 +151,14 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
+template <bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_r1,
                 const __grid_constant__ CUtensorMap map_r2, const __grid_constant__ CUtensorMap map_w,
                 const Tc3Args P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int b_bytes = (P.BN / 2) * kBK * 4;      // one weight tile (this CTA's half of the N rows)
+    const int b_bytes = (P.BN / 2) * kRowBytes;      // one weight tile (this CTA's half of the N rows)
     const int S = P.stages;
     uint8_t* sA = smem;                            // [S][2 subtiles][kSubBytes]
     uint8_t* sB = smem + S * kABytes;              // [S][3 taps][b_bytes]
@@ -153,6 +168,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]   both CTAs (multicast commit)
     uint64_t* tmem_empty = tmem_full + kAccStages; // [2]   leader only, 2 x 128 arrivals
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+    float* stg_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // 4 warps x 32 rows x kStgPitch
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
@@ -202,22 +218,22 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         const uint32_t bytes = 2u * kSubBytes + 3u * (uint32_t)b_bytes;
                         if (leader) mbar_expect_tx(&full[s], 2u * bytes);
                         else mbar_arrive_remote(&full[s], 0);
-                        tma2_load_4d(a_dst, &map_a, &full[s], chunk * kBK, x0 + dx - 1, y0 - 1, b0);
-                        tma2_load_4d(a_dst + kSubBytes, &map_a, &full[s], chunk * kBK, x0 + 8 + dx - 1, y0 - 1, b0);
+                        tma2_load_4d(a_dst, &map_a, &full[s], chunk * P.ke, x0 + dx - 1, y0 - 1, b0);
+                        tma2_load_4d(a_dst + kSubBytes, &map_a, &full[s], chunk * P.ke, x0 + 8 + dx - 1, y0 - 1, b0);
 #pragma unroll
                         for (int dy = 0; dy < 3; ++dy)
-                            tma2_load_2d(b_dst + dy * b_bytes, &map_w, &full[s], (dy * 3 + dx) * P.Ca + chunk * kBK, n0);
+                            tma2_load_2d(b_dst + dy * b_bytes, &map_w, &full[s], (dy * 3 + dx) * P.Ca + chunk * P.ke, n0);
                     } else {
                         const int cs = st - nst_a;
                         const bool first = cs < P.chunks_r1;
                         const CUtensorMap* am = first ? &map_r1 : &map_r2;
-                        const int c0 = (first ? cs : cs - P.chunks_r1) * kBK;
-                        const uint32_t bytes = 2u * (16 * 8 * kBK * 4) + (uint32_t)b_bytes;
+                        const int c0 = (first ? cs : cs - P.chunks_r1) * P.ke;
+                        const uint32_t bytes = 2u * (16 * 8 * kRowBytes) + (uint32_t)b_bytes;
                         if (leader) mbar_expect_tx(&full[s], 2u * bytes);
                         else mbar_arrive_remote(&full[s], 0);
                         tma2_load_4d(a_dst, am, &full[s], c0, x0, y0, b0);
                         tma2_load_4d(a_dst + kSubBytes, am, &full[s], c0, x0 + 8, y0, b0);
-                        tma2_load_2d(b_dst, &map_w, &full[s], 9 * P.Ca + cs * kBK, n0);
+                        tma2_load_2d(b_dst, &map_w, &full[s], 9 * P.Ca + cs * P.ke, n0);
                     }
                 }
             }
@@ -225,7 +241,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     } else if (warp == 1) {
         // ---------------- MMA issuer (leader CTA only) ----------------
         if (leader) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.BN >> 3) << 17) |
+            constexpr uint32_t fmt = F16 ? 0u : 2u;   // a/b format: F16 = 0, TF32 = 2 ; c format F32 = 1
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.BN >> 3) << 17) |
                                    ((uint32_t)(256 >> 4) << 24);
             int kbc = 0, it = 0;
             for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters, ++it) {
@@ -248,10 +265,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             const uint64_t bd = make_sdesc(b_addr + dy * b_bytes);
                             const uint64_t ad0 = a0 + (uint64_t)(dy * 64), ad1 = a1 + (uint64_t)(dy * 64);
 #pragma unroll
-                            for (int k = 0; k < kBK / kUmmaK; ++k) {
+                            for (int k = 0; k < kKSteps; ++k) {
                                 const uint32_t accum = (st | dy | k) ? 1u : 0u;
-                                umma2_tf32(tmem_d0, ad0 + 2 * k, bd + 2 * k, idesc, accum);
-                                umma2_tf32(tmem_d1, ad1 + 2 * k, bd + 2 * k, idesc, accum);
+                                umma2<F16>(tmem_d0, ad0 + 2 * k, bd + 2 * k, idesc, accum);
+                                umma2<F16>(tmem_d1, ad1 + 2 * k, bd + 2 * k, idesc, accum);
                             }
                         }
                         umma2_commit(&empty[s]);
@@ -263,8 +280,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
     } else if (warp >= 4) {
         // ---------------- epilogue (both CTAs) ----------------
+        // TMEM -> registers (thread = pixel row, 32 channels) -> per-warp smem transpose -> each store instruction
+        // writes 4 pixels x 128 B (4 full lines) instead of 32 scattered 16-byte pieces.
         const int quarter = warp & 3;
-        const int m = quarter * 32 + lane;            // row of the subtile: pixel (m / 8, m % 8)
+        float* stg = stg_all + quarter * (32 * kStgPitch);
+        const int rr0 = lane >> 3;          // row within a group of 4 staged rows
+        const int cc = (lane & 7) * 4;      // channel quad within the 32-channel chunk
         int it = 0;
         for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters, ++it) {
             const int acc = it & 1;
@@ -272,14 +293,17 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int R = pair * 2 + (int)rank;
             const bool valid = R < P.n_regions;
             const int b = R / P.regions_per_img, rr = R - b * P.regions_per_img;
-            const int y = (rr / P.regions_x) * 16 + (m >> 3), xb = (rr % P.regions_x) * 16 + (m & 7);
+            const int ybase = (rr / P.regions_x) * 16, xbase = (rr % P.regions_x) * 16;
             const int n0 = nt * P.BN;
             mbar_wait(&tmem_full[acc], (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int cb = 0; cb < P.BN; cb += 32) {
-                float gsum[8], gsq[8];
-#pragma unroll
-                for (int g = 0; g < 8; ++g) { gsum[g] = 0.f; gsq[g] = 0.f; }
+                const int n = n0 + cb + cc;
+                const bool nvalid = valid && n < P.Cout;
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), emb4 = bias4;
+                if (nvalid && P.bias) bias4 = *reinterpret_cast<const float4*>(P.bias + n);
+                if (nvalid && P.emb) emb4 = *reinterpret_cast<const float4*>(P.emb + (size_t)b * P.emb_stride + n);
+                float s1 = 0.f, s2 = 0.f;
 #pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
                     uint32_t r[32];
@@ -300,63 +324,60 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         mbar_arrive_remote(&tmem_empty[acc], 0);   // accumulators fully read
                     }
-                    if (!valid) continue;
-                    const int x = xb + sub * 8;
-                    const size_t q = ((size_t)b * P.H + y) * P.W + x;
-                    const int nb = n0 + cb;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const int n = nb + j;
-                        if (n >= P.Cout) break;
-                        float v[4];
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<uint4*>(stg + lane * kStgPitch + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                    __syncwarp();
+                    if (nvalid) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            v[e] = __uint_as_float(r[j + e]);
-                            if (P.bias) v[e] += P.bias[n + e];
-                            if (P.emb) v[e] += P.emb[(size_t)b * P.emb_stride + n + e];
-                        }
-                        if (P.res_mode == 1) {
-                            const float4 t = *reinterpret_cast<const float4*>(P.res + q * P.Cout + n);
-                            v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
-                        } else if (P.res_mode == 2) {
-                            const int W2 = P.W * 2;
-                            const float* rb = P.res + (((size_t)b * P.H * 2 + 2 * y) * W2 + 2 * x) * P.Cout + n;
-                            const float4 r0 = *reinterpret_cast<const float4*>(rb);
-                            const float4 r1 = *reinterpret_cast<const float4*>(rb + P.Cout);
-                            const float4 r2 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout);
-                            const float4 r3 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout + P.Cout);
-                            v[0] += (r0.x + r1.x + r2.x + r3.x) * 0.25f;
-                            v[1] += (r0.y + r1.y + r2.y + r3.y) * 0.25f;
-                            v[2] += (r0.z + r1.z + r2.z + r3.z) * 0.25f;
-                            v[3] += (r0.w + r1.w + r2.w + r3.w) * 0.25f;
-                        } else if (P.res_mode == 3) {
-                            const int Hh = P.H / 2, Wh = P.W / 2;
-                            const float4 t = *reinterpret_cast<const float4*>(
-                                P.res + (((size_t)b * Hh + (y >> 1)) * Wh + (x >> 1)) * P.Cout + n);
-                            v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
-                        }
-                        *reinterpret_cast<float4*>(P.out + q * P.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
-                        if (P.gn_stats) {   // gn_gs in {4, 8, 16, 32}: a float4 never straddles a group
-                            const int g = j / P.gn_gs;
-                            gsum[g] += (v[0] + v[1]) + (v[2] + v[3]);
-                            gsq[g] += (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+                        for (int i = 0; i < 8; ++i) {
+                            const int rw = 4 * i + rr0;              // staged row = tile row quarter*32 + rw
+                            const int m = quarter * 32 + rw;
+                            const int y = ybase + (m >> 3), x = xbase + sub * 8 + (m & 7);
+                            const size_t q = ((size_t)b * P.H + y) * P.W + x;
+                            const float4 t4 = *reinterpret_cast<const float4*>(stg + rw * kStgPitch + cc);
+                            float v[4] = {t4.x + bias4.x, t4.y + bias4.y, t4.z + bias4.z, t4.w + bias4.w};
+                            v[0] += emb4.x; v[1] += emb4.y; v[2] += emb4.z; v[3] += emb4.w;
+                            if (P.res_mode == 1) {
+                                const float4 t = *reinterpret_cast<const float4*>(P.res + q * P.Cout + n);
+                                v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                            } else if (P.res_mode == 2) {
+                                const int W2 = P.W * 2;
+                                const float* rb = P.res + (((size_t)b * P.H * 2 + 2 * y) * W2 + 2 * x) * P.Cout + n;
+                                const float4 r0 = *reinterpret_cast<const float4*>(rb);
+                                const float4 r1 = *reinterpret_cast<const float4*>(rb + P.Cout);
+                                const float4 r2 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout);
+                                const float4 r3 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout + P.Cout);
+                                v[0] += (r0.x + r1.x + r2.x + r3.x) * 0.25f;
+                                v[1] += (r0.y + r1.y + r2.y + r3.y) * 0.25f;
+                                v[2] += (r0.z + r1.z + r2.z + r3.z) * 0.25f;
+                                v[3] += (r0.w + r1.w + r2.w + r3.w) * 0.25f;
+                            } else if (P.res_mode == 3) {
+                                const int Hh = P.H / 2, Wh = P.W / 2;
+                                const float4 t = *reinterpret_cast<const float4*>(
+                                    P.res + (((size_t)b * Hh + (y >> 1)) * Wh + (x >> 1)) * P.Cout + n);
+                                v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                            }
+                            *reinterpret_cast<float4*>(P.out + q * P.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
+                            s1 += (v[0] + v[1]) + (v[2] + v[3]);
+                            s2 += (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
                         }
                     }
+                    __syncwarp();
                 }
-                if (P.gn_stats) {   // warp-uniform branch; all 32 lanes hold pixels of the same sample b
-                    const int ng = 32 / P.gn_gs;
-                    for (int g = 0; g < ng; ++g) {
-                        float s1 = valid ? gsum[g] : 0.f, s2 = valid ? gsq[g] : 0.f;
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                        }
-                        const int grp = (n0 + cb) / P.gn_gs + g;
-                        if (valid && lane == g && n0 + cb + g * P.gn_gs < P.Cout) {
-                            atomicAdd(&P.gn_stats[((size_t)b * 32 + grp) * 2], (double)s1);
-                            atomicAdd(&P.gn_stats[((size_t)b * 32 + grp) * 2 + 1], (double)s2);
-                        }
+                if (P.gn_stats) {   // warp-uniform; all pixels of the CTA's region belong to sample b
+                    // lanes with equal (lane & 7) hold the same channel quad for different pixel rows
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 8);  s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 16); s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                    const int qpg = P.gn_gs >> 2;               // channel quads per group: 1, 2, 4 or 8
+                    for (int o = 1; o < qpg; o <<= 1) {
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                    }
+                    if (nvalid && lane < 8 && (lane % qpg) == 0) {
+                        const int grp = n / P.gn_gs;
+                        atomicAdd(&P.gn_stats[((size_t)b * 32 + grp) * 2], (double)s1);
+                        atomicAdd(&P.gn_stats[((size_t)b * 32 + grp) * 2 + 1], (double)s2);
                     }
                 }
             }
@@ -387,14 +408,15 @@ EncodeTiledFn get_encode3() {
 }
 
 // NHWC activation map: dims (C, W, H, B), box (32 ch, 8 px, rows, 1)
-int make_act_map3(CUtensorMap* m, const float* p, int C, int W, int H, int B, int rows) {
+int make_act_map3(CUtensorMap* m, const void* p, int f16, int C, int W, int H, int B, int rows) {
     EncodeTiledFn enc = get_encode3();
     if (!enc) { anoddpm_set_error("cuTensorMapEncodeTiled entry point not available"); return ANODDPM_ERR_CUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    cuuint32_t box[4] = {(cuuint32_t)kBK, 8u, (cuuint32_t)rows, 1u};
+    const cuuint64_t es = f16 ? 2 : 4;
+    cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+    cuuint32_t box[4] = {(cuuint32_t)(f16 ? 64 : 32), 8u, (cuuint32_t)rows, 1u};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p), dims, strides, box, estr,
+    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(p), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -404,14 +426,15 @@ int make_act_map3(CUtensorMap* m, const float* p, int C, int W, int H, int B, in
     return ANODDPM_OK;
 }
 
-int make_w_map3(CUtensorMap* m, const float* p, int Ktot, int Cout, int rows) {
+int make_w_map3(CUtensorMap* m, const void* p, int f16, int Ktot, int Cout, int rows) {
     EncodeTiledFn enc = get_encode3();
     if (!enc) { anoddpm_set_error("cuTensorMapEncodeTiled entry point not available"); return ANODDPM_ERR_CUDA; }
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
-    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 4};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)rows};
+    const cuuint64_t es = f16 ? 2 : 4;
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * es};
+    cuuint32_t box[2] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), dims, strides, box, estr,
+    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(p), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -428,7 +451,8 @@ extern "C" int anoddpm_conv_tc3_supported(const anoddpm_conv_desc* d) {
     if (!d) return 0;
     if (d->ksize != 3) return 0;
     if (d->H % 16 || d->W % 16) return 0;
-    if (d->Ca % kBK || d->Cr1 % kBK || d->Cr2 % kBK) return 0;
+    const int ke = d->operand_f16 ? 64 : 32;
+    if (d->Ca % ke || d->Cr1 % ke || d->Cr2 % ke) return 0;
     if (d->Cout % 16) return 0;
     if (d->Cout > 128 && d->Cout % 128) return 0;
     return 1;
@@ -442,15 +466,17 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     P.M = d->B * d->H * d->W; P.H = d->H; P.W = d->W; P.Cout = d->Cout;
     P.emb_stride = d->emb_stride; P.res_mode = d->res_mode;
     P.Ca = d->Ca;
-    P.chunks_a = d->Ca / kBK;
-    P.chunks_r1 = d->Cr1 / kBK;
-    P.chunks_r2 = d->Cr2 / kBK;
+    const int f16 = d->operand_f16 ? 1 : 0;
+    P.ke = f16 ? 64 : 32;
+    P.chunks_a = d->Ca / P.ke;
+    P.chunks_r1 = d->Cr1 / P.ke;
+    P.chunks_r2 = d->Cr2 / P.ke;
     P.BN = d->Cout < 128 ? d->Cout : 128;
     const int acc_cols = kAccStages * 2 * P.BN;
     P.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
     const int Ktot = 9 * d->Ca + d->Cr1 + d->Cr2;
-    const int b_bytes = (P.BN / 2) * kBK * 4;
-    int stages = (200 * 1024) / (kABytes + 3 * b_bytes);
+    const int b_bytes = (P.BN / 2) * kRowBytes;
+    int stages = (204 * 1024) / (kABytes + 3 * b_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     P.stages = stages;
     P.n_tiles_n = adp_ceil_div(d->Cout, P.BN);
@@ -467,21 +493,23 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
 
     CUtensorMap ma, m1, m2, mw;
     int rc;
-    if ((rc = make_act_map3(&ma, d->a, d->Ca, d->W, d->H, d->B, kSubRows))) return rc;
+    if ((rc = make_act_map3(&ma, d->a, f16, d->Ca, d->W, d->H, d->B, kSubRows))) return rc;
     m1 = ma; m2 = ma;
-    if (d->r1 && (rc = make_act_map3(&m1, d->r1, d->Cr1, d->W, d->H, d->B, 16))) return rc;
-    if (d->r2 && (rc = make_act_map3(&m2, d->r2, d->Cr2, d->W, d->H, d->B, 16))) return rc;
-    if ((rc = make_w_map3(&mw, d->w, Ktot, d->Cout, P.BN / 2))) return rc;
+    if (d->r1 && (rc = make_act_map3(&m1, d->r1, f16, d->Cr1, d->W, d->H, d->B, 16))) return rc;
+    if (d->r2 && (rc = make_act_map3(&m2, d->r2, f16, d->Cr2, d->W, d->H, d->B, 16))) return rc;
+    if ((rc = make_w_map3(&mw, d->w, f16, Ktot, d->Cout, P.BN / 2))) return rc;
 
-    const size_t smem = (size_t)stages * (kABytes + 3 * b_bytes) + (2 * kMaxStages + 2 * kAccStages) * 8 + 16 + 1024;
+    const size_t smem = (size_t)stages * (kABytes + 3 * b_bytes) + 256 + 4 * 32 * kStgPitch * 4 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const int sms = 148;
     const int n_clusters = P.n_tiles < sms / 2 ? P.n_tiles : sms / 2;
-    conv_tc3_kernel<<<dim3(2 * n_clusters), kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, P);
+    if (f16) conv_tc3_kernel<true><<<dim3(2 * n_clusters), kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, P);
+    else conv_tc3_kernel<false><<<dim3(2 * n_clusters), kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, P);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }

@@ -7,6 +7,7 @@
 // strict-parity mode (fp32 multiplicands) and the path for shapes the tensor-core tiles do not take.
 #include "common.cuh"
 #include "anoddpm_b200.h"
+#include <cuda_fp16.h>
 #include <math.h>
 
 namespace {
@@ -123,6 +124,20 @@ __device__ __forceinline__ void gn_store(float* p, const float (&v)[V]) {
         p[0] = v[0];
     }
 }
+// fp16 store (round to nearest, saturating to the finite range): `p` indexes HALF elements
+template <int V>
+__device__ __forceinline__ void gn_store_h(__half* p, const float (&v)[V]) {
+    if (V == 4) {
+        const __half2 lo = __floats2half2_rn(fminf(fmaxf(v[0], -65504.f), 65504.f), fminf(fmaxf(v[1 % V], -65504.f), 65504.f));
+        const __half2 hi = __floats2half2_rn(fminf(fmaxf(v[2 % V], -65504.f), 65504.f), fminf(fmaxf(v[3 % V], -65504.f), 65504.f));
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&lo);
+        o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(p) = o;
+    } else {
+        p[0] = __float2half_rn(fminf(fmaxf(v[0], -65504.f), 65504.f));
+    }
+}
 
 template <int V, int NT>   // NT = taps per output pixel: 4 for the avg-pool mode, else 1
 __global__ void __launch_bounds__(256) gn_apply_kernel(float* __restrict__ out, float* __restrict__ raw_out,
@@ -168,8 +183,11 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(float* __restrict__ out, 
             sc[j] = s_rstd[g] * gamma[c + j];
             bi[j] = beta[c + j] - sc[j] * s_mean[g];
         }
-        float* dst = out + (size_t)b * npo * C + c;
-        float* rdst = raw_out ? raw_out + (size_t)b * npo * C + c : nullptr;
+        const bool f16 = rtf32 == 2;     // out_mode: 0 fp32, 1 fp32 rounded to TF32, 2 fp16
+        float* dst = out + (f16 ? 0 : (size_t)b * npo * C + c);
+        float* rdst = raw_out ? raw_out + (f16 ? 0 : (size_t)b * npo * C + c) : nullptr;
+        __half* dsth = reinterpret_cast<__half*>(out) + (size_t)b * npo * C + c;
+        __half* rdsth = reinterpret_cast<__half*>(raw_out) + (size_t)b * npo * C + c;
         constexpr int U = NT == 4 ? 1 : 4;
         for (int pb = p0 + r; pb < p1; pb += rows * U) {
             float v[U][NT][V];   // [pixel in flight][tap][channel]
@@ -213,14 +231,19 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(float* __restrict__ out, 
 #pragma unroll
                     for (int j = 0; j < V; ++j) {
                         if (mode == 1) acc[j] *= 0.25f;
-                        if (rtf32) acc[j] = round_tf32(acc[j]);
+                        if (rtf32 == 1) acc[j] = round_tf32(acc[j]);
                     }
-                    gn_store<V>(dst + (size_t)po * C, acc);
-                    if (rdst) {   // mode 0 only: TF32-rounded concatenated copy of the input for the fused skip conv
-                        float rv[V];
+                    if (f16) gn_store_h<V>(dsth + (size_t)po * C, acc);
+                    else gn_store<V>(dst + (size_t)po * C, acc);
+                    if (rdst) {   // mode 0 only: rounded concatenated copy of the INPUT for the fused skip conv
+                        if (f16) {
+                            gn_store_h<V>(rdsth + (size_t)po * C, v[u][0]);
+                        } else {
+                            float rv[V];
 #pragma unroll
-                        for (int j = 0; j < V; ++j) rv[j] = round_tf32(v[u][0][j]);
-                        gn_store<V>(rdst + (size_t)po * C, rv);
+                            for (int j = 0; j < V; ++j) rv[j] = round_tf32(v[u][0][j]);
+                            gn_store<V>(rdst + (size_t)po * C, rv);
+                        }
                     }
                 }
             }
@@ -262,7 +285,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs A) {
 
     int kbase = 0;  // running offset into the packed K axis
     for (int seg = 0; seg < 3; ++seg) {
-        const float* src = seg == 0 ? d.a : (seg == 1 ? d.r1 : d.r2);
+        const float* src = static_cast<const float*>(seg == 0 ? d.a : (seg == 1 ? d.r1 : d.r2));
         const int Cs = seg == 0 ? d.Ca : (seg == 1 ? d.Cr1 : d.Cr2);
         if (src == nullptr || Cs == 0) continue;
         const int ks = seg == 0 ? d.ksize : 1;
@@ -276,7 +299,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs A) {
                 F4 av = {0.f, 0.f, 0.f, 0.f};
                 if (inb && c0 + lc4 < Cs) av = ld4(arow + c0 + lc4);
                 F4 bv = {0.f, 0.f, 0.f, 0.f};
-                if (nvalid && c0 + lc4 < Cs) bv = ld4(d.w + (size_t)nrow * A.Ktot + kbase + tap * Cs + c0 + lc4);
+                if (nvalid && c0 + lc4 < Cs) bv = ld4(static_cast<const float*>(d.w) + (size_t)nrow * A.Ktot + kbase + tap * Cs + c0 + lc4);
                 __syncthreads();
                 As[lc4 + 0][lp] = av.x; As[lc4 + 1][lp] = av.y; As[lc4 + 2][lp] = av.z; As[lc4 + 3][lp] = av.w;
                 Bs[lc4 + 0][lp] = bv.x; Bs[lc4 + 1][lp] = bv.y; Bs[lc4 + 2][lp] = bv.z; Bs[lc4 + 3][lp] = bv.w;
@@ -510,7 +533,11 @@ __global__ void __launch_bounds__(128) attention_kernel(float* __restrict__ out,
         }
 #pragma unroll
         for (int qi = 0; qi < QB; ++qi)
-            if (t0 + qi < T) out[((size_t)b * T + t0 + qi) * C + h * ch + c] = rtf32 ? round_tf32(acc[qi]) : acc[qi];
+            if (t0 + qi < T) {
+                const size_t o = ((size_t)b * T + t0 + qi) * C + h * ch + c;
+                if (rtf32 == 2) reinterpret_cast<__half*>(out)[o] = __float2half_rn(fminf(fmaxf(acc[qi], -65504.f), 65504.f));
+                else out[o] = rtf32 == 1 ? round_tf32(acc[qi]) : acc[qi];
+            }
     }
 }
 
@@ -565,9 +592,11 @@ extern "C" int anoddpm_gn_stats(double* stats, const float* x1, int C1, const fl
     return ANODDPM_OK;
 }
 
-extern "C" int anoddpm_gn_apply(float* out, float* raw_out, const float* x1, int C1, const float* x2, int C2,
+extern "C" int anoddpm_gn_apply(void* out_v, void* raw_out_v, const float* x1, int C1, const float* x2, int C2,
                                 const double* stats, const float* gamma, const float* beta, int B, int H, int W,
                                 int groups, float eps, int do_silu, int mode, int rtf32, void* stream) {
+    float* out = static_cast<float*>(out_v);
+    float* raw_out = static_cast<float*>(raw_out_v);
     ADP_REQUIRE(out && x1 && stats && gamma && beta && B > 0 && B <= 65535 && H > 0 && W > 0,
                 "anoddpm_gn_apply: bad arguments");
     ADP_REQUIRE((C2 == 0) == (x2 == nullptr), "anoddpm_gn_apply: x2/C2 mismatch");
@@ -576,6 +605,7 @@ extern "C" int anoddpm_gn_apply(float* out, float* raw_out, const float* x1, int
     ADP_REQUIRE(mode >= 0 && mode <= 2, "anoddpm_gn_apply: bad mode %d", mode);
     ADP_REQUIRE(mode != 1 || (H % 2 == 0 && W % 2 == 0), "anoddpm_gn_apply: avg-pool needs even H, W");
     ADP_REQUIRE(raw_out == nullptr || mode == 0, "anoddpm_gn_apply: raw_out needs mode 0");
+    ADP_REQUIRE(rtf32 >= 0 && rtf32 <= 2, "anoddpm_gn_apply: out_mode must be 0 (fp32), 1 (tf32-rounded fp32) or 2 (fp16)");
     const int V = (gn_vec(C1, C2, groups, x1, x2) == 4 && al16(out) && (!raw_out || al16(raw_out))) ? 4 : 1;
     const int Ho = mode == 1 ? H / 2 : (mode == 2 ? H * 2 : H), Wo = mode == 1 ? W / 2 : (mode == 2 ? W * 2 : W);
     const int npo = Ho * Wo;
@@ -608,6 +638,7 @@ extern "C" int anoddpm_conv(const anoddpm_conv_desc* d, void* stream) {
     ADP_REQUIRE(al16(d->out) && al16(d->a) && al16(d->w) && (!d->r1 || al16(d->r1)) && (!d->r2 || al16(d->r2)) &&
                     (!d->res || al16(d->res)),
                 "anoddpm_conv: pointers must be 16-byte aligned");
+    ADP_REQUIRE(!d->operand_f16 || d->impl == 2 || d->impl == 3, "anoddpm_conv: fp16 operands need impl 2 or 3");
     if (d->impl == 3) return anoddpm_conv_tc3(d, stream);
     ADP_REQUIRE(d->gn_stats == nullptr, "anoddpm_conv: fused GroupNorm statistics need impl 3");
     if (d->impl == 1) return anoddpm_conv_tc(d, stream);
@@ -656,8 +687,9 @@ extern "C" int anoddpm_conv_head(float* out, const float* a, const float* w, con
     return ANODDPM_OK;
 }
 
-extern "C" int anoddpm_attention(float* out, const float* qkv, int B, int T, int C, int heads, int rtf32,
+extern "C" int anoddpm_attention(void* out_v, const float* qkv, int B, int T, int C, int heads, int rtf32,
                                  void* stream) {
+    float* out = static_cast<float*>(out_v);
     ADP_REQUIRE(out && qkv && B > 0 && T > 0 && C > 0 && heads > 0 && C % heads == 0, "anoddpm_attention: bad arguments");
     ADP_REQUIRE(B <= 65535 && heads <= 65535, "anoddpm_attention: batch/heads too large");
     const int ch = C / heads;

@@ -47,17 +47,21 @@ class _Conv:
         self.ksize = ksize
         self.cache = {}
 
-    def packed(self, impl):
-        if impl not in self.cache:
+    def packed(self, impl, f16=False):
+        """impl 0: exact fp32; impl >= 1: TF32-rounded fp32, or IEEE fp16 (round to nearest) when f16."""
+        key = "f16" if f16 else ("tf32" if impl >= 1 else "f32")
+        if key not in self.cache:
             parts = [pack_conv_weight(w.detach()) for w in self.weights]
             w = torch.cat(parts, dim=1).contiguous().float()
-            if impl >= 1:
+            if key == "tf32":
                 round_tf32_(w)
+            elif key == "f16":
+                w = w.clamp(-65504.0, 65504.0).half().contiguous()
             b = self.biases[0].detach().float()
             for extra in self.biases[1:]:
                 b = b + extra.detach().float()
-            self.cache[impl] = (w, b.contiguous())
-        return self.cache[impl]
+            self.cache[key] = (w, b.contiguous())
+        return self.cache[key]
 
 
 class UNetEngine:
@@ -155,26 +159,30 @@ class UNetEngine:
         self.launches += 1
 
     def _gn_apply(self, site, srcs, gn, B, H, W, silu, mode, rtf32, want_raw=False):
+        """rtf32 = output mode: 0 fp32, 1 fp32 rounded to TF32, 2 fp16."""
         x1 = srcs[0]
         x2 = srcs[1] if len(srcs) > 1 else None
         C = x1.shape[-1] + (x2.shape[-1] if x2 is not None else 0)
         Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
-        out = torch.empty((B, Ho, Wo, C), device=x1.device, dtype=torch.float32)
-        raw = torch.empty((B, H, W, C), device=x1.device, dtype=torch.float32) if want_raw else None
+        odt = torch.float16 if rtf32 == 2 else torch.float32
+        out = torch.empty((B, Ho, Wo, C), device=x1.device, dtype=odt)
+        raw = torch.empty((B, H, W, C), device=x1.device, dtype=odt) if want_raw else None
         call("anoddpm_gn_apply", ptr(out), ptr(raw), ptr(x1), x1.shape[-1], ptr(x2), x2.shape[-1] if x2 is not None else 0,
              ptr(self.stats[site]), ptr(gn.weight), ptr(gn.bias), B, H, W, 32, float(gn.eps), int(silu), mode,
              int(rtf32), stream())
         self.launches += 1
         return (out, raw) if want_raw else out
 
-    def _conv(self, site, a, B, H, W, cout, r=(), emb=None, res=None, res_mode=0, stats_site=None):
+    def _conv(self, site, a, B, H, W, cout, plan, r=(), emb=None, res=None, res_mode=0, stats_site=None):
+        impl, f16 = plan
         d = ConvDesc()
         d.B, d.H, d.W = B, H, W
         d.Ca, d.Cout, d.ksize = a.shape[-1], cout, site.ksize
         d.Cr1 = r[0].shape[-1] if len(r) > 0 else 0
         d.Cr2 = r[1].shape[-1] if len(r) > 1 else 0
-        impl = self._pick_impl(d)
-        w, b = site.packed(impl)
+        d.operand_f16 = 1 if f16 else 0
+        assert a.dtype == (torch.float16 if f16 else torch.float32)
+        w, b = site.packed(impl, f16)
         out = torch.empty((B, H, W, cout), device=a.device, dtype=torch.float32)
         d.out, d.a, d.w, d.bias = out.data_ptr(), a.data_ptr(), w.data_ptr(), b.data_ptr()
         d.r1 = r[0].data_ptr() if len(r) > 0 else None
@@ -195,62 +203,73 @@ class UNetEngine:
         call("anoddpm_conv", ctypes.byref(d), stream())
         self.launches += 1
         self.tc_convs += 1 if impl else 0
+        self.f16_convs += 1 if f16 else 0
         return out
 
-    def _pick_impl(self, d):
+    def _plan(self, H, W, Ca, Cr, cout, ksize):
+        """(impl, f16) for a conv with main source Ca channels and (single, concatenated) skip source Cr channels."""
         L = _lib.lib()
         if not self.use_tc:
-            return 0
-        if self.tc_impl == 3 and L.anoddpm_conv_tc3_supported(ctypes.byref(d)):
-            return 3
-        if L.anoddpm_conv_tc_supported(ctypes.byref(d)):
-            return min(self.tc_impl, 2)
-        return 0
-
-    def _tc_ok(self, C, H, W):
-        """Will the conv consuming a (.., H, W, C) activation run on tensor cores? (decides the TF32 rounding)"""
-        if not self.use_tc:
-            return False
+            return 0, False
         d = ConvDesc()
-        d.B, d.H, d.W, d.Ca, d.Cr1, d.Cr2, d.Cout, d.ksize = 1, H, W, C, 0, 0, 32, 3
-        return bool(_lib.lib().anoddpm_conv_tc_supported(ctypes.byref(d)))
+        d.B, d.H, d.W, d.Ca, d.Cr1, d.Cr2, d.Cout, d.ksize = 1, H, W, Ca, Cr, 0, cout, ksize
+        f16 = self.allow_f16 and Ca % 64 == 0 and Cr % 64 == 0
+        d.operand_f16 = 1 if f16 else 0
+        if self.tc_impl == 3 and L.anoddpm_conv_tc3_supported(ctypes.byref(d)):
+            return 3, f16
+        if L.anoddpm_conv_tc_supported(ctypes.byref(d)):
+            impl = min(self.tc_impl, 2)
+            return impl, (f16 and impl == 2)
+        return 0, False
+
+    @staticmethod
+    def _out_mode(plan):
+        impl, f16 = plan
+        return 2 if f16 else (1 if impl else 0)
 
     # ------------------------------------------------------------------ blocks
     def _res(self, e, srcs, B, H, W, next_site=None):
         mode = _MODE[e["mode"]]
         Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
+        c_src = sum(t.shape[-1] for t in srcs)
+        plan1 = self._plan(Ho, Wo, e["cin"], 0, e["cout"], 3)
+        plan2 = self._plan(Ho, Wo, e["cout"], c_src if e["skip_conv"] else 0, e["cout"], 3)
         self._gn_stats(e["s1"], srcs, B, H * W)
-        tc1 = self._tc_ok(e["cin"], Ho, Wo)
-        # tensor-core path: the fused 1x1 skip conv reads a TF32-rounded, concatenated copy of x written by the same
-        # pass that normalises x (rounding to nearest instead of the MMA's operand truncation)
+        # tensor-core path: the fused 1x1 skip conv reads a rounded (TF32 / fp16), channel-concatenated copy of x that
+        # is written by the same pass that normalises x (round to nearest instead of the MMA's operand truncation)
         raw = None
-        if e["skip_conv"] and tc1 and self._tc_ok(e["cout"], Ho, Wo):
-            a1, raw = self._gn_apply(e["s1"], srcs, e["gn1"], B, H, W, True, mode, tc1, want_raw=True)
+        if e["skip_conv"] and plan2[0] and self._out_mode(plan1) == self._out_mode(plan2):
+            a1, raw = self._gn_apply(e["s1"], srcs, e["gn1"], B, H, W, True, mode, self._out_mode(plan1), want_raw=True)
         else:
-            a1 = self._gn_apply(e["s1"], srcs, e["gn1"], B, H, W, True, mode, tc1)
+            if e["skip_conv"] and plan2[1]:
+                plan2 = (plan2[0], False)      # no fp16 raw copy available: run conv2 with TF32 operands
+            a1 = self._gn_apply(e["s1"], srcs, e["gn1"], B, H, W, True, mode, self._out_mode(plan1))
         emb = self.emb_all[:, e["emb_off"]:]
-        h = self._conv(e["conv1"], a1, B, Ho, Wo, e["cout"], emb=emb, stats_site=e["s2"])
+        h = self._conv(e["conv1"], a1, B, Ho, Wo, e["cout"], plan1, emb=emb, stats_site=e["s2"])
         del a1
         self._gn_stats(e["s2"], [h], B, Ho * Wo)
-        a2 = self._gn_apply(e["s2"], [h], e["gn2"], B, Ho, Wo, True, 0, self._tc_ok(e["cout"], Ho, Wo))
+        a2 = self._gn_apply(e["s2"], [h], e["gn2"], B, Ho, Wo, True, 0, self._out_mode(plan2))
         del h
         if e["skip_conv"]:
-            return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], r=([raw] if raw is not None else srcs),
+            return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], plan2, r=([raw] if raw is not None else srcs),
                               stats_site=next_site), Ho, Wo
         assert len(srcs) == 1
-        return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], res=srcs[0], res_mode=_RES_FOR_MODE[e["mode"]],
+        return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], plan2, res=srcs[0], res_mode=_RES_FOR_MODE[e["mode"]],
                           stats_site=next_site), Ho, Wo
 
     def _attn(self, e, x, B, H, W):
         C, T = e["c"], H * W
+        plan_qkv = self._plan(H, W, C, 0, 3 * C, 1)
+        plan_proj = self._plan(H, W, C, 0, C, 1)
         self._gn_stats(e["s"], [x], B, T)
-        xn = self._gn_apply(e["s"], [x], e["gn"], B, H, W, False, 0, self._tc_ok(C, H, W))
-        qkv = self._conv(e["qkv"], xn, B, H, W, 3 * C)
+        xn = self._gn_apply(e["s"], [x], e["gn"], B, H, W, False, 0, self._out_mode(plan_qkv))
+        qkv = self._conv(e["qkv"], xn, B, H, W, 3 * C, plan_qkv)
         del xn
-        a = torch.empty((B, H, W, C), device=x.device, dtype=torch.float32)
-        call("anoddpm_attention", ptr(a), ptr(qkv), B, T, C, e["heads"], int(self._tc_ok(C, H, W)), stream())
+        om = self._out_mode(plan_proj)
+        a = torch.empty((B, H, W, C), device=x.device, dtype=torch.float16 if om == 2 else torch.float32)
+        call("anoddpm_attention", ptr(a), ptr(qkv), B, T, C, e["heads"], om, stream())
         self.launches += 1
-        return self._conv(e["proj"], a, B, H, W, C, res=x, res_mode=1)
+        return self._conv(e["proj"], a, B, H, W, C, plan_proj, res=x, res_mode=1)
 
     @staticmethod
     def _first_site(entry):
@@ -282,11 +301,15 @@ class UNetEngine:
         if p0.device != x.device:
             raise RuntimeError(f"UNetModel parameters are on {p0.device} but the input is on {x.device}")
         self._refresh()
-        if m.conv_impl not in ("tc", "tc2", "tc1", "exact"):
-            raise ValueError(f"conv_impl must be 'tc', 'tc2', 'tc1' or 'exact', got {m.conv_impl!r}")
+        if m.conv_impl not in ("tc", "tc_tf32", "tc2", "tc1", "exact"):
+            raise ValueError(f"conv_impl must be 'tc', 'tc_tf32', 'tc2', 'tc1' or 'exact', got {m.conv_impl!r}")
         self.use_tc = m.conv_impl != "exact"
-        # tc: halo-reuse CTA-pair kernel (impl 3) where it applies, else impl 2; tc2: persistent CTA pairs; tc1: single-CTA tiles
-        self.tc_impl = {"tc": 3, "tc2": 2, "tc1": 1, "exact": 0}[m.conv_impl]
+        # tc / tc_tf32: halo-reuse CTA-pair kernel (impl 3) where it applies, else impl 2; tc2: persistent CTA pairs;
+        # tc1: single-CTA tiles.  "tc" additionally feeds fp16 operands (kind::f16: TF32's 10-bit mantissa at twice
+        # the rate and half the bytes) wherever every channel count is a multiple of 64; the others use kind::tf32.
+        self.tc_impl = {"tc": 3, "tc_tf32": 3, "tc2": 2, "tc1": 1, "exact": 0}[m.conv_impl]
+        self.allow_f16 = m.conv_impl == "tc"
+        self.f16_convs = 0
         self.stats_ready = set()
         self.fused_stats = 0
         self.tc_convs = 0
@@ -334,7 +357,7 @@ class UNetEngine:
             h, H, W = self._entry(entry, [h, s], B, H, W, self.head["s"] if i + 1 == len(self.up) else None)
         hd = self.head
         self._gn_stats(hd["s"], [h], B, H * W)
-        a = self._gn_apply(hd["s"], [h], hd["gn"], B, H, W, True, 0, False)
+        a = self._gn_apply(hd["s"], [h], hd["gn"], B, H, W, True, 0, 0)
         out = torch.empty((B, m.out_channels, H, W), device=dev, dtype=torch.float32)
         call("anoddpm_conv_head", ptr(out), ptr(a), ptr(self.head_w), ptr(hd["conv"].bias), B, a.shape[-1], H, W,
              m.out_channels, stream())

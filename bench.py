@@ -143,6 +143,7 @@ def run_native(args):
 
     clocks = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    host_enqueue_ms = None
     if args.full_chain:
         for _ in range(args.warmup):
             chain(x_host, T_DISTANCE)
@@ -162,7 +163,9 @@ def run_native(args):
         torch.cuda.synchronize(); D.barrier()
         clocks.start(); l0, e0 = launches["n"], eng.launches
         ev0.record()
+        h0 = time.perf_counter()
         x = reverse_steps(x, T_DISTANCE - 1 - args.warmup, args.steps)
+        host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / args.steps   # host time to ENQUEUE one step (no sync)
         ev1.record(); torch.cuda.synchronize(); D.barrier()
         ms = ev0.elapsed_time(ev1)
         steps_per_image = float(T_DISTANCE)
@@ -191,7 +194,7 @@ def run_native(args):
 
     out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "tf32" if model.conv_impl != "exact" else "f32", "data": "synthetic",
+           "vs_baseline": None, "dtype": {"tc": "f16 operands (10-bit mantissa, = TF32 precision) / f32 accumulate", "exact": "f32"}.get(model.conv_impl, "tf32"), "data": "synthetic",
            "config": {"workload": "BASELINE configs[2] per GPU: forward_backward 256x256x1 bs=32 T=1000 t_distance=800 "
                                   "simplex(6,0.8,64), UNet 256/base128/attn16,8/2 heads (554.5 GFLOP/image/step); "
                                   + ("step = one full 800-step chain" if args.full_chain else
@@ -200,7 +203,8 @@ def run_native(args):
                       "global_batch": world * B, "per_gpu_batch": B, "t_distance": T_DISTANCE,
                       "parallelism": f"dp{world} (images sharded by index, no collective in the loop)",
                       "l2": "working set per step >> 126 MB L2 (no explicit flush)", "conv_impl": model.conv_impl},
-           "e2e": e2e, "gpu_launches": int(n_launch), "clocks": clk, "tc_convs_per_forward": eng.tc_convs}
+           "e2e": e2e, "gpu_launches": int(n_launch), "clocks": clk, "tc_convs_per_forward": eng.tc_convs,
+           "host_enqueue_ms_per_step": host_enqueue_ms, "fused_gn_stats_per_forward": getattr(eng, "fused_stats", 0)}
 
     if rank == 0:
         out["roofline"] = roofline(model, dev, B)
@@ -218,16 +222,20 @@ def roofline(model, dev, B):
     pk = peaks()
     res = []
     tot_flop, tot_ms = 0.0, 0.0
-    impl = {"tc": 3, "tc2": 2, "tc1": 1}.get(model.conv_impl, 0)
+    impl = {"tc": 3, "tc_tf32": 3, "tc2": 2, "tc1": 1}.get(model.conv_impl, 0)
+    f16 = model.conv_impl == "tc"
     for (Ci, Co, HW, count) in ((128, 128, 256, 9), (256, 128, 256, 3), (128, 128, 128, 9)):
         a = round_tf32_(torch.randn(B, HW, HW, Ci, device=dev))
         w = round_tf32_(torch.randn(Co, 9 * Ci, device=dev) * 0.03)
+        if f16:
+            a, w = a.half(), w.half()
         bias = torch.zeros(Co, device=dev)
         out = torch.empty(B, HW, HW, Co, device=dev)
         d = _lib.ConvDesc()
         d.out, d.a, d.w, d.bias = out.data_ptr(), a.data_ptr(), w.data_ptr(), bias.data_ptr()
         d.B, d.H, d.W, d.Ca, d.Cout, d.ksize, d.impl = B, HW, HW, Ci, Co, 3, impl
         d.gn_stats = None
+        d.operand_f16 = 1 if f16 else 0
         for _ in range(3):
             _lib.call("anoddpm_conv", ctypes.byref(d), _lib.stream())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -243,10 +251,10 @@ def roofline(model, dev, B):
         tot_ms += ms * count
         del a, w, out
     achieved = tot_flop / tot_ms / 1e9
-    return {"bound": "tensor", "kernel": {3: "conv_tc3_kernel (tcgen05.mma.cta_group::2 kind::tf32, halo-reuse persistent CTA pairs, TMA-fed implicit GEMM)", 2: "conv_tc2_kernel (tcgen05.mma.cta_group::2 kind::tf32, persistent CTA pairs, TMA-fed implicit GEMM)", 1: "conv_tc_kernel (tcgen05.mma kind::tf32, TMA-fed implicit GEMM)", 0: "conv_simt_kernel"}[impl],
+    return {"bound": "tensor", "kernel": {3: "conv_tc3_kernel (tcgen05.mma.cta_group::2 kind::%s, halo-reuse persistent CTA pairs, TMA-fed implicit GEMM)" % ("f16" if f16 else "tf32"), 2: "conv_tc2_kernel (tcgen05.mma.cta_group::2 kind::tf32, persistent CTA pairs, TMA-fed implicit GEMM)", 1: "conv_tc_kernel (tcgen05.mma kind::tf32, TMA-fed implicit GEMM)", 0: "conv_simt_kernel"}[impl],
             "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-            "peak_note": f"dense bf16 cuBLAS sustained, {pk['src']} (MEASURED_PEAKS.json); kind::tf32 issues at half the bf16 rate, "
-                         f"so frac of the tf32 rate = {achieved / (pk['bf16_sustained'] / 2):.3f}",
+            "peak_note": f"dense bf16 cuBLAS sustained, {pk['src']} (MEASURED_PEAKS.json)" + ("; kind::f16 operands issue at the bf16 rate" if f16 else
+                         f"; kind::tf32 issues at half the bf16 rate, so frac of the tf32 rate = {achieved / (pk['bf16_sustained'] / 2):.3f}"),
             "traffic": None, "per_shape": res,
             "algorithmic": "2*M*N*K flop per launch, M=B*H*W, N=Cout, K=9*Cin; weighted by launches per forward"}
 
@@ -313,7 +321,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU (BASELINE: 32)")
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--full-chain", action="store_true", help="a step = one whole 800-step chain")
-    ap.add_argument("--conv-impl", default=None, choices=[None, "tc", "tc2", "tc1", "exact"])
+    ap.add_argument("--conv-impl", default=None, choices=[None, "tc", "tc_tf32", "tc2", "tc1", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":

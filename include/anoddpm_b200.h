@@ -94,10 +94,11 @@ int anoddpm_gn_stats(double* stats /* B x groups x 2 */, const float* x1, int C1
 
 /* out = resample(act(GroupNorm(x))) on NHWC: act = SiLU if silu; mode 0 same, 1 avg-pool 2x2, 2 nearest x2
  * (UNet.py:202-210: GN -> SiLU -> h_upd, in that order).  stats from anoddpm_gn_stats over n = HW*(C/groups).
- * round_tf32: round results to TF32 (rna) for the tensor-core conv that consumes them.
+ * round_tf32 = output mode: 0 fp32; 1 fp32 rounded to TF32 (rna) for a kind::tf32 conv; 2 IEEE fp16 (rn, saturating;
+ * `out` / `raw_out` then point to half elements) for a kind::f16 conv.
  * raw_out (optional, mode 0 only): also writes the TF32-rounded, channel-concatenated copy of the INPUT, which the
  * fused 1x1 skip convolution of the same ResBlock reads as its K-major operand (one pass over x for both). */
-int anoddpm_gn_apply(float* out, float* raw_out, const float* x1, int C1, const float* x2, int C2,
+int anoddpm_gn_apply(void* out, void* raw_out, const float* x1, int C1, const float* x2, int C2,
                      const double* stats, const float* gamma, const float* beta, int B, int H, int W, int groups,
                      float eps, int silu, int mode, int round_tf32, void* stream);
 
@@ -114,10 +115,10 @@ int anoddpm_gn_apply(float* out, float* raw_out, const float* x1, int C1, const 
  *     tile) -- 3x3 convs with H, W % 16 == 0; cuts L2->SM operand traffic ~2.5x.  The fast path. */
 typedef struct anoddpm_conv_desc {
     float* out;
-    const float* a;
-    const float* r1;
-    const float* r2;
-    const float* w;
+    const void* a;     /* fp32, or fp16 when operand_f16 (same for r1, r2, w) */
+    const void* r1;
+    const void* r2;
+    const void* w;
     const float* bias;
     const float* emb;
     const float* res;
@@ -127,6 +128,8 @@ typedef struct anoddpm_conv_desc {
     int emb_stride;
     int res_mode;
     int impl;
+    int operand_f16;    /* impl 2/3 only: a, r1, r2, w hold IEEE fp16 (tcgen05 kind::f16, fp32 accumulate): the same 10-bit
+                           mantissa as TF32 at twice the tensor rate and half the operand bytes; channels % 64 == 0 */
     double* gn_stats;   /* optional, impl 3 only: += (sum, sum of squares) of the OUTPUT per (sample, group of Cout/32
                            channels), layout [B][32][2] fp64 = the input anoddpm_gn_apply expects for the next GroupNorm */
 } anoddpm_conv_desc;
@@ -145,8 +148,8 @@ int anoddpm_conv_head(float* out_nchw, const float* a_nhwc, const float* w_packe
 
 /* QKV attention on qkv[B][T][3*C] (channel layout [head][q|k|v][ch], UNet.py:146-147):
  * out[b][t][h*ch + c] = sum_s softmax_s( (q_t . k_s) / sqrt(ch) ) v_s[c].   UNet.py:137-153. */
-int anoddpm_attention(float* out /* B x T x C */, const float* qkv, int B, int T, int C, int heads, int round_tf32,
-                      void* stream);
+int anoddpm_attention(void* out /* B x T x C; fp32, or fp16 when out_mode == 2 */, const float* qkv, int B, int T, int C,
+                      int heads, int out_mode /* as anoddpm_gn_apply */, void* stream);
 
 #ifdef __cplusplus
 }
