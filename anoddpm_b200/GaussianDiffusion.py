@@ -146,14 +146,23 @@ class GaussianDiffusionModel:
         super().__init__()
         if noise == "gauss":
             self.noise_fn = lambda x, t: torch.randn_like(x)
+            self._noise_kind = "gauss"
         else:
             self.simplex = Simplex_CLASS()
             if noise == "simplex_randParam":
                 self.noise_fn = lambda x, t: generate_simplex_noise(self.simplex, x, t, True, in_channels=img_channels)
+                self._noise_kind = "simplex_randParam"
             elif noise == "random":
                 self.noise_fn = lambda x, t: random_noise(self.simplex, x, t)
+                self._noise_kind = "random"
             else:
                 self.noise_fn = lambda x, t: generate_simplex_noise(self.simplex, x, t, False, in_channels=img_channels)
+                self._noise_kind = "simplex"
+        self._default_noise_fn = self.noise_fn
+        # CUDA-graph fast path of the reverse loop (see _reverse_loop); seeds of step `i` come from simplex_seed_source
+        self.use_cuda_graphs = os.environ.get("ANODDPM_CUDA_GRAPHS", "1") == "1"
+        self.simplex_seed_source = None      # optional callable(step_index, n) -> list of n seeds (default: np.random)
+        self._graphs = {}
 
         self.img_size = img_size
         self.img_channels = img_channels
@@ -318,13 +327,128 @@ class GaussianDiffusionModel:
             x = self.sample_q(x, t_tensor, self.noise_fn(x, t_tensor).float())
             if see_whole_sequence == "half":
                 seq.append(x.cpu().detach())
+        if not see_whole_sequence:
+            return self.reverse_steps(model, x, int(t_distance) - 1, int(t_distance), denoise_fn).detach()
         for t in range(int(t_distance) - 1, -1, -1):
             t_batch = torch.full((B,), t, device=x.device, dtype=torch.int64)
             with torch.no_grad():
                 x = self.sample_p(model, x, t_batch, denoise_fn)["sample"]
-            if see_whole_sequence:
-                seq.append(x.cpu().detach())
-        return x.detach() if not see_whole_sequence else seq
+            seq.append(x.cpu().detach())
+        return seq
+
+    # ---- the reverse loop (GaussianDiffusion.py:351-357), optionally as a replayed CUDA graph ------------------
+    def _graph_mode(self, model, x, denoise_fn):
+        """Which noise source a captured step may use, or None if this call must run eagerly."""
+        from .UNet import UNetModel
+        if not (self.use_cuda_graphs and isinstance(model, UNetModel) and isinstance(x, torch.Tensor) and x.is_cuda
+                and x.dim() == 4 and type(denoise_fn) == str):
+            return None
+        if denoise_fn in ("gauss", "random"):
+            return "gauss"
+        if denoise_fn == "noise_fn":
+            if self.noise_fn is not self._default_noise_fn:
+                return None                      # user-supplied noise function: arbitrary python, cannot be captured
+            return {"gauss": "gauss", "simplex": "simplex", "simplex_randParam": "simplex_randParam"}.get(self._noise_kind)
+        return "simplex"                         # any other string -> default-parameter simplex (reference :309-310)
+
+    def _draw_step_seeds(self, step, n):
+        """n = B*C seeds of one noise call (b-major, c-minor)."""
+        if self.simplex_seed_source is not None:
+            seeds = list(self.simplex_seed_source(step, n))
+            if len(seeds) != n:
+                raise ValueError("simplex_seed_source returned the wrong number of seeds")
+            return seeds
+        return draw_simplex_seeds(n)
+
+    @torch.no_grad()
+    def reverse_steps(self, model, x, t_start, n_steps, denoise_fn="gauss"):
+        """n_steps reverse steps t_start, t_start-1, ... (the loop body of forward_backward).  On a CUDA UNetModel with
+        a capturable noise source the step (UNet forward + noise + fused posterior + t -= 1) is captured ONCE as a CUDA
+        graph and replayed: no per-step host work (simplex seed tables of all steps are built and uploaded up front,
+        consuming the host RNG in the same order as the step-by-step loop)."""
+        mode = self._graph_mode(model, x, denoise_fn)
+        if mode is None or n_steps <= 2:
+            for t in range(int(t_start), int(t_start) - int(n_steps), -1):
+                t_batch = torch.full((x.shape[0],), t, device=x.device, dtype=torch.int64)
+                x = self.sample_p(model, x, t_batch, denoise_fn)["sample"]
+            return x
+        return self._graph_loop(model, x, int(t_start), int(n_steps), mode)
+
+    def _graph_loop(self, model, x, t_start, n_steps, mode):
+        x = self._prep(x, "x")
+        B, C, H, W = x.shape
+        dev = x.device
+        eng = model.engine()
+        eng._refresh()
+        key = (id(model), eng._sig, model.conv_impl, (B, C, H, W), str(dev), mode)
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= 4:
+                self._graphs.clear()
+            g = self._capture_step(model, (B, C, H, W), dev, mode)
+            self._graphs[key] = g
+        if mode != "gauss":
+            chans = self.img_channels
+            seeds = []
+            for i in range(n_steps):
+                seeds.extend(self._draw_step_seeds(g["step_base"] + i, B * chans))
+                if mode == "simplex_randParam":
+                    for _ in range(B * chans):
+                        random.choice(_RANDOM_PARAMS)     # drawn and discarded like the reference (SURVEY F7)
+            g["step_base"] += n_steps
+            self.simplex._load_seed(seeds[-1])
+            tabs = torch.from_numpy(init_tables(seeds)).view(n_steps, B * chans * 512)
+            if n_steps > g["tables"].shape[0]:
+                raise RuntimeError("more reverse steps than the captured table buffer holds")
+            g["tables"][:n_steps].copy_(tabs.pin_memory(), non_blocking=True)
+        g["x"].copy_(x)
+        g["t"].fill_(t_start)
+        g["step"].zero_()
+        for _ in range(n_steps):
+            g["graph"].replay()
+        return g["x"].clone()
+
+    def _capture_step(self, model, shape, dev, mode):
+        B, C, H, W = shape
+        chans = self.img_channels
+        tab = self._tables(dev)
+        st = {"x": torch.zeros(shape, device=dev), "t": torch.zeros(B, device=dev, dtype=torch.int64),
+              "step": torch.zeros(1, device=dev, dtype=torch.int64), "step_base": 0,
+              "tables": torch.zeros((self.num_timesteps, B * chans * 512), device=dev, dtype=torch.int16)}
+        x_out = torch.empty(shape, device=dev)
+
+        def step():
+            eps = model.engine().forward(st["x"], st["t"])
+            if mode == "gauss":
+                noise = torch.randn_like(st["x"])
+            else:
+                noise = torch.empty((B, chans, H, W), device=dev, dtype=torch.float32)
+                call("anoddpm_simplex_noise_steps", ptr(noise), B, chans, H, W, ptr(st["tables"]), ptr(st["step"]), 0,
+                     ptr(st["t"]), 6, 0.8, 64.0, stream())
+                if chans != C:
+                    noise = noise.expand(shape).contiguous()
+            call("anoddpm_p_sample", ptr(x_out), None, ptr(st["x"]), ptr(eps), ptr(noise), ptr(st["t"]), ptr(tab[4:]),
+                 self.num_timesteps, B, st["x"].numel() // B, stream())
+            st["x"].copy_(x_out)
+            st["t"].sub_(1)
+            st["step"].add_(1)
+
+        # warm-up on a side stream (sets kernel attributes, fills the engine's weight caches), then capture
+        st["t"].fill_(self.num_timesteps - 1)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        st["t"].fill_(self.num_timesteps - 1)
+        st["step"].zero_()
+        with torch.cuda.graph(graph):
+            step()
+        torch.cuda.synchronize(dev)
+        st["graph"] = graph
+        return st
 
     # aliases named in BASELINE.json's north star
     q_sample = sample_q

@@ -29,6 +29,7 @@ SIGNATURES = {
     "anoddpm_simplex_init": (c_int, [c_i64, c_vp]),
     "anoddpm_simplex_init_batch": (c_int, [c_vp, c_int, c_vp]),
     "anoddpm_simplex_noise": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp, c_int, c_f64, c_f64, c_vp]),
+    "anoddpm_simplex_noise_steps": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_f64, c_f64, c_vp]),
     "anoddpm_simplex_octaves": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_f64, c_f64, c_vp]),
     "anoddpm_simplex_grid3": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
     "anoddpm_simplex_grid2": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp]),

@@ -329,38 +329,48 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         *reinterpret_cast<uint4*>(stg + lane * kStgPitch + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
                     __syncwarp();
                     if (nvalid) {
+                        // two half-passes of 4 staged rows: all residual loads of a half are issued before its first
+                        // store (P.out may alias P.res as far as the compiler knows, so it cannot hoist them itself)
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int rw = 4 * i + rr0;              // staged row = tile row quarter*32 + rw
-                            const int m = quarter * 32 + rw;
-                            const int y = ybase + (m >> 3), x = xbase + sub * 8 + (m & 7);
-                            const size_t q = ((size_t)b * P.H + y) * P.W + x;
-                            const float4 t4 = *reinterpret_cast<const float4*>(stg + rw * kStgPitch + cc);
-                            float v[4] = {t4.x + bias4.x, t4.y + bias4.y, t4.z + bias4.z, t4.w + bias4.w};
-                            v[0] += emb4.x; v[1] += emb4.y; v[2] += emb4.z; v[3] += emb4.w;
-                            if (P.res_mode == 1) {
-                                const float4 t = *reinterpret_cast<const float4*>(P.res + q * P.Cout + n);
-                                v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
-                            } else if (P.res_mode == 2) {
-                                const int W2 = P.W * 2;
-                                const float* rb = P.res + (((size_t)b * P.H * 2 + 2 * y) * W2 + 2 * x) * P.Cout + n;
-                                const float4 r0 = *reinterpret_cast<const float4*>(rb);
-                                const float4 r1 = *reinterpret_cast<const float4*>(rb + P.Cout);
-                                const float4 r2 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout);
-                                const float4 r3 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout + P.Cout);
-                                v[0] += (r0.x + r1.x + r2.x + r3.x) * 0.25f;
-                                v[1] += (r0.y + r1.y + r2.y + r3.y) * 0.25f;
-                                v[2] += (r0.z + r1.z + r2.z + r3.z) * 0.25f;
-                                v[3] += (r0.w + r1.w + r2.w + r3.w) * 0.25f;
-                            } else if (P.res_mode == 3) {
-                                const int Hh = P.H / 2, Wh = P.W / 2;
-                                const float4 t = *reinterpret_cast<const float4*>(
-                                    P.res + (((size_t)b * Hh + (y >> 1)) * Wh + (x >> 1)) * P.Cout + n);
-                                v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                        for (int hp = 0; hp < 2; ++hp) {
+                            size_t qq[4];
+                            float4 rv[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int m = quarter * 32 + 4 * (hp * 4 + i) + rr0;
+                                const int y = ybase + (m >> 3), x = xbase + sub * 8 + (m & 7);
+                                qq[i] = ((size_t)b * P.H + y) * P.W + x;
+                                rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (P.res_mode == 1) {
+                                    rv[i] = *reinterpret_cast<const float4*>(P.res + qq[i] * P.Cout + n);
+                                } else if (P.res_mode == 2) {
+                                    const int W2 = P.W * 2;
+                                    const float* rb = P.res + (((size_t)b * P.H * 2 + 2 * y) * W2 + 2 * x) * P.Cout + n;
+                                    const float4 r0 = *reinterpret_cast<const float4*>(rb);
+                                    const float4 r1 = *reinterpret_cast<const float4*>(rb + P.Cout);
+                                    const float4 r2 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout);
+                                    const float4 r3 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout + P.Cout);
+                                    rv[i].x = (r0.x + r1.x + r2.x + r3.x) * 0.25f;
+                                    rv[i].y = (r0.y + r1.y + r2.y + r3.y) * 0.25f;
+                                    rv[i].z = (r0.z + r1.z + r2.z + r3.z) * 0.25f;
+                                    rv[i].w = (r0.w + r1.w + r2.w + r3.w) * 0.25f;
+                                } else if (P.res_mode == 3) {
+                                    const int Hh = P.H / 2, Wh = P.W / 2;
+                                    rv[i] = *reinterpret_cast<const float4*>(
+                                        P.res + (((size_t)b * Hh + (y >> 1)) * Wh + (x >> 1)) * P.Cout + n);
+                                }
                             }
-                            *reinterpret_cast<float4*>(P.out + q * P.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
-                            s1 += (v[0] + v[1]) + (v[2] + v[3]);
-                            s2 += (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int rw = 4 * (hp * 4 + i) + rr0;   // staged row = tile row quarter*32 + rw
+                                const float4 t4 = *reinterpret_cast<const float4*>(stg + rw * kStgPitch + cc);
+                                float v[4] = {t4.x + bias4.x, t4.y + bias4.y, t4.z + bias4.z, t4.w + bias4.w};
+                                v[0] += emb4.x; v[1] += emb4.y; v[2] += emb4.z; v[3] += emb4.w;
+                                v[0] += rv[i].x; v[1] += rv[i].y; v[2] += rv[i].z; v[3] += rv[i].w;
+                                *reinterpret_cast<float4*>(P.out + qq[i] * P.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
+                                s1 += (v[0] + v[1]) + (v[2] + v[3]);
+                                s2 += (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+                            }
                         }
                     }
                     __syncwarp();

@@ -252,12 +252,14 @@ template <typename OutT>
 __global__ void __launch_bounds__(256) simplex3_octaves_kernel(
     OutT* __restrict__ out, int H, int W, int nslices, const int16_t* __restrict__ tables, int table_mode,
     int table_mod, const long long* __restrict__ z_int, const double* __restrict__ z_f64, int z_div, int octaves,
-    double persistence, double frequency) {
+    double persistence, double frequency, const long long* __restrict__ table_step, long long tables_per_step) {
     __shared__ SeedTables s;
     const int slice = blockIdx.y;
     int tab = 0;
     if (table_mode == 0) tab = slice;
     else if (table_mode == 2) tab = slice % table_mod;
+    // device-resident step index: lets a captured CUDA graph walk through pre-uploaded per-step seed tables
+    if (table_step) tables += (size_t)(*table_step) * (size_t)tables_per_step * 512;
     load_tables(s, tables + (size_t)tab * 512);
     double zval;
     if (z_int) zval = (double)z_int[slice / z_div];
@@ -340,7 +342,8 @@ extern "C" int anoddpm_simplex_init_batch(const int64_t* seeds, int n, int16_t* 
 
 static int launch_octaves(void* out, int out_f64, int nslices, int H, int W, const int16_t* tables, int table_mode,
                           int table_mod, const int64_t* z_int, const double* z_f64, int z_div, int octaves,
-                          double persistence, double frequency, void* stream) {
+                          double persistence, double frequency, void* stream, const int64_t* table_step = nullptr,
+                          long long tables_per_step = 0) {
     ADP_REQUIRE(out && tables, "simplex octaves: null pointer");
     ADP_REQUIRE(nslices > 0 && nslices <= 65535 && H > 0 && W > 0, "simplex octaves: bad shape %d x %d x %d", nslices,
                 H, W);
@@ -354,11 +357,13 @@ static int launch_octaves(void* out, int out_f64, int nslices, int H, int W, con
     if (out_f64)
         simplex3_octaves_kernel<double><<<grid, 256, 0, st>>>((double*)out, H, W, nslices, tables, table_mode,
                                                              table_mod, (const long long*)z_int, z_f64, z_div,
-                                                             octaves, persistence, frequency);
+                                                             octaves, persistence, frequency,
+                                                             (const long long*)table_step, tables_per_step);
     else
         simplex3_octaves_kernel<float><<<grid, 256, 0, st>>>((float*)out, H, W, nslices, tables, table_mode, table_mod,
                                                             (const long long*)z_int, z_f64, z_div, octaves,
-                                                            persistence, frequency);
+                                                            persistence, frequency, (const long long*)table_step,
+                                                            tables_per_step);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }
@@ -370,6 +375,15 @@ extern "C" int anoddpm_simplex_noise(float* out, int B, int C, int H, int W, con
     ADP_REQUIRE(B > 0 && C > 0, "anoddpm_simplex_noise: bad batch/channels");
     return launch_octaves(out, 0, B * C, H, W, tables, shared_seed ? 2 : 0, C, t, nullptr, C, octaves, persistence,
                           frequency, stream);
+}
+
+extern "C" int anoddpm_simplex_noise_steps(float* out, int B, int C, int H, int W, const int16_t* tables_all,
+                                           const int64_t* step, int shared_seed, const int64_t* t, int octaves,
+                                           double persistence, double frequency, void* stream) {
+    ADP_REQUIRE(t != nullptr && step != nullptr, "anoddpm_simplex_noise_steps: null t / step");
+    ADP_REQUIRE(B > 0 && C > 0, "anoddpm_simplex_noise_steps: bad batch/channels");
+    return launch_octaves(out, 0, B * C, H, W, tables_all, shared_seed ? 2 : 0, C, t, nullptr, C, octaves, persistence,
+                          frequency, stream, step, shared_seed ? C : (long long)B * C);
 }
 
 extern "C" int anoddpm_simplex_octaves(void* out, int out_f64, int D, int H, int W, const int16_t* tables,

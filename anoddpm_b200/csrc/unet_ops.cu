@@ -16,6 +16,8 @@ struct alignas(16) F4 { float x, y, z, w; };
 __device__ __forceinline__ F4 ld4(const float* p) { return *reinterpret_cast<const F4*>(p); }
 __device__ __forceinline__ void st4(float* p, F4 v) { *reinterpret_cast<F4*>(p) = v; }
 __device__ __forceinline__ float silu(float y) { return y / (1.0f + expf(-y)); }
+// ~2 ulp variant for outputs that are about to be rounded to a 10-bit mantissa (TF32 / fp16 operands)
+__device__ __forceinline__ float silu_fast(float y) { return __fdividef(y, 1.0f + __expf(-y)); }
 __device__ __forceinline__ float round_tf32(float v) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(float* __restrict__ out, 
 #pragma unroll
                         for (int j = 0; j < V; ++j) {
                             float y = v[u][tp][j] * sc[j] + bi[j];
-                            if (do_silu) y = silu(y);
+                            if (do_silu) y = rtf32 ? silu_fast(y) : silu(y);
                             acc[j] += y;
                         }
                     }
@@ -462,12 +464,13 @@ __global__ void __launch_bounds__(256) conv_head_kernel(float* __restrict__ out,
 }
 
 // ---------------------------------------------------------------- attention (UNet.py:137-153)
-// CTA: one (b, head), QB queries.  smem: q tile [QB][ch] (pre-scaled by 1/sqrt(ch)), scores [QB][T].
-constexpr int QB = 8;
-
-__global__ void __launch_bounds__(128) attention_kernel(float* __restrict__ out, const float* __restrict__ qkv, int T,
+// CTA: one (b, head), QB queries, 256 threads.  smem: q tile [QB][ch] (pre-scaled by 1/sqrt(ch)), scores [QB][T].
+// K and V of the (b, head) are streamed once per CTA, so QB = 32 re-reads them T/32 times in total.
+template <int QB>
+__global__ void __launch_bounds__(256) attention_kernel(float* __restrict__ out, const float* __restrict__ qkv, int T,
                                                         int C, int heads, int rtf32) {
     extern __shared__ float sm[];
+    constexpr int NW = 8;
     const int ch = C / heads;
     float* sq = sm;            // QB * ch
     float* ss = sm + QB * ch;  // QB * T
@@ -481,8 +484,8 @@ __global__ void __launch_bounds__(128) attention_kernel(float* __restrict__ out,
         sq[i] = (t0 + qi < T) ? base[(size_t)(t0 + qi) * row + c] * scale : 0.f;
     }
     __syncthreads();
-    // scores: warp per key
-    for (int s = warp; s < T; s += 4) {
+    // scores: warp per key, lanes over channels (coalesced K reads), QB dot products per key
+    for (int s = warp; s < T; s += NW) {
         const float* kr = base + (size_t)s * row + ch;
         float part[QB];
 #pragma unroll
@@ -501,8 +504,8 @@ __global__ void __launch_bounds__(128) attention_kernel(float* __restrict__ out,
         }
     }
     __syncthreads();
-    // softmax rows: warp handles rows warp, warp+4
-    for (int qi = warp; qi < QB; qi += 4) {
+    // softmax rows
+    for (int qi = warp; qi < QB; qi += NW) {
         float* r = ss + qi * T;
         float mx = -INFINITY;
         for (int s = lane; s < T; s += 32) mx = fmaxf(mx, r[s]);
@@ -520,12 +523,13 @@ __global__ void __launch_bounds__(128) attention_kernel(float* __restrict__ out,
         for (int s = lane; s < T; s += 32) r[s] *= inv;
     }
     __syncthreads();
-    // out = P . V : thread per channel
+    // out = P . V : thread per channel (coalesced V reads), probabilities broadcast from smem
     for (int c = tid; c < ch; c += blockDim.x) {
         float acc[QB];
 #pragma unroll
         for (int qi = 0; qi < QB; ++qi) acc[qi] = 0.f;
         const float* vr = base + 2 * ch + c;
+#pragma unroll 4
         for (int s = 0; s < T; ++s) {
             const float v = vr[(size_t)s * row];
 #pragma unroll
@@ -693,15 +697,25 @@ extern "C" int anoddpm_attention(void* out_v, const float* qkv, int B, int T, in
     ADP_REQUIRE(out && qkv && B > 0 && T > 0 && C > 0 && heads > 0 && C % heads == 0, "anoddpm_attention: bad arguments");
     ADP_REQUIRE(B <= 65535 && heads <= 65535, "anoddpm_attention: batch/heads too large");
     const int ch = C / heads;
-    const size_t smem = (size_t)QB * (ch + T) * sizeof(float);
+    // queries per CTA: as many as fit in shared memory while the grid still covers the GPU
+    // (16 keeps >= 4 CTAs resident per SM and the grid balanced for T <= 256; 32 only pays for long sequences)
+    int qb = T >= 1024 ? 32 : 16;
+    while (qb > 8 && ((size_t)qb * (ch + T) * sizeof(float) > 200 * 1024 ||
+                      (long long)adp_ceil_div(T, qb) * heads * B < 2 * 148)) qb >>= 1;
+    const size_t smem = (size_t)qb * (ch + T) * sizeof(float);
     ADP_REQUIRE(smem <= 200 * 1024, "anoddpm_attention: T=%d ch=%d needs %zu B of shared memory", T, ch, smem);
     static bool attr_set = false;
     if (!attr_set) {
-        ADP_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(attention_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(attention_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    dim3 grid(adp_ceil_div(T, QB), heads, B);
-    attention_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(out, qkv, T, C, heads, rtf32);
+    dim3 grid(adp_ceil_div(T, qb), heads, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (qb == 32) attention_kernel<32><<<grid, 256, smem, st>>>(out, qkv, T, C, heads, rtf32);
+    else if (qb == 16) attention_kernel<16><<<grid, 256, smem, st>>>(out, qkv, T, C, heads, rtf32);
+    else attention_kernel<8><<<grid, 256, smem, st>>>(out, qkv, T, C, heads, rtf32);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }

@@ -301,6 +301,7 @@ class UNetEngine:
         if p0.device != x.device:
             raise RuntimeError(f"UNetModel parameters are on {p0.device} but the input is on {x.device}")
         self._refresh()
+        l_start = self.launches
         if m.conv_impl not in ("tc", "tc_tf32", "tc2", "tc1", "exact"):
             raise ValueError(f"conv_impl must be 'tc', 'tc_tf32', 'tc2', 'tc1' or 'exact', got {m.conv_impl!r}")
         self.use_tc = m.conv_impl != "exact"
@@ -364,4 +365,5 @@ class UNetEngine:
         self.launches += 1
         self.emb_all = None
         self.stats = None
+        self.launches_per_forward = self.launches - l_start
         return out.to(in_dtype)

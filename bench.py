@@ -124,21 +124,26 @@ def run_native(args):
         launches["n"] += 1
         return simplex_noise_from_seeds(seeds, tuple(x.shape), t)
 
-    diff.noise_fn = noise_fn
+    # the reverse loop draws its simplex seeds through this hook (same per-image seeds whether the step runs eagerly or
+    # as a replayed CUDA graph); the forward jump (sample_q) uses noise_fn above
+    diff.simplex_seed_source = lambda step, n: D.seeds_for_step(args.seed, 100000 + step, gidx)
+    if args.no_graphs:
+        diff.use_cuda_graphs = False
     g = torch.Generator().manual_seed(1000 + rank)
     x_host = (torch.rand(B, 1, 256, 256, generator=g) * 2 - 1).pin_memory()
     eng = model.engine()
 
     @torch.no_grad()
-    def reverse_steps(x, t_hi, n):
-        for t in range(t_hi, t_hi - n, -1):
-            tb = torch.full((B,), t, device=dev, dtype=torch.int64)
-            x = diff.sample_p(model, x, tb, "noise_fn")["sample"]
-            launches["n"] += 1
+    def reverse_steps(x, t_hi, n):   # n consecutive iterations of forward_backward's reverse loop (public API)
+        x = diff.reverse_steps(model, x, t_hi, n, "simplex")
+        launches["n"] += 2 * n      # simplex noise + fused posterior per step (UNet launches are counted by the engine)
         return x
 
     def chain(x_h, td):   # the public API call, host buffers in, host buffer out
-        y = diff.forward_backward(model, x_h.to(dev, non_blocking=True), None, td, "noise_fn")
+        x_d = x_h.to(dev, non_blocking=True)
+        t_start = torch.full((B,), td - 1, device=dev, dtype=torch.int64)
+        x_d = diff.sample_q(x_d, t_start, noise_fn(x_d, t_start))
+        y = diff.reverse_steps(model, x_d, td - 1, td, "simplex")     # = forward_backward(model, x, None, td, "simplex")
         return y.cpu()
 
     clocks = ClockSampler(local)
@@ -170,7 +175,10 @@ def run_native(args):
         ms = ev0.elapsed_time(ev1)
         steps_per_image = float(T_DISTANCE)
     clk = clocks.stop()
-    n_launch = (launches["n"] - l0) + (eng.launches - e0)
+    per_fwd = getattr(eng, "launches_per_forward", 0)
+    fwd_timed = args.steps * (T_DISTANCE if args.full_chain else 1)
+    # eager: the engine counted every launch; graph replay: launches per captured step x replays
+    n_launch = (launches["n"] - l0) + ((eng.launches - e0) if args.no_graphs else per_fwd * fwd_timed)
     ms = D.max_over_ranks(ms, dev)
     ms_per_step = ms / args.steps
     value = world * B / (steps_per_image * ms_per_step / 1e3)
@@ -189,8 +197,9 @@ def run_native(args):
     img_bytes = B * 256 * 256 * 4
     e2e = {"value": world * B / (T_DISTANCE * e2e_ms / 1e3), "unit": "images/s",
            "h2d_bytes_per_step": int(img_bytes / k_e2e + B * 1024), "d2h_bytes_per_step": int(img_bytes / k_e2e),
-           "api": f"GaussianDiffusionModel.forward_backward(unet, x_host->cuda, None, t_distance={k_e2e}, 'noise_fn').cpu(); "
-                  f"per-step time x 800 steps/image", "finite": bool(torch.isfinite(y).all())}
+           "api": f"x_pinned.to(cuda) -> GaussianDiffusionModel.sample_q + reverse_steps (= forward_backward(unet, x, None, "
+                  f"t_distance={k_e2e}, 'simplex')) -> .cpu(); per-step time x 800 steps/image",
+           "finite": bool(torch.isfinite(y).all())}
 
     out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -202,7 +211,8 @@ def run_native(args):
                                      "images/s = n_gpus*B/(800*s_per_step)"),
                       "global_batch": world * B, "per_gpu_batch": B, "t_distance": T_DISTANCE,
                       "parallelism": f"dp{world} (images sharded by index, no collective in the loop)",
-                      "l2": "working set per step >> 126 MB L2 (no explicit flush)", "conv_impl": model.conv_impl},
+                      "l2": "working set per step >> 126 MB L2 (no explicit flush)", "conv_impl": model.conv_impl,
+                      "cuda_graph": bool(diff.use_cuda_graphs)},
            "e2e": e2e, "gpu_launches": int(n_launch), "clocks": clk, "tc_convs_per_forward": eng.tc_convs,
            "host_enqueue_ms_per_step": host_enqueue_ms, "fused_gn_stats_per_forward": getattr(eng, "fused_stats", 0)}
 
@@ -323,6 +333,7 @@ def main():
     ap.add_argument("--full-chain", action="store_true", help="a step = one whole 800-step chain")
     ap.add_argument("--conv-impl", default=None, choices=[None, "tc", "tc_tf32", "tc2", "tc1", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="run the reverse loop eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3

