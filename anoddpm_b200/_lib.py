@@ -37,8 +37,8 @@ SIGNATURES = {
     "anoddpm_p_sample": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
     "anoddpm_timestep_embedding": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
     "anoddpm_linear": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
-    "anoddpm_gn_stats": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_vp]),
-    "anoddpm_gn_apply": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32,
+    "anoddpm_gn_stats": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp]),
+    "anoddpm_gn_apply": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32,
                                  c_int, c_int, c_int, c_vp]),
     "anoddpm_conv": (c_int, [ctypes.POINTER(ConvDesc), c_vp]),
     "anoddpm_conv_tc_supported": (c_int, [ctypes.POINTER(ConvDesc)]),

@@ -10,8 +10,9 @@
 //   * CTA pairs (tcgen05.mma.cta_group::2, UMMA M = 256) split the weight tile in halves, persistent clusters,
 //     3-stage smem ring (60 KB/stage), 2 TMEM accumulator stages x 2 subtiles x BN columns (512 columns).
 // 1x1 "skip" sources (raw ResBlock input, centre tap only) are extra stages with a (32, 8, 16) box.
-// Epilogue: as conv_tc2 (bias + timestep embedding + residual), plus optional GroupNorm statistics of the OUTPUT
-// (sum, sum of squares per (sample, group), fp32 per warp -> fp64 atomics) so the next GroupNorm needs no stats pass.
+// Epilogue: as conv_tc2 (bias + timestep embedding + residual), plus optional per-channel statistics of the OUTPUT
+// (sum, sum of squares per (sample, channel), fp32 per warp -> fp64 atomics) so the GroupNorm(s) that consume the
+// tensor -- alone or concatenated with another tensor -- need no statistics pass.
 // Contract: ksize == 3, H % 16 == 0, W % 16 == 0, channels % 32 == 0, Cout % 16 == 0 (anoddpm_conv_tc3_supported).
 #include "common.cuh"
 #include "anoddpm_b200.h"
@@ -45,8 +46,7 @@ struct Tc3Args {
     int ke;                    // elements per 128-byte K-block row: 32 (fp32 operands) or 64 (fp16 operands)
     int n_tiles_n, n_tiles;    // tiles along N, total pair tiles
     int regions_x, regions_per_img, n_regions;   // 16x16 regions
-    double* gn_stats;          // optional [B][32][2] accumulation of the output's GroupNorm statistics
-    int gn_gs;                 // channels per group (Cout / 32)
+    double* gn_stats;          // optional [B][Cout][2]: per-channel (sum, sum of squares) of the output
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -303,7 +303,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), emb4 = bias4;
                 if (nvalid && P.bias) bias4 = *reinterpret_cast<const float4*>(P.bias + n);
                 if (nvalid && P.emb) emb4 = *reinterpret_cast<const float4*>(P.emb + (size_t)b * P.emb_stride + n);
-                float s1 = 0.f, s2 = 0.f;
+                float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};   // per-channel sum / sum of squares
 #pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
                     uint32_t r[32];
@@ -368,26 +368,29 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                 v[0] += emb4.x; v[1] += emb4.y; v[2] += emb4.z; v[3] += emb4.w;
                                 v[0] += rv[i].x; v[1] += rv[i].y; v[2] += rv[i].z; v[3] += rv[i].w;
                                 *reinterpret_cast<float4*>(P.out + qq[i] * P.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
-                                s1 += (v[0] + v[1]) + (v[2] + v[3]);
-                                s2 += (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) { s1[e] += v[e]; s2[e] += v[e] * v[e]; }
                             }
                         }
                     }
                     __syncwarp();
                 }
                 if (P.gn_stats) {   // warp-uniform; all pixels of the CTA's region belong to sample b
-                    // lanes with equal (lane & 7) hold the same channel quad for different pixel rows
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, 8);  s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, 16); s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-                    const int qpg = P.gn_gs >> 2;               // channel quads per group: 1, 2, 4 or 8
-                    for (int o = 1; o < qpg; o <<= 1) {
-                        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                    // lanes with equal (lane & 7) hold the same 4 channels for different pixel rows
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 8);
+                        s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 8);
+                        s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
+                        s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
                     }
-                    if (nvalid && lane < 8 && (lane % qpg) == 0) {
-                        const int grp = n / P.gn_gs;
-                        atomicAdd(&P.gn_stats[((size_t)b * 32 + grp) * 2], (double)s1);
-                        atomicAdd(&P.gn_stats[((size_t)b * 32 + grp) * 2 + 1], (double)s2);
+                    if (nvalid && lane < 8) {
+                        double* st = P.gn_stats + ((size_t)b * P.Cout + n) * 2;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            atomicAdd(st + 2 * e, (double)s1[e]);
+                            atomicAdd(st + 2 * e + 1, (double)s2[e]);
+                        }
                     }
                 }
             }
@@ -495,11 +498,6 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     P.n_regions = d->B * P.regions_per_img;
     P.n_tiles = adp_ceil_div(P.n_regions, 2) * P.n_tiles_n;
     P.gn_stats = d->gn_stats;
-    P.gn_gs = d->Cout / 32;
-    if (d->gn_stats) {
-        ADP_REQUIRE(d->Cout % 32 == 0 && (P.gn_gs == 4 || P.gn_gs == 8 || P.gn_gs == 16 || P.gn_gs == 32),
-                    "anoddpm_conv(impl=3): fused GroupNorm statistics need Cout in {128, 256, 512, 1024} (got %d)", d->Cout);
-    }
 
     CUtensorMap ma, m1, m2, mw;
     int rc;

@@ -57,16 +57,18 @@ __global__ void __launch_bounds__(256) linear_kernel(float* __restrict__ y, int 
     if (lane == 0) y[(size_t)b * ldy + n] = acc + (bias ? bias[n] : 0.f);
 }
 
-// ---------------------------------------------------------------- GroupNorm statistics
-// grid (chunks, B); a CTA reduces a pixel range of one sample; each thread owns a fixed channel
-// vector (so a fixed group), accumulates in fp32, then fp64 shared + global atomics.
+// ---------------------------------------------------------------- GroupNorm statistics (per channel)
+// stats[b][c] = (sum, sum of squares) over the H*W pixels of channel c, fp64.  Per-CHANNEL (not per-group) sums
+// are what every producer of a tensor can emit without knowing how a consumer will group or concatenate it: the
+// consumer (gn_apply) adds up the channels of each group, possibly across two concatenated tensors.
+// grid (chunks, B); a CTA reduces a pixel range of one sample; each thread owns a fixed channel vector,
+// accumulates in fp32, then fp64 shared + global atomics.
 template <int V>
-__global__ void __launch_bounds__(256) gn_stats_kernel(double* __restrict__ stats, const float* __restrict__ x1,
-                                                       int C1, const float* __restrict__ x2, int C2, int HW,
-                                                       int groups, int pix_per_cta) {
-    __shared__ double sh[64][2];
-    const int b = blockIdx.y, C = C1 + C2, gs = C / groups, ncv = C / V;
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i >> 1][i & 1] = 0.0;
+__global__ void __launch_bounds__(256) gn_stats_kernel(double* __restrict__ stats, const float* __restrict__ x, int C,
+                                                       int HW, int pix_per_cta) {
+    extern __shared__ double sh[];   // [C][2]
+    const int b = blockIdx.y, ncv = C / V;
+    for (int i = threadIdx.x; i < C * 2; i += blockDim.x) sh[i] = 0.0;
     __syncthreads();
     const int p0 = blockIdx.x * pix_per_cta;
     const int p1 = min(HW, p0 + pix_per_cta);
@@ -77,31 +79,30 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(double* __restrict__ stat
     if (r < rows) {
         for (int cv = lane; cv < ncv; cv += tpr) {
             const int c = cv * V;
-            const float* src;
-            int cs, cc;
-            if (c < C1) { src = x1; cs = C1; cc = c; }
-            else { src = x2; cs = C2; cc = c - C1; }
-            src += (size_t)b * HW * cs + cc;
-            float s = 0.f, q = 0.f;
+            const float* src = x + (size_t)b * HW * C + c;
+            float s[V], q[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) { s[j] = 0.f; q[j] = 0.f; }
             for (int p = p0 + r; p < p1; p += rows) {
                 if (V == 4) {
-                    const F4 v = ld4(src + (size_t)p * cs);
-                    s += (v.x + v.y) + (v.z + v.w);
-                    q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                    const F4 v = ld4(src + (size_t)p * C);
+                    s[0] += v.x; s[1 % V] += v.y; s[2 % V] += v.z; s[3 % V] += v.w;
+                    q[0] += v.x * v.x; q[1 % V] += v.y * v.y; q[2 % V] += v.z * v.z; q[3 % V] += v.w * v.w;
                 } else {
-                    const float v = src[(size_t)p * cs];
-                    s += v;
-                    q += v * v;
+                    const float v = src[(size_t)p * C];
+                    s[0] += v;
+                    q[0] += v * v;
                 }
             }
-            const int g = c / gs;
-            atomicAdd(&sh[g][0], (double)s);
-            atomicAdd(&sh[g][1], (double)q);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                atomicAdd(&sh[(c + j) * 2], (double)s[j]);
+                atomicAdd(&sh[(c + j) * 2 + 1], (double)q[j]);
+            }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
-        atomicAdd(&stats[((size_t)b * groups + (i >> 1)) * 2 + (i & 1)], sh[i >> 1][i & 1]);
+    for (int i = threadIdx.x; i < C * 2; i += blockDim.x) atomicAdd(&stats[(size_t)b * C * 2 + i], sh[i]);
 }
 
 // ---------------------------------------------------------------- GroupNorm apply (+SiLU, +resample)
@@ -145,15 +146,22 @@ template <int V, int NT>   // NT = taps per output pixel: 4 for the avg-pool mod
 __global__ void __launch_bounds__(256) gn_apply_kernel(float* __restrict__ out, float* __restrict__ raw_out,
                                                        const float* __restrict__ x1, int C1,
                                                        const float* __restrict__ x2, int C2,
-                                                       const double* __restrict__ stats,
+                                                       const double* __restrict__ stats1,
+                                                       const double* __restrict__ stats2,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        int H, int W, int groups, float eps, int do_silu, int mode,
                                                        int rtf32, int pix_per_cta) {
     __shared__ float s_mean[64], s_rstd[64];
     const int b = blockIdx.y, C = C1 + C2, gs = C / groups, ncv = C / V;
     if (threadIdx.x < groups) {
+        // group statistics = sum of the per-channel sums of its gs channels (which may straddle the two sources)
         const double n = (double)H * W * gs;
-        const double s = stats[((size_t)b * groups + threadIdx.x) * 2], q = stats[((size_t)b * groups + threadIdx.x) * 2 + 1];
+        double s = 0.0, q = 0.0;
+        for (int c = threadIdx.x * gs; c < (threadIdx.x + 1) * gs; ++c) {
+            const double* st = c < C1 ? stats1 + ((size_t)b * C1 + c) * 2 : stats2 + ((size_t)b * C2 + (c - C1)) * 2;
+            s += st[0];
+            q += st[1];
+        }
         const double m = s / n;
         double var = q / n - m * m;
         if (var < 0) var = 0;
@@ -574,35 +582,34 @@ extern "C" int anoddpm_linear(float* y, int ldy, const float* x, int ldx, const 
 
 static int gn_vec(int C1, int C2, int groups, const void* p1, const void* p2) {
     const int C = C1 + C2, gs = C / groups;
-    return (gs % 4 == 0 && C1 % 4 == 0 && C2 % 4 == 0 && al16(p1) && (!p2 || al16(p2))) ? 4 : 1;
+    (void)gs;
+    return (C1 % 4 == 0 && C2 % 4 == 0 && al16(p1) && (!p2 || al16(p2))) ? 4 : 1;
 }
 
-extern "C" int anoddpm_gn_stats(double* stats, const float* x1, int C1, const float* x2, int C2, int B, int HW,
-                                int groups, void* stream) {
-    ADP_REQUIRE(stats && x1 && B > 0 && B <= 65535 && HW > 0, "anoddpm_gn_stats: bad arguments");
-    ADP_REQUIRE((C2 == 0) == (x2 == nullptr), "anoddpm_gn_stats: x2/C2 mismatch");
-    const int C = C1 + C2;
-    ADP_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0, "anoddpm_gn_stats: C=%d not divisible into %d groups", C,
-                groups);
+extern "C" int anoddpm_gn_stats(double* stats, const float* x, int C, int B, int HW, void* stream) {
+    ADP_REQUIRE(stats && x && B > 0 && B <= 65535 && HW > 0 && C > 0, "anoddpm_gn_stats: bad arguments");
+    ADP_REQUIRE((size_t)C * 2 * sizeof(double) <= 48 * 1024, "anoddpm_gn_stats: too many channels (%d)", C);
     int ppc = 2048;  // pixels per CTA
     while (ppc > 64 && (long long)adp_ceil_div(HW, ppc) * B < 148 * 2) ppc >>= 1;
     dim3 grid(adp_ceil_div(HW, ppc), B);
     cudaStream_t st = (cudaStream_t)stream;
-    if (gn_vec(C1, C2, groups, x1, x2) == 4)
-        gn_stats_kernel<4><<<grid, 256, 0, st>>>(stats, x1, C1, x2, C2, HW, groups, ppc);
+    const size_t smem = (size_t)C * 2 * sizeof(double);
+    if (C % 4 == 0 && al16(x))
+        gn_stats_kernel<4><<<grid, 256, smem, st>>>(stats, x, C, HW, ppc);
     else
-        gn_stats_kernel<1><<<grid, 256, 0, st>>>(stats, x1, C1, x2, C2, HW, groups, ppc);
+        gn_stats_kernel<1><<<grid, 256, smem, st>>>(stats, x, C, HW, ppc);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }
 
 extern "C" int anoddpm_gn_apply(void* out_v, void* raw_out_v, const float* x1, int C1, const float* x2, int C2,
-                                const double* stats, const float* gamma, const float* beta, int B, int H, int W,
+                                const double* stats1, const double* stats2, const float* gamma, const float* beta, int B, int H, int W,
                                 int groups, float eps, int do_silu, int mode, int rtf32, void* stream) {
     float* out = static_cast<float*>(out_v);
     float* raw_out = static_cast<float*>(raw_out_v);
-    ADP_REQUIRE(out && x1 && stats && gamma && beta && B > 0 && B <= 65535 && H > 0 && W > 0,
+    ADP_REQUIRE(out && x1 && stats1 && gamma && beta && B > 0 && B <= 65535 && H > 0 && W > 0,
                 "anoddpm_gn_apply: bad arguments");
+    ADP_REQUIRE((C2 == 0) || stats2 != nullptr, "anoddpm_gn_apply: second source without statistics");
     ADP_REQUIRE((C2 == 0) == (x2 == nullptr), "anoddpm_gn_apply: x2/C2 mismatch");
     const int C = C1 + C2;
     ADP_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0, "anoddpm_gn_apply: bad groups");
@@ -618,7 +625,7 @@ extern "C" int anoddpm_gn_apply(void* out_v, void* raw_out_v, const float* x1, i
     dim3 grid((unsigned)adp_ceil_div(npo, wpc), B);
     cudaStream_t st = (cudaStream_t)stream;
 #define ADP_GN_APPLY(VV, NN)                                                                                       \
-    gn_apply_kernel<VV, NN><<<grid, 256, 0, st>>>(out, raw_out, x1, C1, x2, C2, stats, gamma, beta, H, W, groups, eps, \
+    gn_apply_kernel<VV, NN><<<grid, 256, 0, st>>>(out, raw_out, x1, C1, x2, C2, stats1, stats2, gamma, beta, H, W, groups, eps, \
                                                   do_silu, mode, rtf32, wpc)
     if (V == 4) { if (mode == 1) ADP_GN_APPLY(4, 4); else ADP_GN_APPLY(4, 1); }
     else { if (mode == 1) ADP_GN_APPLY(1, 4); else ADP_GN_APPLY(1, 1); }

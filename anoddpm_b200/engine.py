@@ -38,6 +38,14 @@ def pack_conv_weight(w):
     return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci)
 
 
+class _T:
+    """An NHWC activation and (optionally) its per-channel statistics [B][C][2] fp64 (sum, sum of squares)."""
+    __slots__ = ("t", "st")
+
+    def __init__(self, t, st=None):
+        self.t, self.st = t, st
+
+
 class _Conv:
     """One fused convolution site (weights packed lazily per implementation)."""
 
@@ -77,12 +85,10 @@ class UNetEngine:
     def _build(self):
         from .UNet import AttentionBlock, ResBlock
         m = self.model
-        self.gn_sites = 0
         self.emb_w, self.emb_b, self.emb_off = [], [], 0
 
         def gn_site():
-            self.gn_sites += 1
-            return self.gn_sites - 1
+            return None
 
         def build_res(rb):
             if not isinstance(rb.skip_connection, (torch.nn.Identity, torch.nn.Conv2d)) or (
@@ -131,6 +137,19 @@ class UNetEngine:
         self.emb_cat_b = torch.cat([b.detach() for b in self.emb_b], dim=0).contiguous().float()
         self.head_w = pack_conv_weight(self.head["conv"].weight.detach()).contiguous().float()
 
+    def _stats_pool_size(self, B):
+        """doubles needed for the per-channel statistics of all conv / stem / attention outputs of one forward"""
+        total = 0
+        for entry in self.down + [self.middle] + self.up:
+            for e in entry:
+                if e["kind"] == "res":
+                    total += 2 * e["cout"]
+                elif e["kind"] == "attn":
+                    total += e["c"]
+                else:
+                    total += e["conv"].out_channels
+        return (total + 64) * B * 2
+
     def _refresh(self):
         sig = self._signature()
         if sig != self._sig:
@@ -148,32 +167,45 @@ class UNetEngine:
         return self._freq_cache[key]
 
     # ------------------------------------------------------------------ op wrappers
-    def _gn_stats(self, site, srcs, B, HW):
-        if site in self.stats_ready:       # already produced by the conv that wrote srcs[0]
-            assert len(srcs) == 1
-            return
-        x1 = srcs[0]
-        x2 = srcs[1] if len(srcs) > 1 else None
-        call("anoddpm_gn_stats", ptr(self.stats[site]), ptr(x1), x1.shape[-1], ptr(x2), x2.shape[-1] if x2 is not None else 0,
-             B, HW, 32, stream())
-        self.launches += 1
+    def _stats_slot(self, B, C):
+        """[B][C][2] fp64 slice of the per-forward statistics pool (zeroed once per forward)."""
+        n = B * C * 2
+        if self.stats_used + n > self.stats_pool.numel():
+            raise RuntimeError("statistics pool exhausted")
+        sl = self.stats_pool[self.stats_used:self.stats_used + n]
+        self.stats_used += n
+        return sl
 
-    def _gn_apply(self, site, srcs, gn, B, H, W, silu, mode, rtf32, want_raw=False):
-        """rtf32 = output mode: 0 fp32, 1 fp32 rounded to TF32, 2 fp16."""
+    def _stats_of(self, x, B, HW):
+        """per-channel statistics of activation x (_T): taken from its producer's epilogue, else one reduction pass"""
+        if x.st is None:
+            C = x.t.shape[-1]
+            x.st = self._stats_slot(B, C)
+            call("anoddpm_gn_stats", ptr(x.st), ptr(x.t), C, B, HW, stream())
+            self.launches += 1
+            self.stats_passes += 1
+        return x.st
+
+    def _gn_apply(self, srcs, gn, B, H, W, silu, mode, out_mode, want_raw=False):
+        """srcs: one or two _T (channel-concatenated).  out_mode: 0 fp32, 1 fp32 rounded to TF32, 2 fp16."""
         x1 = srcs[0]
         x2 = srcs[1] if len(srcs) > 1 else None
-        C = x1.shape[-1] + (x2.shape[-1] if x2 is not None else 0)
+        st1 = self._stats_of(x1, B, H * W)
+        st2 = self._stats_of(x2, B, H * W) if x2 is not None else None
+        C1 = x1.t.shape[-1]
+        C2 = x2.t.shape[-1] if x2 is not None else 0
+        C = C1 + C2
         Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
-        odt = torch.float16 if rtf32 == 2 else torch.float32
-        out = torch.empty((B, Ho, Wo, C), device=x1.device, dtype=odt)
-        raw = torch.empty((B, H, W, C), device=x1.device, dtype=odt) if want_raw else None
-        call("anoddpm_gn_apply", ptr(out), ptr(raw), ptr(x1), x1.shape[-1], ptr(x2), x2.shape[-1] if x2 is not None else 0,
-             ptr(self.stats[site]), ptr(gn.weight), ptr(gn.bias), B, H, W, 32, float(gn.eps), int(silu), mode,
-             int(rtf32), stream())
+        odt = torch.float16 if out_mode == 2 else torch.float32
+        out = torch.empty((B, Ho, Wo, C), device=x1.t.device, dtype=odt)
+        raw = torch.empty((B, H, W, C), device=x1.t.device, dtype=odt) if want_raw else None
+        call("anoddpm_gn_apply", ptr(out), ptr(raw), ptr(x1.t), C1, ptr(x2.t) if x2 is not None else None, C2,
+             ptr(st1), ptr(st2), ptr(gn.weight), ptr(gn.bias), B, H, W, 32, float(gn.eps), int(silu), mode,
+             int(out_mode), stream())
         self.launches += 1
         return (out, raw) if want_raw else out
 
-    def _conv(self, site, a, B, H, W, cout, plan, r=(), emb=None, res=None, res_mode=0, stats_site=None):
+    def _conv(self, site, a, B, H, W, cout, plan, r=(), emb=None, res=None, res_mode=0, want_stats=True):
         impl, f16 = plan
         d = ConvDesc()
         d.B, d.H, d.W = B, H, W
@@ -195,16 +227,18 @@ class UNetEngine:
         d.res_mode = res_mode
         d.impl = impl
         d.gn_stats = None
-        if stats_site is not None and impl == 3 and cout in (128, 256, 512, 1024):
-            # the epilogue also accumulates the GroupNorm statistics of its output: the consumer skips its stats pass
-            d.gn_stats = self.stats[stats_site].data_ptr()
-            self.stats_ready.add(stats_site)
+        st = None
+        if want_stats and impl == 3:
+            # the epilogue also accumulates the per-channel statistics of its output: no statistics pass for any
+            # GroupNorm that later consumes this tensor (alone or concatenated with a skip tensor)
+            st = self._stats_slot(B, cout)
+            d.gn_stats = st.data_ptr()
             self.fused_stats += 1
         call("anoddpm_conv", ctypes.byref(d), stream())
         self.launches += 1
         self.tc_convs += 1 if impl else 0
         self.f16_convs += 1 if f16 else 0
-        return out
+        return _T(out, st)
 
     def _plan(self, H, W, Ca, Cr, cout, ksize):
         """(impl, f16) for a conv with main source Ca channels and (single, concatenated) skip source Cr channels."""
@@ -228,68 +262,58 @@ class UNetEngine:
         return 2 if f16 else (1 if impl else 0)
 
     # ------------------------------------------------------------------ blocks
-    def _res(self, e, srcs, B, H, W, next_site=None):
+    def _res(self, e, srcs, B, H, W):
+        """srcs: one or two _T (the up path concatenates h with a skip tensor)."""
         mode = _MODE[e["mode"]]
         Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
-        c_src = sum(t.shape[-1] for t in srcs)
+        c_src = sum(x.t.shape[-1] for x in srcs)
         plan1 = self._plan(Ho, Wo, e["cin"], 0, e["cout"], 3)
         plan2 = self._plan(Ho, Wo, e["cout"], c_src if e["skip_conv"] else 0, e["cout"], 3)
-        self._gn_stats(e["s1"], srcs, B, H * W)
         # tensor-core path: the fused 1x1 skip conv reads a rounded (TF32 / fp16), channel-concatenated copy of x that
         # is written by the same pass that normalises x (round to nearest instead of the MMA's operand truncation)
         raw = None
         if e["skip_conv"] and plan2[0] and self._out_mode(plan1) == self._out_mode(plan2):
-            a1, raw = self._gn_apply(e["s1"], srcs, e["gn1"], B, H, W, True, mode, self._out_mode(plan1), want_raw=True)
+            a1, raw = self._gn_apply(srcs, e["gn1"], B, H, W, True, mode, self._out_mode(plan1), want_raw=True)
         else:
             if e["skip_conv"] and plan2[1]:
                 plan2 = (plan2[0], False)      # no fp16 raw copy available: run conv2 with TF32 operands
-            a1 = self._gn_apply(e["s1"], srcs, e["gn1"], B, H, W, True, mode, self._out_mode(plan1))
+            a1 = self._gn_apply(srcs, e["gn1"], B, H, W, True, mode, self._out_mode(plan1))
         emb = self.emb_all[:, e["emb_off"]:]
-        h = self._conv(e["conv1"], a1, B, Ho, Wo, e["cout"], plan1, emb=emb, stats_site=e["s2"])
+        h = self._conv(e["conv1"], a1, B, Ho, Wo, e["cout"], plan1, emb=emb)
         del a1
-        self._gn_stats(e["s2"], [h], B, Ho * Wo)
-        a2 = self._gn_apply(e["s2"], [h], e["gn2"], B, Ho, Wo, True, 0, self._out_mode(plan2))
+        a2 = self._gn_apply([h], e["gn2"], B, Ho, Wo, True, 0, self._out_mode(plan2))
         del h
         if e["skip_conv"]:
-            return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], plan2, r=([raw] if raw is not None else srcs),
-                              stats_site=next_site), Ho, Wo
+            rs = [raw] if raw is not None else [x.t for x in srcs]
+            return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], plan2, r=rs), Ho, Wo
         assert len(srcs) == 1
-        return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], plan2, res=srcs[0], res_mode=_RES_FOR_MODE[e["mode"]],
-                          stats_site=next_site), Ho, Wo
+        return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], plan2, res=srcs[0].t,
+                          res_mode=_RES_FOR_MODE[e["mode"]]), Ho, Wo
 
     def _attn(self, e, x, B, H, W):
         C, T = e["c"], H * W
         plan_qkv = self._plan(H, W, C, 0, 3 * C, 1)
         plan_proj = self._plan(H, W, C, 0, C, 1)
-        self._gn_stats(e["s"], [x], B, T)
-        xn = self._gn_apply(e["s"], [x], e["gn"], B, H, W, False, 0, self._out_mode(plan_qkv))
-        qkv = self._conv(e["qkv"], xn, B, H, W, 3 * C, plan_qkv)
+        xn = self._gn_apply([x], e["gn"], B, H, W, False, 0, self._out_mode(plan_qkv))
+        qkv = self._conv(e["qkv"], xn, B, H, W, 3 * C, plan_qkv, want_stats=False).t
         del xn
         om = self._out_mode(plan_proj)
-        a = torch.empty((B, H, W, C), device=x.device, dtype=torch.float16 if om == 2 else torch.float32)
+        a = torch.empty((B, H, W, C), device=x.t.device, dtype=torch.float16 if om == 2 else torch.float32)
         call("anoddpm_attention", ptr(a), ptr(qkv), B, T, C, e["heads"], om, stream())
         self.launches += 1
-        return self._conv(e["proj"], a, B, H, W, C, plan_proj, res=x, res_mode=1)
+        return self._conv(e["proj"], a, B, H, W, C, plan_proj, res=x.t, res_mode=1)
 
-    @staticmethod
-    def _first_site(entry):
-        e = entry[0]
-        return e["s1"] if e["kind"] == "res" else e["s"]
-
-    def _entry(self, entry, srcs, B, H, W, next_site=None):
-        """next_site: GroupNorm site that consumes this entry's output as a SINGLE source (None if the consumer
-        concatenates it with a skip tensor, whose statistics need both sources)."""
+    def _entry(self, entry, srcs, B, H, W):
         h = None
-        for i, e in enumerate(entry):
+        for e in entry:
             cur = srcs if h is None else [h]
-            nxt = self._first_site(entry[i + 1:]) if i + 1 < len(entry) else next_site
             if e["kind"] == "stem":
                 raise RuntimeError("stem handled by forward()")
             if e["kind"] == "res":
-                h, H, W = self._res(e, cur, B, H, W, nxt)
+                h, H, W = self._res(e, cur, B, H, W)
             else:
                 assert len(cur) == 1
-                h = self._attn(e, cur[0], B, H, W)   # 1x1 proj conv: no fused statistics
+                h = self._attn(e, cur[0], B, H, W)
         return h, H, W
 
     # ------------------------------------------------------------------ forward
@@ -311,8 +335,8 @@ class UNetEngine:
         self.tc_impl = {"tc": 3, "tc_tf32": 3, "tc2": 2, "tc1": 1, "exact": 0}[m.conv_impl]
         self.allow_f16 = m.conv_impl == "tc"
         self.f16_convs = 0
-        self.stats_ready = set()
         self.fused_stats = 0
+        self.stats_passes = 0
         self.tc_convs = 0
         in_dtype = x.dtype
         x = x.contiguous().float()
@@ -338,32 +362,32 @@ class UNetEngine:
         call("anoddpm_linear", ptr(self.emb_all), S, ptr(emb), E, ptr(self.emb_cat_w), ptr(self.emb_cat_b), B, S, E, 1,
              stream())
         self.launches += 4
-        self.stats = torch.zeros((self.gn_sites, B, 32, 2), device=dev, dtype=torch.float64)
+        # per-channel statistics of every activation that feeds a GroupNorm, bump-allocated, one memset per forward
+        self.stats_pool = torch.zeros(self._stats_pool_size(B), device=dev, dtype=torch.float64)
+        self.stats_used = 0
 
         stem = self.down[0][0]["conv"]
         C0 = stem.out_channels
         h = torch.empty((B, H, W, C0), device=dev, dtype=torch.float32)
         call("anoddpm_conv_stem", ptr(h), ptr(x), ptr(stem.weight), ptr(stem.bias), B, Cin, H, W, C0, stream())
         self.launches += 1
+        h = _T(h)
         skips = [(h, H, W)]
-        downs = self.down[1:]
-        for i, entry in enumerate(downs):
-            nxt = self._first_site(downs[i + 1]) if i + 1 < len(downs) else self._first_site(self.middle)
-            h, H, W = self._entry(entry, [h], B, H, W, nxt)
+        for entry in self.down[1:]:
+            h, H, W = self._entry(entry, [h], B, H, W)
             skips.append((h, H, W))
-        h, H, W = self._entry(self.middle, [h], B, H, W, None)
-        for i, entry in enumerate(self.up):
-            s, sh, sw = skips.pop()
+        h, H, W = self._entry(self.middle, [h], B, H, W)
+        for entry in self.up:
+            sk, sh, sw = skips.pop()
             assert (sh, sw) == (H, W)
-            h, H, W = self._entry(entry, [h, s], B, H, W, self.head["s"] if i + 1 == len(self.up) else None)
+            h, H, W = self._entry(entry, [h, sk], B, H, W)
         hd = self.head
-        self._gn_stats(hd["s"], [h], B, H * W)
-        a = self._gn_apply(hd["s"], [h], hd["gn"], B, H, W, True, 0, 0)
+        a = self._gn_apply([h], hd["gn"], B, H, W, True, 0, 0)
         out = torch.empty((B, m.out_channels, H, W), device=dev, dtype=torch.float32)
         call("anoddpm_conv_head", ptr(out), ptr(a), ptr(self.head_w), ptr(hd["conv"].bias), B, a.shape[-1], H, W,
              m.out_channels, stream())
         self.launches += 1
         self.emb_all = None
-        self.stats = None
+        self.stats_pool = None
         self.launches_per_forward = self.launches - l_start
         return out.to(in_dtype)

@@ -214,7 +214,8 @@ def run_native(args):
                       "l2": "working set per step >> 126 MB L2 (no explicit flush)", "conv_impl": model.conv_impl,
                       "cuda_graph": bool(diff.use_cuda_graphs)},
            "e2e": e2e, "gpu_launches": int(n_launch), "clocks": clk, "tc_convs_per_forward": eng.tc_convs,
-           "host_enqueue_ms_per_step": host_enqueue_ms, "fused_gn_stats_per_forward": getattr(eng, "fused_stats", 0)}
+           "host_enqueue_ms_per_step": host_enqueue_ms, "fused_gn_stats_per_forward": getattr(eng, "fused_stats", 0),
+           "gn_stats_passes_per_forward": getattr(eng, "stats_passes", 0)}
 
     if rank == 0:
         out["roofline"] = roofline(model, dev, B)
@@ -294,8 +295,13 @@ def cpu_reverse_step_seconds(steps, threads):
     return float(np.mean(times))
 
 
+def cpu_threads():
+    """torch's CPU conv kernels stop scaling (and oversubscribe badly) beyond a few dozen threads at batch size 1"""
+    return min(os.cpu_count() or 1, 32)
+
+
 def cpu_baseline(sample_steps=2):
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     s = cpu_reverse_step_seconds(sample_steps, threads)
     return {"value": 1.0 / (T_DISTANCE * s), "unit": "images/s", "cores": threads, "kind": "port",
             "sample": f"{sample_steps} reverse steps at bs 1 (256x256, same UNet) after 1 warm-up step, "
@@ -308,7 +314,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     steps = max(1, min(args.steps, 3))
     s = cpu_reverse_step_seconds(steps, threads)
     v = 1.0 / (T_DISTANCE * s)

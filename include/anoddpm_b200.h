@@ -93,21 +93,22 @@ int anoddpm_timestep_embedding(float* emb /* B x dim */, const int64_t* t, const
 int anoddpm_linear(float* y, int ldy, const float* x, int ldx, const float* w, const float* bias, int B, int N, int K,
                    int silu_in, void* stream);
 
-/* GroupNorm statistics of a (possibly channel-concatenated) NHWC tensor: for sample b, group g
- * accumulates (sum, sum of squares) in fp64 into stats[b][g][2] (+=; caller zeroes).  UNet.py:409-411.
- * x2 may be NULL (C2 = 0): channels [0,C1) come from x1, [C1,C1+C2) from x2 (torch.cat, UNet.py:402). */
-int anoddpm_gn_stats(double* stats /* B x groups x 2 */, const float* x1, int C1, const float* x2, int C2, int B,
-                     int HW, int groups, void* stream);
+/* Per-channel statistics of an NHWC tensor: stats[b][c] += (sum, sum of squares) over the HW pixels, fp64 (caller
+ * zeroes).  Per-channel sums are grouping-agnostic: a GroupNorm over this tensor, or over its concatenation with another
+ * one (torch.cat, UNet.py:402), adds up the channels of each group in anoddpm_gn_apply.  The tensor-core conv
+ * (anoddpm_conv impl 3) can emit the same numbers for its output from its epilogue (gn_stats field).  UNet.py:409-411. */
+int anoddpm_gn_stats(double* stats /* B x C x 2 */, const float* x, int C, int B, int HW, void* stream);
 
-/* out = resample(act(GroupNorm(x))) on NHWC: act = SiLU if silu; mode 0 same, 1 avg-pool 2x2, 2 nearest x2
- * (UNet.py:202-210: GN -> SiLU -> h_upd, in that order).  stats from anoddpm_gn_stats over n = HW*(C/groups).
+/* out = resample(act(GroupNorm(cat(x1, x2)))) on NHWC: act = SiLU if silu; mode 0 same, 1 avg-pool 2x2, 2 nearest x2
+ * (UNet.py:202-210: GN -> SiLU -> h_upd, in that order).  stats1 / stats2: per-channel statistics of x1 / x2
+ * ([B][C1][2], [B][C2][2]); x2, stats2 may be NULL (C2 = 0).
  * round_tf32 = output mode: 0 fp32; 1 fp32 rounded to TF32 (rna) for a kind::tf32 conv; 2 IEEE fp16 (rn, saturating;
  * `out` / `raw_out` then point to half elements) for a kind::f16 conv.
- * raw_out (optional, mode 0 only): also writes the TF32-rounded, channel-concatenated copy of the INPUT, which the
+ * raw_out (optional, mode 0 only): also writes the rounded, channel-concatenated copy of the INPUT, which the
  * fused 1x1 skip convolution of the same ResBlock reads as its K-major operand (one pass over x for both). */
 int anoddpm_gn_apply(void* out, void* raw_out, const float* x1, int C1, const float* x2, int C2,
-                     const double* stats, const float* gamma, const float* beta, int B, int H, int W, int groups,
-                     float eps, int silu, int mode, int round_tf32, void* stream);
+                     const double* stats1, const double* stats2, const float* gamma, const float* beta, int B, int H,
+                     int W, int groups, float eps, int silu, int mode, int round_tf32, void* stream);
 
 /* Convolution as implicit GEMM over NHWC pixels.  out[b,y,x,:] =
  *     conv_k(a)[..] (k = ksize 3 pad 1, or 1)  +  r1 . W_r1  +  r2 . W_r2      (1x1 "skip" sources, optional)
@@ -137,8 +138,8 @@ typedef struct anoddpm_conv_desc {
     int impl;
     int operand_f16;    /* impl 2/3 only: a, r1, r2, w hold IEEE fp16 (tcgen05 kind::f16, fp32 accumulate): the same 10-bit
                            mantissa as TF32 at twice the tensor rate and half the operand bytes; channels % 64 == 0 */
-    double* gn_stats;   /* optional, impl 3 only: += (sum, sum of squares) of the OUTPUT per (sample, group of Cout/32
-                           channels), layout [B][32][2] fp64 = the input anoddpm_gn_apply expects for the next GroupNorm */
+    double* gn_stats;   /* optional, impl 3 only: += (sum, sum of squares) of the OUTPUT per (sample, channel), layout
+                           [B][Cout][2] fp64 = what anoddpm_gn_stats would compute for the output tensor */
 } anoddpm_conv_desc;
 int anoddpm_conv(const anoddpm_conv_desc* d /* [host] */, void* stream);
 /* 1 if impl=1/2 (tcgen05 tiles: channels % 32, Cout % 16, power-of-two W) covers the problem, else 0. */

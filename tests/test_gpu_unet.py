@@ -160,13 +160,13 @@ def test_gn_apply_and_attention_fp16_outputs():
     x = (torch.randn(B, C, H, W, generator=g) * 3).to(DEV)
     gamma, beta = torch.randn(C, generator=g).to(DEV), torch.randn(C, generator=g).to(DEV)
     xn = nhwc(x)
-    stats = torch.zeros(B, 32, 2, dtype=torch.float64, device=DEV)
-    _lib.call("anoddpm_gn_stats", _lib.ptr(stats), _lib.ptr(xn), C, None, 0, B, H * W, 32, _lib.stream())
+    stats = torch.zeros(B, C, 2, dtype=torch.float64, device=DEV)
+    _lib.call("anoddpm_gn_stats", _lib.ptr(stats), _lib.ptr(xn), C, B, H * W, _lib.stream())
     o32 = torch.empty(B, H, W, C, device=DEV)
     o16 = torch.empty(B, H, W, C, device=DEV, dtype=torch.float16)
     r16 = torch.empty(B, H, W, C, device=DEV, dtype=torch.float16)
     for out, raw, mode in ((o32, None, 0), (o16, r16, 2)):
-        _lib.call("anoddpm_gn_apply", _lib.ptr(out), _lib.ptr(raw), _lib.ptr(xn), C, None, 0, _lib.ptr(stats),
+        _lib.call("anoddpm_gn_apply", _lib.ptr(out), _lib.ptr(raw), _lib.ptr(xn), C, None, 0, _lib.ptr(stats), None,
                   _lib.ptr(gamma), _lib.ptr(beta), B, H, W, 32, 1e-5, 1, 0, mode, _lib.stream())
     assert torch.equal(o16, o32.half()) and torch.equal(r16, xn.half())      # fp16 = round-to-nearest of the fp32 result
     qkv = torch.randn(B, 64, 3 * C, generator=g).to(DEV)
@@ -179,7 +179,7 @@ def test_gn_apply_and_attention_fp16_outputs():
 
 @pytest.mark.parametrize("shape", [(2, 128, 128, 32, 32), (1, 64, 256, 16, 16), (3, 256, 512, 16, 32), (1, 128, 128, 256, 256)])
 def test_conv_fused_groupnorm_statistics(shape):
-    """impl 3 epilogue also emits (sum, sumsq) of its OUTPUT per (sample, group) = what gn_stats computes."""
+    """impl 3 epilogue also emits per-channel (sum, sumsq) of its OUTPUT = what anoddpm_gn_stats computes."""
     from anoddpm_b200 import _lib
     B, Ci, Co, H, W = shape
     g = torch.Generator().manual_seed(Ci + Co)
@@ -187,13 +187,13 @@ def test_conv_fused_groupnorm_statistics(shape):
     w = (torch.randn(Co, Ci, 3, 3, generator=g) * (9 * Ci) ** -0.5).to(DEV)
     b = torch.randn(Co, generator=g).to(DEV)
     res = torch.randn(B, Co, H, W, generator=g).to(DEV)
-    fused = torch.zeros(B, 32, 2, dtype=torch.float64, device=DEV)
+    fused = torch.zeros(B, Co, 2, dtype=torch.float64, device=DEV)
     out = run_conv(a, w, b, 3, 3, res=res, res_mode=1, gn_stats=fused)
     torch.cuda.synchronize()
     ref = torch.zeros_like(fused)
     on = nhwc(out)
-    _lib.call("anoddpm_gn_stats", _lib.ptr(ref), _lib.ptr(on), Co, None, 0, B, H * W, 32, _lib.stream())
-    xg = out.double().reshape(B, 32, -1)
+    _lib.call("anoddpm_gn_stats", _lib.ptr(ref), _lib.ptr(on), Co, B, H * W, _lib.stream())
+    xg = out.double().reshape(B, Co, -1)
     exact = torch.stack([xg.sum(-1), (xg * xg).sum(-1)], dim=-1)
     assert torch.allclose(fused, exact, rtol=1e-5, atol=1e-3)
     assert torch.allclose(ref, exact, rtol=1e-5, atol=1e-3)
@@ -202,20 +202,24 @@ def test_conv_fused_groupnorm_statistics(shape):
 def test_groupnorm_silu_resample_vs_torch():
     from anoddpm_b200 import _lib
     g = torch.Generator().manual_seed(5)
-    for (B, C1, C2, H, W) in [(2, 64, 0, 16, 16), (1, 96, 32, 8, 8), (3, 32, 0, 32, 32), (2, 512, 256, 8, 8), (1, 128, 0, 256, 256)]:
+    for (B, C1, C2, H, W) in [(2, 64, 0, 16, 16), (1, 96, 32, 8, 8), (3, 32, 0, 32, 32), (2, 512, 256, 8, 8), (1, 128, 0, 256, 256),
+                              (2, 64, 32, 16, 16), (1, 256, 128, 16, 16)]:   # last two: groups straddle the concat boundary
         x1 = (torch.randn(B, C1, H, W, generator=g) * 2 + 0.5).to(DEV)
         x2 = torch.randn(B, C2, H, W, generator=g).to(DEV) if C2 else None
         C = C1 + C2
         gamma, beta = torch.randn(C, generator=g).to(DEV), torch.randn(C, generator=g).to(DEV)
         xcat = torch.cat([x1, x2], 1) if C2 else x1
         for mode, silu in ((0, 1), (1, 1), (2, 1), (0, 0)):
-            stats = torch.zeros(B, 32, 2, dtype=torch.float64, device=DEV)
             x1n, x2n = nhwc(x1), (nhwc(x2) if C2 else None)
-            _lib.call("anoddpm_gn_stats", _lib.ptr(stats), _lib.ptr(x1n), C1, _lib.ptr(x2n), C2, B, H * W, 32, _lib.stream())
+            st1 = torch.zeros(B, C1, 2, dtype=torch.float64, device=DEV)
+            st2 = torch.zeros(B, C2, 2, dtype=torch.float64, device=DEV) if C2 else None
+            _lib.call("anoddpm_gn_stats", _lib.ptr(st1), _lib.ptr(x1n), C1, B, H * W, _lib.stream())
+            if C2:
+                _lib.call("anoddpm_gn_stats", _lib.ptr(st2), _lib.ptr(x2n), C2, B, H * W, _lib.stream())
             Ho, Wo = (H // 2, W // 2) if mode == 1 else ((2 * H, 2 * W) if mode == 2 else (H, W))
             out = torch.empty(B, Ho, Wo, C, device=DEV)
-            _lib.call("anoddpm_gn_apply", _lib.ptr(out), None, _lib.ptr(x1n), C1, _lib.ptr(x2n), C2, _lib.ptr(stats),
-                      _lib.ptr(gamma), _lib.ptr(beta), B, H, W, 32, 1e-5, silu, mode, 0, _lib.stream())
+            _lib.call("anoddpm_gn_apply", _lib.ptr(out), None, _lib.ptr(x1n), C1, _lib.ptr(x2n), C2, _lib.ptr(st1),
+                      _lib.ptr(st2), _lib.ptr(gamma), _lib.ptr(beta), B, H, W, 32, 1e-5, silu, mode, 0, _lib.stream())
             ref = F.group_norm(xcat.double(), 32, gamma.double(), beta.double(), 1e-5)
             if silu:
                 ref = F.silu(ref)
@@ -327,7 +331,8 @@ def test_baseline_model_256_forward_vs_reference_golden(golden, impl):
     if impl != "exact":
         assert m.engine().tc_convs >= 100
     if impl in ("tc", "tc_tf32"):
-        assert m.engine().fused_stats > 40      # GroupNorm statistics came out of the conv epilogues
+        assert m.engine().fused_stats >= 60     # per-channel statistics came out of the conv epilogues ...
+        assert m.engine().stats_passes <= 30    # ... only the stem / 1x1 / 8x8 outputs need a reduction pass
     if impl == "tc":
         assert m.engine().f16_convs >= 100      # kind::f16 operands (all channel counts of this model are % 64 == 0)
 
