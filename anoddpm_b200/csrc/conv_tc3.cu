@@ -168,7 +168,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]   both CTAs (multicast commit)
     uint64_t* tmem_empty = tmem_full + kAccStages; // [2]   leader only, 2 x 128 arrivals
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
-    float* stg_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // 4 warps x 32 rows x kStgPitch
+    float* stg_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // 4 warps x 2 subtiles x 32 rows x kStgPitch
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
@@ -283,7 +283,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // TMEM -> registers (thread = pixel row, 32 channels) -> per-warp smem transpose -> each store instruction
         // writes 4 pixels x 128 B (4 full lines) instead of 32 scattered 16-byte pieces.
         const int quarter = warp & 3;
-        float* stg = stg_all + quarter * (32 * kStgPitch);
+        float* stg = stg_all + quarter * (64 * kStgPitch);   // [2 subtiles][32 rows][kStgPitch]
         const int rr0 = lane >> 3;          // row within a group of 4 staged rows
         const int cc = (lane & 7) * 4;      // channel quad within the 32-channel chunk
         int it = 0;
@@ -304,6 +304,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 if (nvalid && P.bias) bias4 = *reinterpret_cast<const float4*>(P.bias + n);
                 if (nvalid && P.emb) emb4 = *reinterpret_cast<const float4*>(P.emb + (size_t)b * P.emb_stride + n);
                 float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};   // per-channel sum / sum of squares
+                // 1. both subtiles of this 32-channel chunk: TMEM -> registers -> per-warp staging rows
 #pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
                     uint32_t r[32];
@@ -326,55 +327,60 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     }
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<uint4*>(stg + lane * kStgPitch + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-                    __syncwarp();
-                    if (nvalid) {
-                        // two half-passes of 4 staged rows: all residual loads of a half are issued before its first
-                        // store (P.out may alias P.res as far as the compiler knows, so it cannot hoist them itself)
+                        *reinterpret_cast<uint4*>(stg + (sub * 32 + lane) * kStgPitch + j) =
+                            make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                }
+                __syncwarp();
+                if (nvalid) {
+                    // 2. transposed pass: item k = (subtile k/8, staged row 4*(k%8) + rr0); lane owns channels n..n+3.
+                    //    All residual loads of a batch are issued before its first store (memory-level parallelism:
+                    //    P.out may alias P.res as far as the compiler knows, so it cannot hoist them itself).
+                    constexpr int kBatch = 8;
 #pragma unroll
-                        for (int hp = 0; hp < 2; ++hp) {
-                            size_t qq[4];
-                            float4 rv[4];
+                    for (int k0 = 0; k0 < 16; k0 += kBatch) {
+                        size_t qq[kBatch];
+                        float4 rv[kBatch];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int m = quarter * 32 + 4 * (hp * 4 + i) + rr0;
-                                const int y = ybase + (m >> 3), x = xbase + sub * 8 + (m & 7);
-                                qq[i] = ((size_t)b * P.H + y) * P.W + x;
-                                rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (P.res_mode == 1) {
-                                    rv[i] = *reinterpret_cast<const float4*>(P.res + qq[i] * P.Cout + n);
-                                } else if (P.res_mode == 2) {
-                                    const int W2 = P.W * 2;
-                                    const float* rb = P.res + (((size_t)b * P.H * 2 + 2 * y) * W2 + 2 * x) * P.Cout + n;
-                                    const float4 r0 = *reinterpret_cast<const float4*>(rb);
-                                    const float4 r1 = *reinterpret_cast<const float4*>(rb + P.Cout);
-                                    const float4 r2 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout);
-                                    const float4 r3 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout + P.Cout);
-                                    rv[i].x = (r0.x + r1.x + r2.x + r3.x) * 0.25f;
-                                    rv[i].y = (r0.y + r1.y + r2.y + r3.y) * 0.25f;
-                                    rv[i].z = (r0.z + r1.z + r2.z + r3.z) * 0.25f;
-                                    rv[i].w = (r0.w + r1.w + r2.w + r3.w) * 0.25f;
-                                } else if (P.res_mode == 3) {
-                                    const int Hh = P.H / 2, Wh = P.W / 2;
-                                    rv[i] = *reinterpret_cast<const float4*>(
-                                        P.res + (((size_t)b * Hh + (y >> 1)) * Wh + (x >> 1)) * P.Cout + n);
-                                }
-                            }
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int rw = 4 * (hp * 4 + i) + rr0;   // staged row = tile row quarter*32 + rw
-                                const float4 t4 = *reinterpret_cast<const float4*>(stg + rw * kStgPitch + cc);
-                                float v[4] = {t4.x + bias4.x, t4.y + bias4.y, t4.z + bias4.z, t4.w + bias4.w};
-                                v[0] += emb4.x; v[1] += emb4.y; v[2] += emb4.z; v[3] += emb4.w;
-                                v[0] += rv[i].x; v[1] += rv[i].y; v[2] += rv[i].z; v[3] += rv[i].w;
-                                *reinterpret_cast<float4*>(P.out + qq[i] * P.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) { s1[e] += v[e]; s2[e] += v[e] * v[e]; }
+                        for (int k = 0; k < kBatch; ++k) {
+                            const int sub = (k0 + k) >> 3;
+                            const int m = quarter * 32 + 4 * ((k0 + k) & 7) + rr0;
+                            const int y = ybase + (m >> 3), x = xbase + sub * 8 + (m & 7);
+                            qq[k] = ((size_t)b * P.H + y) * P.W + x;
+                            rv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (P.res_mode == 1) {
+                                rv[k] = *reinterpret_cast<const float4*>(P.res + qq[k] * P.Cout + n);
+                            } else if (P.res_mode == 2) {
+                                const int W2 = P.W * 2;
+                                const float* rb = P.res + (((size_t)b * P.H * 2 + 2 * y) * W2 + 2 * x) * P.Cout + n;
+                                const float4 r0 = *reinterpret_cast<const float4*>(rb);
+                                const float4 r1 = *reinterpret_cast<const float4*>(rb + P.Cout);
+                                const float4 r2 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout);
+                                const float4 r3 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout + P.Cout);
+                                rv[k].x = (r0.x + r1.x + r2.x + r3.x) * 0.25f;
+                                rv[k].y = (r0.y + r1.y + r2.y + r3.y) * 0.25f;
+                                rv[k].z = (r0.z + r1.z + r2.z + r3.z) * 0.25f;
+                                rv[k].w = (r0.w + r1.w + r2.w + r3.w) * 0.25f;
+                            } else if (P.res_mode == 3) {
+                                const int Hh = P.H / 2, Wh = P.W / 2;
+                                rv[k] = *reinterpret_cast<const float4*>(
+                                    P.res + (((size_t)b * Hh + (y >> 1)) * Wh + (x >> 1)) * P.Cout + n);
                             }
                         }
+#pragma unroll
+                        for (int k = 0; k < kBatch; ++k) {
+                            const int sub = (k0 + k) >> 3;
+                            const int rw = 4 * ((k0 + k) & 7) + rr0;
+                            const float4 t4 = *reinterpret_cast<const float4*>(stg + (sub * 32 + rw) * kStgPitch + cc);
+                            float v[4] = {t4.x + bias4.x, t4.y + bias4.y, t4.z + bias4.z, t4.w + bias4.w};
+                            v[0] += emb4.x; v[1] += emb4.y; v[2] += emb4.z; v[3] += emb4.w;
+                            v[0] += rv[k].x; v[1] += rv[k].y; v[2] += rv[k].z; v[3] += rv[k].w;
+                            *reinterpret_cast<float4*>(P.out + qq[k] * P.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { s1[e] += v[e]; s2[e] += v[e] * v[e]; }
+                        }
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
                 if (P.gn_stats) {   // warp-uniform; all pixels of the CTA's region belong to sample b
                     // lanes with equal (lane & 7) hold the same 4 channels for different pixel rows
 #pragma unroll
@@ -489,7 +495,7 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     P.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
     const int Ktot = 9 * d->Ca + d->Cr1 + d->Cr2;
     const int b_bytes = (P.BN / 2) * kRowBytes;
-    int stages = (204 * 1024) / (kABytes + 3 * b_bytes);
+    int stages = (186 * 1024) / (kABytes + 3 * b_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     P.stages = stages;
     P.n_tiles_n = adp_ceil_div(d->Cout, P.BN);
@@ -507,7 +513,7 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     if (d->r2 && (rc = make_act_map3(&m2, d->r2, f16, d->Cr2, d->W, d->H, d->B, 16))) return rc;
     if ((rc = make_w_map3(&mw, d->w, f16, Ktot, d->Cout, P.BN / 2))) return rc;
 
-    const size_t smem = (size_t)stages * (kABytes + 3 * b_bytes) + 256 + 4 * 32 * kStgPitch * 4 + 1024;
+    const size_t smem = (size_t)stages * (kABytes + 3 * b_bytes) + 256 + 4 * 64 * kStgPitch * 4 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

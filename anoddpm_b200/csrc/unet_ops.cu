@@ -620,7 +620,7 @@ extern "C" int anoddpm_gn_apply(void* out_v, void* raw_out_v, const float* x1, i
     const int V = (gn_vec(C1, C2, groups, x1, x2) == 4 && al16(out) && (!raw_out || al16(raw_out))) ? 4 : 1;
     const int Ho = mode == 1 ? H / 2 : (mode == 2 ? H * 2 : H), Wo = mode == 1 ? W / 2 : (mode == 2 ? W * 2 : W);
     const int npo = Ho * Wo;
-    int wpc = 1024;  // output pixels per CTA
+    int wpc = 512;   // output pixels per CTA (>= 6 waves at full resolution: small tail)
     while (wpc > 32 && (long long)adp_ceil_div(npo, wpc) * B < 148 * 4) wpc >>= 1;
     dim3 grid((unsigned)adp_ceil_div(npo, wpc), B);
     cudaStream_t st = (cudaStream_t)stream;

@@ -168,7 +168,8 @@ def test_gn_apply_and_attention_fp16_outputs():
     for out, raw, mode in ((o32, None, 0), (o16, r16, 2)):
         _lib.call("anoddpm_gn_apply", _lib.ptr(out), _lib.ptr(raw), _lib.ptr(xn), C, None, 0, _lib.ptr(stats), None,
                   _lib.ptr(gamma), _lib.ptr(beta), B, H, W, 32, 1e-5, 1, 0, mode, _lib.stream())
-    assert torch.equal(o16, o32.half()) and torch.equal(r16, xn.half())      # fp16 = round-to-nearest of the fp32 result
+    # fp16 = round-to-nearest of the fp32 result (the rounded-output modes use the ~2 ulp fast SiLU: allow 1 fp16 ulp)
+    assert torch.allclose(o16.float(), o32, rtol=2e-3, atol=1e-4) and torch.equal(r16, xn.half())
     qkv = torch.randn(B, 64, 3 * C, generator=g).to(DEV)
     a32 = torch.empty(B, 64, C, device=DEV)
     a16 = torch.empty(B, 64, C, device=DEV, dtype=torch.float16)
