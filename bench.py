@@ -218,15 +218,36 @@ def run_native(args):
            "gn_stats_passes_per_forward": getattr(eng, "stats_passes", 0)}
 
     if rank == 0:
+        x = None
+        torch.cuda.empty_cache()
         out["roofline"] = roofline(model, dev, B)
+        out["aux_rooflines"] = aux_rooflines(dev)
         out["cpu_baseline"] = cpu_baseline(sample_steps=2) if world == 1 and not args.no_cpu_baseline else None
         print(json.dumps(out))
     D.barrier()
 
 
+def _time_ms(fn, n=10, warm=3):
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel/shape (conv 128->128 @256^2 bs 32,
+# fp16 operands, fp32 output) from the committed `ncu --set full` capture profiles/r01b_ncu_conv_tc3.md
+NCU_TRAFFIC_DOMINANT = {"bytes": 0.538801e9 + 1.016694e9, "source": "profiles/r01b_ncu_conv_tc3.md (launch 1)"}
+
+
 def roofline(model, dev, B):
-    """Dominant kernel = conv_tc_kernel (tcgen05 kind::tf32).  Live CUDA-event timing of the three conv shapes that
-    carry 61% of the UNet MACs, through the same C-ABI entry point the engine uses."""
+    """Dominant kernel = the tensor-core conv (conv_tc3_kernel).  Live CUDA-event timing, through the same C-ABI entry
+    point the engine uses, of the three conv shapes that carry 61% of the UNet MACs; the
+    headline entry is the single most frequent shape (128->128 @256^2: 9 launches per forward, 31% of the MACs)."""
     import ctypes
     from anoddpm_b200 import _lib
     from anoddpm_b200.engine import round_tf32_
@@ -247,27 +268,76 @@ def roofline(model, dev, B):
         d.B, d.H, d.W, d.Ca, d.Cout, d.ksize, d.impl = B, HW, HW, Ci, Co, 3, impl
         d.gn_stats = None
         d.operand_f16 = 1 if f16 else 0
-        for _ in range(3):
-            _lib.call("anoddpm_conv", ctypes.byref(d), _lib.stream())
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n = 10
-        e0.record()
-        for _ in range(n):
-            _lib.call("anoddpm_conv", ctypes.byref(d), _lib.stream())
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / n
+        ms = _time_ms(lambda: _lib.call("anoddpm_conv", ctypes.byref(d), _lib.stream()))
         flop = 2.0 * B * HW * HW * Co * 9 * Ci
-        res.append({"shape": f"conv3x3 {Ci}->{Co} @{HW}^2 bs{B}", "ms": ms, "tflops": flop / ms / 1e9, "count_per_forward": count})
+        abytes = a.numel() * a.element_size() + out.numel() * 4 + w.numel() * w.element_size()
+        res.append({"shape": f"conv3x3 {Ci}->{Co} @{HW}^2 bs{B}", "ms": ms, "tflops": flop / ms / 1e9,
+                    "count_per_forward": count, "flop": flop, "algorithmic_bytes": abytes})
         tot_flop += flop * count
         tot_ms += ms * count
         del a, w, out
-    achieved = tot_flop / tot_ms / 1e9
-    return {"bound": "tensor", "kernel": {3: "conv_tc3_kernel (tcgen05.mma.cta_group::2 kind::%s, halo-reuse persistent CTA pairs, TMA-fed implicit GEMM)" % ("f16" if f16 else "tf32"), 2: "conv_tc2_kernel (tcgen05.mma.cta_group::2 kind::tf32, persistent CTA pairs, TMA-fed implicit GEMM)", 1: "conv_tc_kernel (tcgen05.mma kind::tf32, TMA-fed implicit GEMM)", 0: "conv_simt_kernel"}[impl],
-            "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-            "peak_note": f"dense bf16 cuBLAS sustained, {pk['src']} (MEASURED_PEAKS.json)" + ("; kind::f16 operands issue at the bf16 rate" if f16 else
-                         f"; kind::tf32 issues at half the bf16 rate, so frac of the tf32 rate = {achieved / (pk['bf16_sustained'] / 2):.3f}"),
-            "traffic": None, "per_shape": res,
-            "algorithmic": "2*M*N*K flop per launch, M=B*H*W, N=Cout, K=9*Cin; weighted by launches per forward"}
+    dom = res[0]
+    kname = {3: "conv_tc3_kernel (tcgen05.mma.cta_group::2 kind::%s, halo-reuse persistent CTA pairs, TMA-fed implicit GEMM)" % ("f16" if f16 else "tf32"),
+             2: "conv_tc2_kernel (tcgen05.mma.cta_group::2, persistent CTA pairs)", 1: "conv_tc_kernel (tcgen05.mma kind::tf32)",
+             0: "conv_simt_kernel"}[impl]
+    peak = pk["bf16_burst"]      # the kernel is timed alone here -> burst figure (B200_PROFILING.md)
+    return {"bound": "tensor", "kernel": kname, "shape": dom["shape"], "achieved": dom["tflops"], "peak": peak,
+            "unit": "TFLOP/s", "frac": dom["tflops"] / peak,
+            "peak_note": f"dense bf16 cuBLAS burst, {pk['src']} (MEASURED_PEAKS.json); sustained figure {pk['bf16_sustained']}: frac "
+                         f"{dom['tflops'] / pk['bf16_sustained']:.3f}" + ("" if f16 else "; kind::tf32 issues at half the bf16 rate"),
+            "algorithmic": "2*M*N*K flop per launch, M=B*H*W, N=Cout, K=9*Cin", "flop_per_launch": dom["flop"],
+            "algorithmic_bytes": dom["algorithmic_bytes"],
+            "traffic": NCU_TRAFFIC_DOMINANT["bytes"] if (f16 and impl == 3 and B == 32) else None,
+            "traffic_source": NCU_TRAFFIC_DOMINANT["source"],
+            "weighted_3_shapes_tflops": tot_flop / tot_ms / 1e9, "per_shape": res}
+
+
+def aux_rooflines(dev):
+    """HBM-bound fused elementwise kernels at a size that exercises HBM (bs 256: 64 MiB per tensor, > 126 MB L2 in total),
+    GroupNorm apply at full resolution, and the simplex generator (BASELINE config 5, FP64-ALU bound)."""
+    from anoddpm_b200 import GaussianDiffusionModel, _lib, get_beta_schedule
+    from anoddpm_b200.simplex import init_tables
+    pk = peaks()
+    out = {}
+    D = GaussianDiffusionModel([256, 256], get_beta_schedule(1000, "linear"))
+    Bq = 256
+    x, n, e = (torch.randn(Bq, 1, 256, 256, device=dev) for _ in range(3))
+    t = torch.randint(0, 1000, (Bq,), device=dev)
+    tab = D._tables(dev)
+    o = torch.empty_like(x)
+    per = x.numel() // Bq
+    ms = _time_ms(lambda: _lib.call("anoddpm_q_sample", _lib.ptr(o), _lib.ptr(x), _lib.ptr(n), _lib.ptr(t), _lib.ptr(tab[0]),
+                                    _lib.ptr(tab[1]), Bq, per, _lib.stream()))
+    gb = 12.0 * x.numel() / 1e9
+    out["q_sample"] = {"bound": "hbm", "shape": "(256,1,256,256)", "bytes": gb * 1e9, "ms": ms, "achieved": gb / ms * 1e3,
+                       "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / ms * 1e3 / pk["hbm_gbs"]}
+    ms = _time_ms(lambda: _lib.call("anoddpm_p_sample", _lib.ptr(o), None, _lib.ptr(x), _lib.ptr(e), _lib.ptr(n), _lib.ptr(t),
+                                    _lib.ptr(tab[4:]), 1000, Bq, per, _lib.stream()))
+    gb = 16.0 * x.numel() / 1e9
+    out["p_sample"] = {"bound": "hbm", "shape": "(256,1,256,256)", "bytes": gb * 1e9, "ms": ms, "achieved": gb / ms * 1e3,
+                       "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / ms * 1e3 / pk["hbm_gbs"]}
+    del x, n, e, o
+    # GroupNorm apply, (32,256,256,128) fp32 -> fp16
+    xa = torch.randn(32, 256, 256, 128, device=dev)
+    st = torch.zeros(32, 128, 2, device=dev, dtype=torch.float64)
+    _lib.call("anoddpm_gn_stats", _lib.ptr(st), _lib.ptr(xa), 128, 32, 65536, _lib.stream())
+    g1, b1 = torch.ones(128, device=dev), torch.zeros(128, device=dev)
+    oa = torch.empty(32, 256, 256, 128, device=dev, dtype=torch.float16)
+    ms = _time_ms(lambda: _lib.call("anoddpm_gn_apply", _lib.ptr(oa), None, _lib.ptr(xa), 128, None, 0, _lib.ptr(st), None,
+                                    _lib.ptr(g1), _lib.ptr(b1), 32, 256, 256, 32, 1e-5, 1, 0, 2, _lib.stream()))
+    gb = 6.0 * xa.numel() / 1e9
+    out["gn_apply"] = {"bound": "hbm", "shape": "(32,256,256,128) fp32 -> fp16", "bytes": gb * 1e9, "ms": ms,
+                       "achieved": gb / ms * 1e3, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / ms * 1e3 / pk["hbm_gbs"]}
+    del xa, oa
+    # simplex: BASELINE config 5 = 3-D field (32,256,256) x 8 octaves (there is no 4-D generator in the reference, SURVEY F3)
+    tabs = torch.from_numpy(init_tables([12345])).to(dev)
+    vol = torch.empty(32, 256, 256, device=dev)
+    ms = _time_ms(lambda: _lib.call("anoddpm_simplex_octaves", _lib.ptr(vol), 0, 32, 256, 256, _lib.ptr(tabs), None, 8, 0.8, 64.0,
+                                    _lib.stream()))
+    out["simplex_config5"] = {"bound": "fp64 alu", "shape": "(32,256,256) x 8 octaves, fp32 out", "ms": ms,
+                              "mvox_per_s": 32 * 65536 / ms / 1e3, "gflops_fp64": 146.0 * 8 * 32 * 65536 / ms / 1e6,
+                              "algorithmic": "~146 fp64 flop per voxel-octave (SURVEY App. C.4)"}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
@@ -303,9 +373,17 @@ def cpu_threads():
 def cpu_baseline(sample_steps=2):
     threads = cpu_threads()
     s = cpu_reverse_step_seconds(sample_steps, threads)
+    # simplex microbench (config 5) on the host cores with the C oracle
+    from oracle.simplex_oracle import OracleSimplex
+    O = OracleSimplex(12345, threads=threads)
+    O.rand_3d_octaves((4, 64, 64), 2, 0.8, 64)
+    t0 = time.perf_counter()
+    O.rand_3d_octaves((32, 256, 256), 8, 0.8, 64)
+    sx = time.perf_counter() - t0
     return {"value": 1.0 / (T_DISTANCE * s), "unit": "images/s", "cores": threads, "kind": "port",
             "sample": f"{sample_steps} reverse steps at bs 1 (256x256, same UNet) after 1 warm-up step, "
-                      f"{s:.3f} s/step, extrapolated x800 steps/image", "s_per_step": s}
+                      f"{s:.3f} s/step, extrapolated x800 steps/image", "s_per_step": s,
+            "simplex_config5_mvox_per_s": 32 * 65536 / sx / 1e6}
 
 
 def run_reference(args):
