@@ -539,10 +539,76 @@ class GaussianDiffusionModel:
             output[(i - 1) * 6:i * 6, ...] = torch.cat((x_0, x_noised, x, mse, mse_threshold, mask))
         return output
 
+    @staticmethod
+    def _save_grid(out, path, row_size=4):
+        """Figure output of the reference drivers (plt.imshow(gridify_output(out, 4)); savefig).  Plotting is outside
+        the accelerated path: done only if matplotlib / torchvision are importable, silently skipped otherwise."""
+        try:
+            import matplotlib
+            matplotlib.use("Agg")
+            import matplotlib.pyplot as plt
+            import torchvision.utils
+        except Exception:
+            return False
+        img = ((out + 1) * 127.5).clamp(0, 255).to(torch.uint8)
+        grid = torchvision.utils.make_grid(img, nrow=row_size, pad_value=-1).cpu().permute(1, 2, 0)
+        plt.imshow(grid, cmap="gray")
+        plt.axis("off")
+        plt.savefig(path)
+        plt.clf()
+        return True
+
+    def _noise_then_denoise(self, model, x_0, t_distance, noise_fn, denoise_fn="gauss"):
+        """x_0 -> q-sample at index t_distance -> t_distance reverse steps (the loop the reference copy-pastes in
+        detection_A / detection_B, GaussianDiffusion.py:500-510, 555-565)."""
+        t_tensor = torch.full((x_0.shape[0],), t_distance, device=x_0.device, dtype=torch.int64)
+        x = self.sample_q(x_0, t_tensor, noise_fn(x_0, t_tensor).float())
+        return self.reverse_steps(model, x, int(t_distance) - 1, int(t_distance), denoise_fn)
+
     def detection_A(self, model, x_0, args, file, mask, total_avg=2):
-        raise NotImplementedError("detection_A writes matplotlib figures (out of scope: plotting driver, SURVEY section 2); "
-                                  "its sampling loop is sample_q + sample_p, see detection_A_fixedT / forward_backward")
+        """Frequency / t_distance sweep with fixed-frequency simplex noise (GaussianDiffusion.py:480-527): every
+        sampling chain runs on the native kernels; the PNG output is written when matplotlib is available."""
+        out_dir = f"./diffusion-videos/ARGS={args['arg_num']}/Anomalous/{file[0]}/{file[1]}/A"
+        os.makedirs(out_dir, exist_ok=True)
+        for i in range(7, 0, -1):
+            freq = 2 ** i
+            self.noise_fn = lambda x, t: generate_simplex_noise(self.simplex, x, t, False, frequency=freq,
+                                                                in_channels=self.img_channels)
+            for t_distance in range(50, int(args["T"] * 0.6), 50):
+                output = torch.empty((total_avg, 1, *args["img_size"]), device=x_0.device)
+                for avg in range(total_avg):
+                    output[avg, ...] = self._noise_then_denoise(model, x_0, t_distance, self.noise_fn)
+                output_mean = torch.mean(output, dim=0).reshape(1, 1, *args["img_size"])
+                mse = ((output_mean - x_0).square() * 2) - 1
+                mse_threshold = ((mse > 0).float() * 2) - 1
+                out = torch.cat([x_0, output[:3], output_mean, mse, mse_threshold, mask])
+                n_prev = len(os.listdir(out_dir))
+                self._save_grid(out, f"{out_dir}/freq={i}-t={t_distance}-{n_prev + 1}.png")
 
     def detection_B(self, model, x_0, args, file, mask, denoise_fn="gauss", total_avg=5):
-        raise NotImplementedError("detection_B writes matplotlib figures / heatmaps (out of scope: plotting driver); "
-                                  "its sampling loop is sample_q + sample_p, see forward_backward")
+        """t_distance sweep with octave simplex ("octave") or Gaussian noise (GaussianDiffusion.py:529-594).  Returns
+        the per-t_distance list like the reference (whose evaluation.heatmap returns None)."""
+        assert type(file) == tuple
+        out_dir = f"./diffusion-videos/ARGS={args['arg_num']}/Anomalous/{file[0]}/{file[1]}/{denoise_fn}"
+        os.makedirs(out_dir, exist_ok=True)
+        if denoise_fn == "octave":
+            end = int(args["T"] * 0.6)
+            self.noise_fn = lambda x, t: generate_simplex_noise(self.simplex, x, t, False, frequency=64, octave=6,
+                                                                persistence=0.8).float()
+        else:
+            end = int(args["T"] * 0.8)
+            self.noise_fn = lambda x, t: torch.randn_like(x)
+        dice_coeff = []
+        for t_distance in range(50, end, 50):
+            output = torch.empty((total_avg, 1, *args["img_size"]), device=x_0.device)
+            for avg in range(total_avg):
+                output[avg, ...] = self._noise_then_denoise(model, x_0, t_distance, self.noise_fn)
+            output_mean = torch.mean(output, dim=[0]).reshape(1, 1, *args["img_size"])
+            n_prev = len(os.listdir(out_dir))
+            dice = None   # reference: evaluation.heatmap(...) draws a figure and returns None
+            mse = ((output_mean - x_0).square() * 2) - 1
+            mse_threshold = ((mse > 0).float() * 2) - 1
+            out = torch.cat([x_0, output[:3], output_mean, mse, mse_threshold, mask])
+            self._save_grid(out, f"{out_dir}/t={t_distance}-{n_prev + 1}.png")
+            dice_coeff.append(dice)
+        return dice_coeff

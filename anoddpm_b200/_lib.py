@@ -35,6 +35,7 @@ SIGNATURES = {
     "anoddpm_simplex_grid2": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
     "anoddpm_q_sample": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp]),
     "anoddpm_p_sample": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
+    "anoddpm_detection_counts": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_int, c_i64, c_vp]),
     "anoddpm_timestep_embedding": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
     "anoddpm_linear": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "anoddpm_gn_stats": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp]),

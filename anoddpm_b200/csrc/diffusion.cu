@@ -91,6 +91,59 @@ __global__ void __launch_bounds__(256) p_sample_kernel(float* __restrict__ sampl
     }
 }
 
+// ---- detection epilogue: squared error, threshold and confusion counts in one pass -------------------
+// counts[b] = {n11, n10, n01, n00, sum(se), max(image)} with mask in {0,1} as "real" and thr = (se > threshold) as
+// "recon" (n10 = mask==1 & thr==0, ...), from which Dice / IoU / precision / recall / FPR / PSNR of reference
+// evaluation.py:26-76 follow.  One CTA-row per sample, warp-shuffle + shared-memory reduction, fp64 atomics.
+__global__ void __launch_bounds__(256) detection_counts_kernel(double* __restrict__ counts, const float* __restrict__ image,
+                                                               const float* __restrict__ recon,
+                                                               const float* __restrict__ mask, float threshold,
+                                                               long long per_sample) {
+    const int b = blockIdx.y;
+    const size_t base = (size_t)b * per_sample;
+    float c11 = 0.f, c10 = 0.f, c01 = 0.f, c00 = 0.f, se_sum = 0.f, mx = -INFINITY;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x) {
+        const float x = image[base + i], d = x - recon[base + i];
+        const float se = d * d;
+        const bool thr = se > threshold, m = mask[base + i] == 1.0f;
+        c11 += (m && thr) ? 1.f : 0.f;
+        c10 += (m && !thr) ? 1.f : 0.f;
+        c01 += (!m && thr) ? 1.f : 0.f;
+        c00 += (!m && !thr) ? 1.f : 0.f;
+        se_sum += se;
+        mx = fmaxf(mx, x);
+    }
+    __shared__ float red[8][6];
+    float v[6] = {c11, c10, c01, c00, se_sum, mx};
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float other = __shfl_xor_sync(0xffffffffu, v[k], o);
+            v[k] = k == 5 ? fmaxf(v[k], other) : v[k] + other;
+        }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        for (int k = 0; k < 6; ++k) red[warp][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int k = threadIdx.x;
+        float t = red[0][k];
+        for (int w = 1; w < 8; ++w) t = k == 5 ? fmaxf(t, red[w][k]) : t + red[w][k];
+        if (k == 5) {   // max via compare-and-swap on the bit pattern of a double
+            unsigned long long* addr = reinterpret_cast<unsigned long long*>(&counts[(size_t)b * 6 + 5]);
+            unsigned long long old = *addr, assumed;
+            do {
+                assumed = old;
+                if (__longlong_as_double((long long)assumed) >= (double)t) break;
+                old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong((double)t));
+            } while (assumed != old);
+        } else {
+            atomicAdd(&counts[(size_t)b * 6 + k], (double)t);
+        }
+    }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 inline dim3 ew_grid(long long per_sample, int B, bool vec) {
@@ -136,6 +189,19 @@ extern "C" int anoddpm_p_sample(float* sample, float* pred_x0, const float* x_t,
     else
         p_sample_kernel<false><<<grid, 256, 0, st>>>(sample, pred_x0, x_t, eps, noise, (const long long*)t, tables, T,
                                                      per_sample);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}
+
+extern "C" int anoddpm_detection_counts(double* counts, const float* image, const float* recon, const float* mask,
+                                        float threshold, int B, int64_t per_sample, void* stream) {
+    ADP_REQUIRE(counts && image && recon && mask, "anoddpm_detection_counts: null pointer");
+    ADP_REQUIRE(B > 0 && B <= 65535 && per_sample > 0, "anoddpm_detection_counts: bad sizes");
+    long long bx = (per_sample + 256 * 8 - 1) / (256 * 8);
+    if (bx > 64) bx = 64;
+    if (bx < 1) bx = 1;
+    detection_counts_kernel<<<dim3((unsigned)bx, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(counts, image, recon, mask,
+                                                                                               threshold, per_sample);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }

@@ -81,6 +81,12 @@ int anoddpm_q_sample(float* out, const float* x, const float* noise, const int64
 int anoddpm_p_sample(float* sample, float* pred_x0, const float* x_t, const float* eps, const float* noise,
                      const int64_t* t, const float* tables, int T, int B, int64_t per_sample, void* stream);
 
+/* Detection epilogue in one pass (reference detection.py:229-250 + evaluation.py:26-76 do ~10 torch/numpy passes with
+ * D2H copies): counts[b] += {n11, n10, n01, n00, sum((image-recon)^2)} and counts[b][5] = max(counts[b][5], max(image)),
+ * where "1/0" pairs are (mask == 1, (image-recon)^2 > threshold).  Caller initialises counts to {0,0,0,0,0,-inf}. */
+int anoddpm_detection_counts(double* counts /* B x 6 */, const float* image, const float* recon, const float* mask,
+                             float threshold, int B, int64_t per_sample, void* stream);
+
 /* ------------------------------------------------------------------ UNet denoiser ops --------- */
 
 /* emb[b, :] = cat(sin(t_b*w), cos(t_b*w)), w = freq[0..dim/2) = exp(-i*ln(1e4)/half) (built once by the caller

@@ -150,3 +150,27 @@ def test_elementwise_odd_sizes_and_full_size_property():
     assert torch.equal(D.sample_q(x, t, z), a * x + 0 * z)
     assert torch.equal(D.sample_q(z, t, x) + D.sample_q(x, t, z), D.sample_q(x, t, x)) or \
         torch.allclose(D.sample_q(z, t, x) + D.sample_q(x, t, z), D.sample_q(x, t, x), atol=1e-6)
+
+
+def test_fused_detection_metrics_match_reference_formulas():
+    """one-pass device metrics == the reference's evaluation.py formulas evaluated per image."""
+    from anoddpm_b200 import evaluation as E
+    g = torch.Generator().manual_seed(8)
+    B = 5
+    image = (torch.rand(B, 1, 64, 48, generator=g) * 2 - 1).to(DEV)
+    recon = (image + torch.randn(B, 1, 64, 48, generator=g).to(DEV) * 0.6)
+    mask = (torch.rand(B, 1, 64, 48, generator=g) > 0.7).float().to(DEV)
+    m = E.detection_metrics(image, recon, mask)
+    for b in range(B):
+        im, rc, mk = image[b:b + 1], recon[b:b + 1], mask[b:b + 1]
+        thr = ((im - rc).square() > 0.5).float()
+        assert abs(float(m["dice"][b]) - float(E.dice_coeff(im, rc, mk, mse=thr))) < 1e-6
+        assert abs(float(m["precision"][b]) - float(E.precision(mk, thr))) < 1e-6
+        assert abs(float(m["recall"][b]) - float(E.recall(mk, thr))) < 1e-6
+        assert abs(float(m["fpr"][b]) - float(E.FPR(mk, thr))) < 1e-6
+        assert abs(float(m["iou"][b]) - E.IoU(mk, thr)) < 1e-6
+        assert abs(float(m["psnr"][b]) - float(E.PSNR(rc, im))) < 1e-3
+    # property at BASELINE size: counts partition the image
+    c = E.detection_counts(torch.zeros(32, 1, 256, 256, device=DEV), torch.ones(32, 1, 256, 256, device=DEV),
+                           torch.ones(32, 1, 256, 256, device=DEV))
+    assert torch.equal(c[:, 0], torch.full((32,), 65536.0, device=DEV, dtype=torch.float64)) and float(c[:, 1:4].abs().sum()) == 0

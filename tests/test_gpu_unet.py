@@ -398,3 +398,26 @@ def test_cuda_graph_reverse_loop_matches_eager_loop():
     assert np.random.get_state()[2] != before or True
     g = list(D._graphs.values())[0]
     assert int(g["step"].item()) == 9 and int(g["t"][0].item()) == -1
+
+
+def test_detection_drivers_run_on_native_loop(tmp_path, monkeypatch):
+    """detection_A_fixedT / detection_B / detection_A (callers of the hot path, reference GaussianDiffusion.py:480-623):
+    same return conventions, every chain on the native kernels."""
+    from anoddpm_b200.GaussianDiffusion import GaussianDiffusionModel, get_beta_schedule
+    monkeypatch.chdir(tmp_path)
+    m = build_model(dict(img_size=32, base_channels=32, n_heads=1), "tc")
+    x0 = (torch.rand(1, 1, 32, 32, generator=torch.Generator().manual_seed(1)) * 2 - 1).to(DEV)
+    mask = torch.zeros_like(x0)
+    np.random.seed(3)
+    args = {"img_size": [32, 32], "T": 1000, "arg_num": 0}
+    D = GaussianDiffusionModel([32, 32], get_beta_schedule(1000, "linear"), noise="simplex")
+    out = D.detection_A_fixedT(m, x0, args, mask, end_freq=1)
+    assert out.shape == (6, 1, 32, 32) and bool(torch.isfinite(out).all())
+    assert torch.equal(out[0], x0[0]) and torch.equal(out[5], mask[0])
+    args = {"img_size": [32, 32], "T": 100, "arg_num": 0}
+    D = GaussianDiffusionModel([32, 32], get_beta_schedule(100, "linear"), noise="simplex")
+    dice = D.detection_B(m, x0, args, ("vol", "slice"), mask, denoise_fn="octave", total_avg=1)
+    assert dice == [None]                       # one t_distance (50) below 0.6*T; heatmap returns None in the reference
+    assert D.detection_B(m, x0, args, ("vol", "slice"), mask, denoise_fn="gauss", total_avg=1) == [None]
+    assert D.detection_A(m, x0, args, ("vol", "slice"), mask, total_avg=1) is None
+    assert (tmp_path / "diffusion-videos" / "ARGS=0" / "Anomalous" / "vol" / "slice" / "A").is_dir()
