@@ -36,6 +36,9 @@ SIGNATURES = {
     "anoddpm_q_sample": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp]),
     "anoddpm_p_sample": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
     "anoddpm_detection_counts": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_int, c_i64, c_vp]),
+    "anoddpm_sumsq": (c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "anoddpm_adamw_ema_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_int,
+                                       c_f32, c_f32, c_vp]),
     "anoddpm_timestep_embedding": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
     "anoddpm_linear": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "anoddpm_gn_stats": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp]),

@@ -46,7 +46,8 @@ struct Tc3Args {
     int ke;                    // elements per 128-byte K-block row: 32 (fp32 operands) or 64 (fp16 operands)
     int n_tiles_n, n_tiles;    // tiles along N, total pair tiles
     int regions_x, regions_per_img, n_regions;   // 16x16 regions
-    double* gn_stats;          // optional [B][Cout][2]: per-channel (sum, sum of squares) of the output
+    double* gn_stats;          // optional [REPLICAS][B][Cout][2]: per-channel (sum, sum of squares) of the output
+    long long stat_replica_stride;   // B*Cout*2
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -391,7 +392,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
                     }
                     if (nvalid && lane < 8) {
-                        double* st = P.gn_stats + ((size_t)b * P.Cout + n) * 2;
+                        // replica = cluster id mod 8: the ~148 CTAs working on the same image hit 8x more addresses
+                        double* st = P.gn_stats + (size_t)(cluster_id % ANODDPM_STAT_REPLICAS) * P.stat_replica_stride +
+                                     ((size_t)b * P.Cout + n) * 2;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             atomicAdd(st + 2 * e, (double)s1[e]);
@@ -504,6 +507,7 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     P.n_regions = d->B * P.regions_per_img;
     P.n_tiles = adp_ceil_div(P.n_regions, 2) * P.n_tiles_n;
     P.gn_stats = d->gn_stats;
+    P.stat_replica_stride = (long long)d->B * d->Cout * 2;
 
     CUtensorMap ma, m1, m2, mw;
     int rc;

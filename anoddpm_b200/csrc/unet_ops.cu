@@ -153,20 +153,34 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(float* __restrict__ out, 
                                                        int rtf32, int pix_per_cta) {
     __shared__ float s_mean[64], s_rstd[64];
     const int b = blockIdx.y, C = C1 + C2, gs = C / groups, ncv = C / V;
-    if (threadIdx.x < groups) {
-        // group statistics = sum of the per-channel sums of its gs channels (which may straddle the two sources)
-        const double n = (double)H * W * gs;
+    {
+        // group statistics = sum over the group's gs channels (which may straddle the two sources) and over the statistic
+        // replicas; thread (g, r) adds up replica r of group g, 8 consecutive lanes are then combined by shuffles
+        const int g = threadIdx.x / ANODDPM_STAT_REPLICAS, r = threadIdx.x % ANODDPM_STAT_REPLICAS;
+        const int nb = gridDim.y;   // batch size
         double s = 0.0, q = 0.0;
-        for (int c = threadIdx.x * gs; c < (threadIdx.x + 1) * gs; ++c) {
-            const double* st = c < C1 ? stats1 + ((size_t)b * C1 + c) * 2 : stats2 + ((size_t)b * C2 + (c - C1)) * 2;
-            s += st[0];
-            q += st[1];
+        if (g < groups) {
+            for (int c = g * gs; c < (g + 1) * gs; ++c) {
+                const bool first = c < C1;
+                const int Cs = first ? C1 : C2, cc = first ? c : c - C1;
+                const double* st = (first ? stats1 : stats2) + (size_t)r * nb * Cs * 2 + ((size_t)b * Cs + cc) * 2;
+                s += st[0];
+                q += st[1];
+            }
         }
-        const double m = s / n;
-        double var = q / n - m * m;
-        if (var < 0) var = 0;
-        s_mean[threadIdx.x] = (float)m;
-        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+        for (int o = 1; o < ANODDPM_STAT_REPLICAS; o <<= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (g < groups && r == 0) {
+            const double n = (double)H * W * gs;
+            const double m = s / n;
+            double var = q / n - m * m;
+            if (var < 0) var = 0;
+            s_mean[g] = (float)m;
+            s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+        }
     }
     __syncthreads();
     const int Ho = mode == 1 ? H / 2 : (mode == 2 ? H * 2 : H);
@@ -410,6 +424,68 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(float* __restrict__ out,
     }
 }
 
+// stem, 4 horizontally adjacent pixels per thread (W % 4 == 0): the 3 x 6 input window is loaded once per input
+// channel, index arithmetic is amortised over 16 outputs, four coalesced float4 stores per thread.
+__global__ void __launch_bounds__(256) conv_stem4_kernel(float* __restrict__ out, const float* __restrict__ x,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         int B, int Cin, int H, int W, int Cout) {
+    extern __shared__ float sw[];  // [Cin*9][Cout] then bias[Cout]
+    const int K = Cin * 9;
+    for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+        const int co = i / K, k = i - co * K;
+        sw[k * Cout + co] = w[i];
+    }
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[K * Cout + i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const int nc4 = Cout >> 2;
+    const int gpb = blockDim.x / nc4;              // pixel groups per block iteration
+    const int gl = threadIdx.x / nc4, c4 = (threadIdx.x - gl * nc4) * 4;
+    if (gl >= gpb) return;
+    const int W4 = W >> 2;
+    const int ngroups = B * H * W4;
+    for (int g = blockIdx.x * gpb + gl; g < ngroups; g += gridDim.x * gpb) {
+        const int xg = g % W4, yh = (g / W4) % H, b = g / (W4 * H);
+        const int x0 = xg * 4;
+        float acc[4][4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[p][e] = sw[K * Cout + c4 + e];
+        for (int ci = 0; ci < Cin; ++ci) {
+            const float* xp = x + ((size_t)b * Cin + ci) * H * W;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int yy = yh + ky - 1;
+                if (yy < 0 || yy >= H) continue;
+                float win[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int xx = x0 + j - 1;
+                    win[j] = (xx >= 0 && xx < W) ? xp[(size_t)yy * W + xx] : 0.f;
+                }
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const F4 wv = ld4(&sw[(ci * 9 + ky * 3 + kx) * Cout + c4]);
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const float v = win[p + kx];
+                        acc[p][0] = fmaf(v, wv.x, acc[p][0]);
+                        acc[p][1] = fmaf(v, wv.y, acc[p][1]);
+                        acc[p][2] = fmaf(v, wv.z, acc[p][2]);
+                        acc[p][3] = fmaf(v, wv.w, acc[p][3]);
+                    }
+                }
+            }
+        }
+        float* o = out + (((size_t)b * H + yh) * W + x0) * Cout + c4;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            F4 v; v.x = acc[p][0]; v.y = acc[p][1]; v.z = acc[p][2]; v.w = acc[p][3];
+            st4(o + (size_t)p * Cout, v);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- head: NHWC features -> NCHW image
 // CTA = 8x32 output pixels; per 16-channel chunk the (10 x 34)-pixel halo tile is staged in shared memory as
 // [pixel][20] floats (stride 20: 128-bit reads by 8 pixel-consecutive lanes touch all 32 banks once), weights of the
@@ -612,7 +688,7 @@ extern "C" int anoddpm_gn_apply(void* out_v, void* raw_out_v, const float* x1, i
     ADP_REQUIRE((C2 == 0) || stats2 != nullptr, "anoddpm_gn_apply: second source without statistics");
     ADP_REQUIRE((C2 == 0) == (x2 == nullptr), "anoddpm_gn_apply: x2/C2 mismatch");
     const int C = C1 + C2;
-    ADP_REQUIRE(groups > 0 && groups <= 64 && C % groups == 0, "anoddpm_gn_apply: bad groups");
+    ADP_REQUIRE(groups > 0 && groups * ANODDPM_STAT_REPLICAS <= 256 && C % groups == 0, "anoddpm_gn_apply: bad groups (at most 32)");
     ADP_REQUIRE(mode >= 0 && mode <= 2, "anoddpm_gn_apply: bad mode %d", mode);
     ADP_REQUIRE(mode != 1 || (H % 2 == 0 && W % 2 == 0), "anoddpm_gn_apply: avg-pool needs even H, W");
     ADP_REQUIRE(raw_out == nullptr || mode == 0, "anoddpm_gn_apply: raw_out needs mode 0");
@@ -675,7 +751,13 @@ extern "C" int anoddpm_conv_stem(float* out, const float* x, const float* w, con
     const int ppb = 256 / (Cout / 4) > 0 ? 256 / (Cout / 4) : 1;
     int blocks = adp_ceil_div((long long)B * H * W, ppb);
     if (blocks > 148 * 32) blocks = 148 * 32;
-    conv_stem_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(out, x, w, bias, B, Cin, H, W, Cout);
+    if (W % 4 == 0) {
+        int blocks4 = adp_ceil_div((long long)B * H * (W / 4), ppb);
+        if (blocks4 > 148 * 16) blocks4 = 148 * 16;
+        conv_stem4_kernel<<<blocks4, 256, smem, (cudaStream_t)stream>>>(out, x, w, bias, B, Cin, H, W, Cout);
+    } else {
+        conv_stem_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(out, x, w, bias, B, Cin, H, W, Cout);
+    }
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }

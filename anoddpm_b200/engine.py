@@ -6,11 +6,13 @@ GEMM, so a 32-channel K-block is one 128-byte TMA row); conv weights packed [Cou
 Ktot ordered tap-major / channel-minor followed by the 1x1 skip-connection channels; GroupNorm
 statistics fp64 (sum, sum of squares) per (sample, group).
 
-Fusion map of one ResBlock (reference UNet.py:202-217), 6 launches instead of ~20 library calls:
-    gn_stats(x[,skip]) -> gn_apply(+SiLU,+avgpool/upsample,+concat,+tf32 round)
-    -> conv3x3(+bias,+timestep-embedding row)
-    -> gn_stats -> gn_apply(+SiLU) -> conv3x3(+bias,+1x1 skip conv as extra K-blocks | +identity residual
-       with the x_upd resample folded into the epilogue read)
+Fusion map of one ResBlock (reference UNet.py:202-217), 4 launches instead of ~20 library calls:
+    gn_apply(cat(x, skip): +SiLU, +avgpool/upsample, +fp16/TF32 rounding, +rounded raw copy for the skip conv)
+    -> conv3x3(+bias, +timestep-embedding row, +per-channel statistics of h)
+    -> gn_apply(+SiLU) -> conv3x3(+bias, +1x1 skip conv as extra K-blocks | +identity residual with the x_upd
+       resample folded into the epilogue read, +per-channel statistics of the block output)
+Every activation carries its per-channel (sum, sum of squares) out of the conv epilogue that produced it, so GroupNorm
+needs a separate statistics pass only for the few tensors produced by other kernels (stem, 1x1 / 8x8 convs).
 """
 import ctypes
 
@@ -19,6 +21,7 @@ import torch
 from . import _lib
 from ._lib import ConvDesc, call, ptr, stream
 
+STAT_REPLICAS = 8     # ANODDPM_STAT_REPLICAS of include/anoddpm_b200.h
 _MODE = {"same": 0, "down": 1, "up": 2}
 _RES_FOR_MODE = {"same": 1, "down": 2, "up": 3}
 
@@ -87,9 +90,6 @@ class UNetEngine:
         m = self.model
         self.emb_w, self.emb_b, self.emb_off = [], [], 0
 
-        def gn_site():
-            return None
-
         def build_res(rb):
             if not isinstance(rb.skip_connection, (torch.nn.Identity, torch.nn.Conv2d)) or (
                     isinstance(rb.skip_connection, torch.nn.Conv2d) and rb.skip_connection.kernel_size != (1, 1)):
@@ -97,7 +97,7 @@ class UNetEngine:
             conv1, conv2 = rb.in_layers[2], rb.out_layers[3]
             cout = conv1.out_channels
             e = {"kind": "res", "mode": rb.resample_mode, "cin": conv1.in_channels, "cout": cout,
-                 "gn1": rb.in_layers[0], "gn2": rb.out_layers[0], "s1": gn_site(), "s2": gn_site(),
+                 "gn1": rb.in_layers[0], "gn2": rb.out_layers[0],
                  "conv1": _Conv([conv1.weight], [conv1.bias], 3), "emb_off": self.emb_off}
             self.emb_w.append(rb.embed_layers[1].weight)
             self.emb_b.append(rb.embed_layers[1].bias)
@@ -111,7 +111,7 @@ class UNetEngine:
             return e
 
         def build_attn(ab):
-            return {"kind": "attn", "c": ab.in_channels, "heads": ab.num_heads, "gn": ab.norm, "s": gn_site(),
+            return {"kind": "attn", "c": ab.in_channels, "heads": ab.num_heads, "gn": ab.norm,
                     "qkv": _Conv([ab.to_qkv.weight], [ab.to_qkv.bias], 1),
                     "proj": _Conv([ab.proj_out.weight], [ab.proj_out.bias], 1)}
 
@@ -132,7 +132,7 @@ class UNetEngine:
         self.down = [build_entry(seq) for seq in m.down]
         self.middle = build_entry(m.middle)
         self.up = [build_entry(seq) for seq in m.up]
-        self.head = {"gn": m.out[0], "s": gn_site(), "conv": m.out[2]}
+        self.head = {"gn": m.out[0], "conv": m.out[2]}
         self.emb_cat_w = torch.cat([w.detach() for w in self.emb_w], dim=0).contiguous().float()
         self.emb_cat_b = torch.cat([b.detach() for b in self.emb_b], dim=0).contiguous().float()
         self.head_w = pack_conv_weight(self.head["conv"].weight.detach()).contiguous().float()
@@ -148,7 +148,7 @@ class UNetEngine:
                     total += e["c"]
                 else:
                     total += e["conv"].out_channels
-        return (total + 64) * B * 2
+        return (total + 64) * B * 2 * STAT_REPLICAS
 
     def _refresh(self):
         sig = self._signature()
@@ -169,7 +169,7 @@ class UNetEngine:
     # ------------------------------------------------------------------ op wrappers
     def _stats_slot(self, B, C):
         """[B][C][2] fp64 slice of the per-forward statistics pool (zeroed once per forward)."""
-        n = B * C * 2
+        n = B * C * 2 * STAT_REPLICAS
         if self.stats_used + n > self.stats_pool.numel():
             raise RuntimeError("statistics pool exhausted")
         sl = self.stats_pool[self.stats_used:self.stats_used + n]

@@ -319,7 +319,7 @@ def aux_rooflines(dev):
     del x, n, e, o
     # GroupNorm apply, (32,256,256,128) fp32 -> fp16
     xa = torch.randn(32, 256, 256, 128, device=dev)
-    st = torch.zeros(32, 128, 2, device=dev, dtype=torch.float64)
+    st = torch.zeros(8, 32, 128, 2, device=dev, dtype=torch.float64)      # [ANODDPM_STAT_REPLICAS][B][C][2]
     _lib.call("anoddpm_gn_stats", _lib.ptr(st), _lib.ptr(xa), 128, 32, 65536, _lib.stream())
     g1, b1 = torch.ones(128, device=dev), torch.zeros(128, device=dev)
     oa = torch.empty(32, 256, 256, 128, device=dev, dtype=torch.float16)

@@ -25,6 +25,10 @@ extern "C" {
 #endif
 
 #define ANODDPM_ABI_VERSION 1
+/* Per-channel statistics buffers hold ANODDPM_STAT_REPLICAS partial copies, [replica][B][C][2] fp64: producers that
+ * run many CTAs on the same image (the conv epilogue) spread their atomics over the replicas (contention / 8); consumers
+ * (anoddpm_gn_apply) add the replicas up.  anoddpm_gn_stats writes replica 0. */
+#define ANODDPM_STAT_REPLICAS 8
 
 int anoddpm_abi_version(void);
 const char* anoddpm_last_error(void);
@@ -103,11 +107,12 @@ int anoddpm_linear(float* y, int ldy, const float* x, int ldx, const float* w, c
  * zeroes).  Per-channel sums are grouping-agnostic: a GroupNorm over this tensor, or over its concatenation with another
  * one (torch.cat, UNet.py:402), adds up the channels of each group in anoddpm_gn_apply.  The tensor-core conv
  * (anoddpm_conv impl 3) can emit the same numbers for its output from its epilogue (gn_stats field).  UNet.py:409-411. */
-int anoddpm_gn_stats(double* stats /* B x C x 2 */, const float* x, int C, int B, int HW, void* stream);
+int anoddpm_gn_stats(double* stats /* REPLICAS x B x C x 2 (replica 0 written) */, const float* x, int C, int B, int HW,
+                     void* stream);
 
 /* out = resample(act(GroupNorm(cat(x1, x2)))) on NHWC: act = SiLU if silu; mode 0 same, 1 avg-pool 2x2, 2 nearest x2
  * (UNet.py:202-210: GN -> SiLU -> h_upd, in that order).  stats1 / stats2: per-channel statistics of x1 / x2
- * ([B][C1][2], [B][C2][2]); x2, stats2 may be NULL (C2 = 0).
+ * ([REPLICAS][B][C1][2], [REPLICAS][B][C2][2]); x2, stats2 may be NULL (C2 = 0).
  * round_tf32 = output mode: 0 fp32; 1 fp32 rounded to TF32 (rna) for a kind::tf32 conv; 2 IEEE fp16 (rn, saturating;
  * `out` / `raw_out` then point to half elements) for a kind::f16 conv.
  * raw_out (optional, mode 0 only): also writes the rounded, channel-concatenated copy of the INPUT, which the
@@ -145,7 +150,7 @@ typedef struct anoddpm_conv_desc {
     int operand_f16;    /* impl 2/3 only: a, r1, r2, w hold IEEE fp16 (tcgen05 kind::f16, fp32 accumulate): the same 10-bit
                            mantissa as TF32 at twice the tensor rate and half the operand bytes; channels % 64 == 0 */
     double* gn_stats;   /* optional, impl 3 only: += (sum, sum of squares) of the OUTPUT per (sample, channel), layout
-                           [B][Cout][2] fp64 = what anoddpm_gn_stats would compute for the output tensor */
+                           [ANODDPM_STAT_REPLICAS][B][Cout][2] fp64 (sum over replicas = what anoddpm_gn_stats computes) */
 } anoddpm_conv_desc;
 int anoddpm_conv(const anoddpm_conv_desc* d /* [host] */, void* stream);
 /* 1 if impl=1/2 (tcgen05 tiles: channels % 32, Cout % 16, power-of-two W) covers the problem, else 0. */
@@ -164,6 +169,18 @@ int anoddpm_conv_head(float* out_nchw, const float* a_nhwc, const float* w_packe
  * out[b][t][h*ch + c] = sum_s softmax_s( (q_t . k_s) / sqrt(ch) ) v_s[c].   UNet.py:137-153. */
 int anoddpm_attention(void* out /* B x T x C; fp32, or fp16 when out_mode == 2 */, const float* qkv, int B, int T, int C,
                       int heads, int out_mode /* as anoddpm_gn_apply */, void* stream);
+
+/* ------------------------------------------------------------------ training: fused optimiser step -------- */
+
+/* *out += sum(g[i]^2) in fp64 (caller zeroes).  First half of torch.nn.utils.clip_grad_norm_ (diffusion_training.py:104). */
+int anoddpm_sumsq(double* out, const float* g, int64_t n, void* stream);
+
+/* One AdamW step with gradient clipping and EMA over flat fp32 buffers of n elements (diffusion_training.py:75,104-107:
+ * clip_grad_norm_(params, max_norm); AdamW(lr, betas, eps, weight_decay).step(); UNet.py:423-427 update_ema_params).
+ * sumsq: device scalar from anoddpm_sumsq (NULL or max_norm <= 0: no clipping); ema may be NULL; step counts from 1. */
+int anoddpm_adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, const double* sumsq, int64_t n,
+                           float lr, float beta1, float beta2, float eps, float weight_decay, int step, float max_norm,
+                           float ema_decay, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+REPL = 8        # ANODDPM_STAT_REPLICAS
 TOL = {"exact": 2e-5, "tc": 1e-3, "tc_tf32": 1e-3, "tc1": 1e-3, "tc2": 1e-3}
 TOL_SMALL = {"exact": 2e-5, "tc": 3e-3, "tc_tf32": 3e-3, "tc1": 3e-3, "tc2": 3e-3}
 
@@ -160,7 +161,7 @@ def test_gn_apply_and_attention_fp16_outputs():
     x = (torch.randn(B, C, H, W, generator=g) * 3).to(DEV)
     gamma, beta = torch.randn(C, generator=g).to(DEV), torch.randn(C, generator=g).to(DEV)
     xn = nhwc(x)
-    stats = torch.zeros(B, C, 2, dtype=torch.float64, device=DEV)
+    stats = torch.zeros(REPL, B, C, 2, dtype=torch.float64, device=DEV)
     _lib.call("anoddpm_gn_stats", _lib.ptr(stats), _lib.ptr(xn), C, B, H * W, _lib.stream())
     o32 = torch.empty(B, H, W, C, device=DEV)
     o16 = torch.empty(B, H, W, C, device=DEV, dtype=torch.float16)
@@ -188,7 +189,7 @@ def test_conv_fused_groupnorm_statistics(shape):
     w = (torch.randn(Co, Ci, 3, 3, generator=g) * (9 * Ci) ** -0.5).to(DEV)
     b = torch.randn(Co, generator=g).to(DEV)
     res = torch.randn(B, Co, H, W, generator=g).to(DEV)
-    fused = torch.zeros(B, Co, 2, dtype=torch.float64, device=DEV)
+    fused = torch.zeros(REPL, B, Co, 2, dtype=torch.float64, device=DEV)      # [replica][B][C][2]
     out = run_conv(a, w, b, 3, 3, res=res, res_mode=1, gn_stats=fused)
     torch.cuda.synchronize()
     ref = torch.zeros_like(fused)
@@ -196,8 +197,8 @@ def test_conv_fused_groupnorm_statistics(shape):
     _lib.call("anoddpm_gn_stats", _lib.ptr(ref), _lib.ptr(on), Co, B, H * W, _lib.stream())
     xg = out.double().reshape(B, Co, -1)
     exact = torch.stack([xg.sum(-1), (xg * xg).sum(-1)], dim=-1)
-    assert torch.allclose(fused, exact, rtol=1e-5, atol=1e-3)
-    assert torch.allclose(ref, exact, rtol=1e-5, atol=1e-3)
+    assert torch.allclose(fused.sum(0), exact, rtol=1e-5, atol=1e-3)
+    assert torch.allclose(ref.sum(0), exact, rtol=1e-5, atol=1e-3) and float(ref[1:].abs().sum()) == 0.0
 
 
 def test_groupnorm_silu_resample_vs_torch():
@@ -212,8 +213,8 @@ def test_groupnorm_silu_resample_vs_torch():
         xcat = torch.cat([x1, x2], 1) if C2 else x1
         for mode, silu in ((0, 1), (1, 1), (2, 1), (0, 0)):
             x1n, x2n = nhwc(x1), (nhwc(x2) if C2 else None)
-            st1 = torch.zeros(B, C1, 2, dtype=torch.float64, device=DEV)
-            st2 = torch.zeros(B, C2, 2, dtype=torch.float64, device=DEV) if C2 else None
+            st1 = torch.zeros(REPL, B, C1, 2, dtype=torch.float64, device=DEV)
+            st2 = torch.zeros(REPL, B, C2, 2, dtype=torch.float64, device=DEV) if C2 else None
             _lib.call("anoddpm_gn_stats", _lib.ptr(st1), _lib.ptr(x1n), C1, B, H * W, _lib.stream())
             if C2:
                 _lib.call("anoddpm_gn_stats", _lib.ptr(st2), _lib.ptr(x2n), C2, B, H * W, _lib.stream())
@@ -392,10 +393,8 @@ def test_cuda_graph_reverse_loop_matches_eager_loop():
         assert bool(D._graphs) == graphs
     assert rel(outs[1], outs[0]) < 1e-5
     # a second call re-uses the captured graph and keeps consuming the host RNG (new seeds -> different noise)
-    before = np.random.get_state()[2]
     y2 = D.forward_backward(m, x0, None, 9, "noise_fn")
     assert len(D._graphs) == 1 and bool(torch.isfinite(y2).all())
-    assert np.random.get_state()[2] != before or True
     g = list(D._graphs.values())[0]
     assert int(g["step"].item()) == 9 and int(g["t"][0].item()) == -1
 
@@ -421,3 +420,39 @@ def test_detection_drivers_run_on_native_loop(tmp_path, monkeypatch):
     assert D.detection_B(m, x0, args, ("vol", "slice"), mask, denoise_fn="gauss", total_avg=1) == [None]
     assert D.detection_A(m, x0, args, ("vol", "slice"), mask, total_avg=1) is None
     assert (tmp_path / "diffusion-videos" / "ARGS=0" / "Anomalous" / "vol" / "slice" / "A").is_dir()
+
+
+def test_fused_adamw_ema_step_matches_torch_sequence():
+    """clip_grad_norm_(…, 1) -> AdamW.step() -> update_ema_params, as two native kernels over flat buffers."""
+    import copy
+    from anoddpm_b200.optim import FusedAdamWEMA
+    from anoddpm_b200.UNet import UNetModel, update_ema_params
+    torch.manual_seed(0)
+    m1 = UNetModel(32, 32).to(DEV)
+    for p in m1.parameters():                   # zero-initialised tensors would make the comparison vacuous
+        if float(p.abs().max()) == 0:
+            p.data.normal_(0, 0.02)
+    e1 = copy.deepcopy(m1)
+    m2, e2 = copy.deepcopy(m1), copy.deepcopy(m1)
+    ref_opt = torch.optim.AdamW(m1.parameters(), lr=1e-3, weight_decay=0.01, betas=(0.9, 0.999))
+    fused = FusedAdamWEMA(m2, e2, lr=1e-3, weight_decay=0.01, betas=(0.9, 0.999), max_norm=1.0, ema_decay=0.99)
+    g = torch.Generator().manual_seed(1)
+    for it in range(3):
+        grads = [torch.randn(p.shape, generator=g).to(DEV) * (3.0 if it == 0 else 0.001) for p in m1.parameters()]
+        ref_opt.zero_grad()
+        fused.zero_grad()
+        for p1, p2, gr in zip(m1.parameters(), m2.parameters(), grads):
+            p1.grad = gr.clone()
+            p2.grad.copy_(gr)
+        torch.nn.utils.clip_grad_norm_(m1.parameters(), 1)
+        ref_opt.step()
+        update_ema_params(e1, m1, 0.99)
+        fused.step()
+    for (k, a), b in zip(m1.named_parameters(), m2.parameters()):
+        assert torch.allclose(a, b, rtol=2e-5, atol=2e-7), k
+    for a, b in zip(e1.parameters(), e2.parameters()):
+        assert torch.allclose(a, b, rtol=2e-5, atol=2e-7)
+    # the fused model is still a working UNetModel (parameters are views into the flat buffer)
+    with torch.no_grad():
+        y = m2(torch.randn(1, 1, 32, 32, device=DEV), torch.tensor([5], device=DEV))
+    assert bool(torch.isfinite(y).all())
