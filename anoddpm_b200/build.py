@@ -16,7 +16,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 # exact-arithmetic translation units: no fma contraction so fp64/fp32 results match the CPU reference bit for bit
 EXACT = {"simplex.cu", "diffusion.cu", "optim.cu"}
-SOURCES = ["abi.cu", "simplex.cu", "diffusion.cu", "unet_ops.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "optim.cu"]
+SOURCES = ["abi.cu", "simplex.cu", "diffusion.cu", "unet_ops.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "attention_tc.cu",
+           "optim.cu"]
 
 
 def _stale(target, deps):

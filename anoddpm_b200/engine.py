@@ -299,8 +299,16 @@ class UNetEngine:
         del xn
         om = self._out_mode(plan_proj)
         a = torch.empty((B, H, W, C), device=x.t.device, dtype=torch.float16 if om == 2 else torch.float32)
-        call("anoddpm_attention", ptr(a), ptr(qkv), B, T, C, e["heads"], om, stream())
-        self.launches += 1
+        L = _lib.lib()
+        if self.use_tc and L.anoddpm_attention_tc_supported(T, C, e["heads"]):
+            # tcgen05 attention: fp16 pack pass + one CTA per (128 queries, sample x head)
+            ws = torch.empty(L.anoddpm_attention_tc_workspace_bytes(B, T, C), device=x.t.device, dtype=torch.uint8)
+            call("anoddpm_attention_tc", ptr(a), ptr(qkv), ptr(ws), B, T, C, e["heads"], om, stream())
+            self.launches += 2
+            self.tc_attn += 1
+        else:
+            call("anoddpm_attention", ptr(a), ptr(qkv), B, T, C, e["heads"], om, stream())
+            self.launches += 1
         return self._conv(e["proj"], a, B, H, W, C, plan_proj, res=x.t, res_mode=1)
 
     def _entry(self, entry, srcs, B, H, W):
@@ -338,6 +346,7 @@ class UNetEngine:
         self.fused_stats = 0
         self.stats_passes = 0
         self.tc_convs = 0
+        self.tc_attn = 0
         in_dtype = x.dtype
         x = x.contiguous().float()
         B, Cin, H, W = x.shape

@@ -170,6 +170,15 @@ int anoddpm_conv_head(float* out_nchw, const float* a_nhwc, const float* w_packe
 int anoddpm_attention(void* out /* B x T x C; fp32, or fp16 when out_mode == 2 */, const float* qkv, int B, int T, int C,
                       int heads, int out_mode /* as anoddpm_gn_apply */, void* stream);
 
+/* The same attention on tcgen05 tensor cores (fp16 operands rounded to nearest, fp32 accumulation and softmax):
+ * a pack pass (q, k scaled by ch^-1/4 as UNet.py:143, v transposed) and one CTA per (128 queries, sample x head).
+ * Needs T and C/heads in {64,128,192,256} (anoddpm_attention_tc_supported) and a caller-owned, 128-byte aligned
+ * workspace of anoddpm_attention_tc_workspace_bytes(B, T, C) bytes. */
+int anoddpm_attention_tc_supported(int T, int C, int heads);
+long long anoddpm_attention_tc_workspace_bytes(int B, int T, int C);
+int anoddpm_attention_tc(void* out, const float* qkv, void* workspace, int B, int T, int C, int heads, int out_mode,
+                         void* stream);
+
 /* ------------------------------------------------------------------ training: fused optimiser step -------- */
 
 /* *out += sum(g[i]^2) in fp64 (caller zeroes).  First half of torch.nn.utils.clip_grad_norm_ (diffusion_training.py:104). */

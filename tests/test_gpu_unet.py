@@ -247,6 +247,37 @@ def test_attention_vs_reference_formula():
         assert rel(out.permute(0, 2, 1), ref) < 1e-5, (B, C, T, heads)
 
 
+def test_attention_tensor_core_vs_reference_formula():
+    """tcgen05 attention (fp16 operands, fp32 accumulate / softmax) against the fp64 formula of UNet.py:137-153."""
+    from anoddpm_b200 import _lib
+    import math
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(10)
+    assert L.anoddpm_attention_tc_supported(256, 512, 2) == 1
+    assert L.anoddpm_attention_tc_supported(1024, 256, 2) == 0
+    assert L.anoddpm_attention_tc_supported(16, 256, 4) == 0
+    for (B, C, T, heads, scale) in [(2, 512, 256, 2, 1.0), (3, 512, 64, 2, 1.0), (2, 128, 128, 2, 3.0), (1, 192, 192, 1, 1.0),
+                                    (32, 512, 256, 2, 2.0)]:
+        qkv = (torch.randn(B, 3 * C, T, generator=g) * scale).to(DEV)
+        ch = C // heads
+        q, k, v = qkv.double().reshape(B * heads, 3 * ch, T).split(ch, dim=1)
+        s = 1 / math.sqrt(math.sqrt(ch))
+        wgt = torch.softmax(torch.einsum("bct,bcs->bts", q * s, k * s), dim=-1)
+        ref = torch.einsum("bts,bcs->bct", wgt, v).reshape(B, C, T).float()
+        qn = qkv.permute(0, 2, 1).contiguous()
+        ws = torch.empty(L.anoddpm_attention_tc_workspace_bytes(B, T, C), device=DEV, dtype=torch.uint8)
+        for om, dt in ((0, torch.float32), (2, torch.float16), (1, torch.float32)):
+            out = torch.full((B, T, C), float("nan"), device=DEV, dtype=dt)
+            _lib.call("anoddpm_attention_tc", _lib.ptr(out), _lib.ptr(qn), _lib.ptr(ws), B, T, C, heads, om, _lib.stream())
+            err = rel(out.float().permute(0, 2, 1), ref)
+            assert err < 2e-3, (B, C, T, heads, om, err)
+        exact = torch.empty(B, T, C, device=DEV)
+        _lib.call("anoddpm_attention", _lib.ptr(exact), _lib.ptr(qn), B, T, C, heads, 0, _lib.stream())
+        out = torch.empty(B, T, C, device=DEV)
+        _lib.call("anoddpm_attention_tc", _lib.ptr(out), _lib.ptr(qn), _lib.ptr(ws), B, T, C, heads, 0, _lib.stream())
+        assert rel(out, exact) < 2e-3
+
+
 def test_timestep_embedding_and_linear():
     from anoddpm_b200 import _lib
     from anoddpm_b200.UNet import PositionalEmbedding
