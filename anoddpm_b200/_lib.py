@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libanoddpm_b200.so")
+LIB_PATH = os.environ.get("ANODDPM_B200_LIB") or os.path.join(_HERE, "libanoddpm_b200.so")   # override: A/B runs of two builds
 
 c_int, c_i64, c_f32, c_f64, c_vp = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
 

@@ -10,10 +10,17 @@
 //   * CTA pairs (tcgen05.mma.cta_group::2, UMMA M = 256) split the weight tile in halves, persistent clusters,
 //     3-stage smem ring (60 KB/stage), 2 TMEM accumulator stages x 2 subtiles x BN columns (512 columns).
 // 1x1 "skip" sources (raw ResBlock input, centre tap only) are extra stages with a (32, 8, 16) box.
-// Epilogue: as conv_tc2 (bias + timestep embedding + residual), plus optional per-channel statistics of the OUTPUT
-// (sum, sum of squares per (sample, channel), fp32 per warp -> fp64 atomics) so the GroupNorm(s) that consume the
-// tensor -- alone or concatenated with another tensor -- need no statistics pass.
-// Contract: ksize == 3, H % 16 == 0, W % 16 == 0, channels % 32 == 0, Cout % 16 == 0 (anoddpm_conv_tc3_supported).
+// Epilogue (8 warps: TMEM lane quarter x subtile; two per scheduler -- the work is a chain of short-latency steps), in
+// steps of (32 pixels x 16 channels) per warp through two 2 KB shared-memory buffers in the TMA SWIZZLE_64B layout:
+// the residual box of step s+2 is TMA-loaded into the buffer once the store of step s has read it, the
+// thread-per-pixel pass adds bias + timestep embedding + residual to the TMEM row and writes it back in place, a TMA
+// store moves the buffer to the NHWC output, and a column pass over the buffer accumulates optional per-channel
+// statistics of the OUTPUT (sum, sum of squares per (sample, channel)): fp32 in registers while the cluster stays on
+// one sample (contiguous tile runs per cluster), flushed with fp64 atomics, so the GroupNorm(s) that consume the tensor
+// -- alone or concatenated with another tensor -- need no statistics pass.
+// Residual modes: 1 = same resolution, 3 = nearest-upsampled (half-resolution source); an avg-pooled residual is
+// pooled by the preceding anoddpm_gn_apply pass (res_mode 2 is not taken by this kernel).
+// Contract: ksize == 3, H % 16 == 0, W % 16 == 0, channels % 32 == 0, Cout % 32 == 0 (anoddpm_conv_tc3_supported).
 #include "common.cuh"
 #include "anoddpm_b200.h"
 #include <cuda.h>
@@ -23,13 +30,16 @@ namespace {
 constexpr int kBM = 128;
 constexpr int kRowBytes = 128;   // one K-block row: 32 fp32 (TF32 MMA) or 64 fp16 elements
 constexpr int kKSteps = 4;       // MMAs per K-block: 32 B of K each (8 tf32 / 16 f16 elements)
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;       // warps 0-3: TMA producer, MMA issuer, TMEM allocator, idle; warps 4-11: epilogue
 constexpr int kSubRows = 18;                        // 16 output rows + 1 halo row above and below
 constexpr int kSubBytes = kSubRows * 8 * kRowBytes;   // one (32 ch, 8 px, 18 rows) box = 18432 B
 constexpr int kABytes = 2 * kSubBytes;              // two subtiles per CTA
 constexpr int kAccStages = 2;
 constexpr int kMaxStages = 4;
-constexpr int kStgPitch = 36;                       // floats per staged epilogue row (32 + 4: conflict-free 128-bit access)
+constexpr int kEpiWarps = 8;
+constexpr int kStgBuf = 32 * 64;                    // one epilogue buffer: 32 pixel rows x 16 fp32 channels, SWIZZLE_64B
+constexpr int kStgBytes = kEpiWarps * 2 * kStgBuf;  // 8 epilogue warps x 2 buffers
+constexpr int kBeBytes = kEpiWarps * 128 * 4;       // per-warp (bias + embedding) row of the current tile
 
 struct Tc3Args {
     float* out;
@@ -48,6 +58,7 @@ struct Tc3Args {
     int regions_x, regions_per_img, n_regions;   // 16x16 regions
     double* gn_stats;          // optional [REPLICAS][B][Cout][2]: per-channel (sum, sum of squares) of the output
     long long stat_replica_stride;   // B*Cout*2
+    int tile_order;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -117,6 +128,29 @@ __device__ __forceinline__ void tma2_load_2d(void* smem, const CUtensorMap* map,
         ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
         : "memory");
 }
+// explicit shared-window accesses: pointers derived from the re-aligned dynamic smem base are generic to the compiler
+// (LD.E / ST.E through the L1TEX path); the epilogue buffers are hot enough for that to matter
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// plain (per-CTA) TMA load / store used by the epilogue
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 template <bool F16>
 __device__ __forceinline__ void umma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                       uint32_t accumulate) {
@@ -156,6 +190,7 @@ template <bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_r1,
                 const __grid_constant__ CUtensorMap map_r2, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_out,
                 const Tc3Args P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -163,18 +198,29 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int S = P.stages;
     uint8_t* sA = smem;                            // [S][2 subtiles][kSubBytes]
     uint8_t* sB = smem + S * kABytes;              // [S][3 taps][b_bytes]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + S * 3 * b_bytes);
+    uint8_t* stg_all = sB + S * 3 * b_bytes;       // [4 warps][2][kStgBuf], 1024-byte aligned (ring sizes are multiples)
+    float* be_all = reinterpret_cast<float*>(stg_all + kStgBytes);   // [4 warps][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + kStgBytes + kBeBytes);
     uint64_t* full = bars;                         // [S]   leader only
     uint64_t* empty = bars + kMaxStages;           // [S]   both CTAs (multicast commit)
     uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]   both CTAs (multicast commit)
-    uint64_t* tmem_empty = tmem_full + kAccStages; // [2]   leader only, 2 x 128 arrivals
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
-    float* stg_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // 4 warps x 2 subtiles x 32 rows x kStgPitch
+    uint64_t* tmem_empty = tmem_full + kAccStages; // [2]   leader only, 2 x 256 arrivals
+    uint64_t* res_bar = tmem_empty + kAccStages;   // [8 warps][2] residual box landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    // tile sequence of this cluster: strided (tile_order 0: the clusters sweep the tensor together) or one contiguous run
+    int tile_first, tile_step, tile_end;
+    if (P.tile_order == 0) { tile_first = cluster_id; tile_step = n_clusters; tile_end = P.n_tiles; }
+    else {
+        const int q = P.n_tiles / n_clusters, rem = P.n_tiles - q * n_clusters;
+        tile_first = cluster_id * q + min(cluster_id, rem);
+        tile_step = 1;
+        tile_end = tile_first + q + (cluster_id < rem ? 1 : 0);
+    }
     const int nst_a = P.chunks_a * 3;                       // (chunk, dx) stages of the 3x3 source
     const int nst = nst_a + P.chunks_r1 + P.chunks_r2;      // + centre-tap stages of the 1x1 skip sources
 
@@ -182,10 +228,13 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+        if (P.res) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_res) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < S; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * 128); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * 32 * kEpiWarps); }
+        for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -203,7 +252,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ---------------- TMA producer (both CTAs) ----------------
         if (elect_one()) {
             int kbc = 0;
-            for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters) {
+            for (int tile = tile_first; tile < tile_end; tile += tile_step) {
                 const int pair = tile / P.n_tiles_n, nt = tile - pair * P.n_tiles_n;
                 const int R = pair * 2 + (int)rank;                 // this CTA's 16x16 region (may be past the end)
                 const int b0 = R / P.regions_per_img, rr = R - b0 * P.regions_per_img;
@@ -246,7 +295,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.BN >> 3) << 17) |
                                    ((uint32_t)(256 >> 4) << 24);
             int kbc = 0, it = 0;
-            for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters, ++it) {
+            for (int tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
                 const int acc = it & 1;
                 mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -281,129 +330,173 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
     } else if (warp >= 4) {
         // ---------------- epilogue (both CTAs) ----------------
-        // TMEM -> registers (thread = pixel row, 32 channels) -> per-warp smem transpose -> each store instruction
-        // writes 4 pixels x 128 B (4 full lines) instead of 32 scattered 16-byte pieces.
-        const int quarter = warp & 3;
-        float* stg = stg_all + quarter * (64 * kStgPitch);   // [2 subtiles][32 rows][kStgPitch]
-        const int rr0 = lane >> 3;          // row within a group of 4 staged rows
-        const int cc = (lane & 7) * 4;      // channel quad within the 32-channel chunk
-        int it = 0;
-        for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters, ++it) {
-            const int acc = it & 1;
+        const int ew = warp - 4;            // 0..7
+        const int quarter = warp & 3;       // TMEM lanes 32*quarter.. : image rows 4*quarter..+3 of the subtile
+        const int sub = ew >> 2;            // subtile (left / right 8 pixel columns of the 16x16 region)
+        uint8_t* stg = stg_all + ew * (2 * kStgBuf);
+        float* be = be_all + ew * 128;
+        const bool has_res = P.res != nullptr;
+        auto tile_region = [&](int tile, int& b, int& ybase, int& xbase, int& n0) -> bool {
             const int pair = tile / P.n_tiles_n, nt = tile - pair * P.n_tiles_n;
             const int R = pair * 2 + (int)rank;
-            const bool valid = R < P.n_regions;
-            const int b = R / P.regions_per_img, rr = R - b * P.regions_per_img;
-            const int ybase = (rr / P.regions_x) * 16, xbase = (rr % P.regions_x) * 16;
-            const int n0 = nt * P.BN;
-            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int cb = 0; cb < P.BN; cb += 32) {
-                const int n = n0 + cb + cc;
-                const bool nvalid = valid && n < P.Cout;
-                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), emb4 = bias4;
-                if (nvalid && P.bias) bias4 = *reinterpret_cast<const float4*>(P.bias + n);
-                if (nvalid && P.emb) emb4 = *reinterpret_cast<const float4*>(P.emb + (size_t)b * P.emb_stride + n);
-                float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};   // per-channel sum / sum of squares
-                // 1. both subtiles of this 32-channel chunk: TMEM -> registers -> per-warp staging rows
+            b = R / P.regions_per_img;
+            const int rr = R - b * P.regions_per_img;
+            ybase = (rr / P.regions_x) * 16;
+            xbase = (rr % P.regions_x) * 16;
+            n0 = nt * P.BN;
+            return tile < tile_end && R < P.n_regions;
+        };
+        const int cc = (lane & 3) * 4;      // channel quad of the column pass
+        // residual box of step (tile, cb) -> buffer buf (one lane issues; the warp's 4 image rows x 8 px x 16 ch).
+        // TMA, not register loads: measured, global loads issued by the epilogue warps (pixel-per-lane or coalesced, one
+        // or two steps ahead) are 15-25% slower -- they queue behind the operand bursts of the main loop
+        uint64_t* rbar = res_bar + ew * 2;
+        const uint32_t res_bytes = P.res_mode == 3 ? 8u * 64u : (uint32_t)kStgBuf;
+        auto issue_res = [&](int tile, int cb, int buf) {
+            int b, ybase, xbase, n0;
+            if (!tile_region(tile, b, ybase, xbase, n0)) return;
+            mbar_expect_tx(&rbar[buf], res_bytes);
+            const int y = ybase + 4 * quarter, x = xbase + 8 * sub;
+            if (P.res_mode == 3) tma_load_4d(stg + buf * kStgBuf, &map_res, &rbar[buf], n0 + cb, x >> 1, y >> 1, b);
+            else tma_load_4d(stg + buf * kStgBuf, &map_res, &rbar[buf], n0 + cb, x, y, b);
+        };
+        if (has_res && lane == 0) {
+            issue_res(tile_first, 0, 0);
+            issue_res(tile_first, 16, 1);
+        }
+        // per-channel statistics: lane (g = lane >> 2, q = lane & 3) keeps the running sums of channels 16 g + 4 q .. + 3
+        // of the current (sample, channel tile) in registers and flushes them with fp64 atomics when either changes
+        float keep1[4] = {0.f, 0.f, 0.f, 0.f}, keep2[4] = {0.f, 0.f, 0.f, 0.f};
+        int cur_b = -1, cur_n0 = 0, kept = 0;
+        auto flush_stats = [&]() {
+            if (cur_b >= 0 && 16 * (lane >> 2) < P.BN) {
+                // replica = cluster id mod 8 spreads the CTAs that work on the same image over 8x more addresses
+                double* st = P.gn_stats + (size_t)(cluster_id % ANODDPM_STAT_REPLICAS) * P.stat_replica_stride +
+                             ((size_t)cur_b * P.Cout + cur_n0 + 16 * (lane >> 2) + cc) * 2;
 #pragma unroll
-                for (int sub = 0; sub < 2; ++sub) {
-                    uint32_t r[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                                           (uint32_t)((acc * 2 + sub) * P.BN + cb);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-                          "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
-                          "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
-                          "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                        : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (sub == 1 && cb + 32 >= P.BN) {
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        mbar_arrive_remote(&tmem_empty[acc], 0);   // accumulators fully read
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<uint4*>(stg + (sub * 32 + lane) * kStgPitch + j) =
-                            make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-                }
-                __syncwarp();
-                if (nvalid) {
-                    // 2. transposed pass: item k = (subtile k/8, staged row 4*(k%8) + rr0); lane owns channels n..n+3.
-                    //    All residual loads of a batch are issued before its first store (memory-level parallelism:
-                    //    P.out may alias P.res as far as the compiler knows, so it cannot hoist them itself).
-                    constexpr int kBatch = 8;
-#pragma unroll
-                    for (int k0 = 0; k0 < 16; k0 += kBatch) {
-                        size_t qq[kBatch];
-                        float4 rv[kBatch];
-#pragma unroll
-                        for (int k = 0; k < kBatch; ++k) {
-                            const int sub = (k0 + k) >> 3;
-                            const int m = quarter * 32 + 4 * ((k0 + k) & 7) + rr0;
-                            const int y = ybase + (m >> 3), x = xbase + sub * 8 + (m & 7);
-                            qq[k] = ((size_t)b * P.H + y) * P.W + x;
-                            rv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (P.res_mode == 1) {
-                                rv[k] = *reinterpret_cast<const float4*>(P.res + qq[k] * P.Cout + n);
-                            } else if (P.res_mode == 2) {
-                                const int W2 = P.W * 2;
-                                const float* rb = P.res + (((size_t)b * P.H * 2 + 2 * y) * W2 + 2 * x) * P.Cout + n;
-                                const float4 r0 = *reinterpret_cast<const float4*>(rb);
-                                const float4 r1 = *reinterpret_cast<const float4*>(rb + P.Cout);
-                                const float4 r2 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout);
-                                const float4 r3 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout + P.Cout);
-                                rv[k].x = (r0.x + r1.x + r2.x + r3.x) * 0.25f;
-                                rv[k].y = (r0.y + r1.y + r2.y + r3.y) * 0.25f;
-                                rv[k].z = (r0.z + r1.z + r2.z + r3.z) * 0.25f;
-                                rv[k].w = (r0.w + r1.w + r2.w + r3.w) * 0.25f;
-                            } else if (P.res_mode == 3) {
-                                const int Hh = P.H / 2, Wh = P.W / 2;
-                                rv[k] = *reinterpret_cast<const float4*>(
-                                    P.res + (((size_t)b * Hh + (y >> 1)) * Wh + (x >> 1)) * P.Cout + n);
-                            }
-                        }
-#pragma unroll
-                        for (int k = 0; k < kBatch; ++k) {
-                            const int sub = (k0 + k) >> 3;
-                            const int rw = 4 * ((k0 + k) & 7) + rr0;
-                            const float4 t4 = *reinterpret_cast<const float4*>(stg + (sub * 32 + rw) * kStgPitch + cc);
-                            float v[4] = {t4.x + bias4.x, t4.y + bias4.y, t4.z + bias4.z, t4.w + bias4.w};
-                            v[0] += emb4.x; v[1] += emb4.y; v[2] += emb4.z; v[3] += emb4.w;
-                            v[0] += rv[k].x; v[1] += rv[k].y; v[2] += rv[k].z; v[3] += rv[k].w;
-                            *reinterpret_cast<float4*>(P.out + qq[k] * P.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) { s1[e] += v[e]; s2[e] += v[e] * v[e]; }
-                        }
-                    }
-                }
-                __syncwarp();
-                if (P.gn_stats) {   // warp-uniform; all pixels of the CTA's region belong to sample b
-                    // lanes with equal (lane & 7) hold the same 4 channels for different pixel rows
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 8);
-                        s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 8);
-                        s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
-                        s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
-                    }
-                    if (nvalid && lane < 8) {
-                        // replica = cluster id mod 8: the ~148 CTAs working on the same image hit 8x more addresses
-                        double* st = P.gn_stats + (size_t)(cluster_id % ANODDPM_STAT_REPLICAS) * P.stat_replica_stride +
-                                     ((size_t)b * P.Cout + n) * 2;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            atomicAdd(st + 2 * e, (double)s1[e]);
-                            atomicAdd(st + 2 * e + 1, (double)s2[e]);
-                        }
-                    }
+                for (int e = 0; e < 4; ++e) {
+                    atomicAdd(st + 2 * e, (double)keep1[e]);
+                    atomicAdd(st + 2 * e + 1, (double)keep2[e]);
+                    keep1[e] = 0.f;
+                    keep2[e] = 0.f;
                 }
             }
+        };
+        int it = 0, step = 0;
+        for (int tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
+            const int acc = it & 1;
+            int b, ybase, xbase, n0;
+            const bool valid = tile_region(tile, b, ybase, xbase, n0);
+            if (P.gn_stats && valid) {
+                if (b != cur_b || n0 != cur_n0 || kept == 8) {   // bounded fp32 chains: at most 8 tiles per flush
+                    flush_stats();
+                    cur_b = b;
+                    cur_n0 = n0;
+                    kept = 0;
+                }
+                ++kept;
+            }
+            // (bias + timestep embedding) row of this tile; lanes own 4 channels each
+            {
+                const int n = n0 + lane * 4;
+                float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid && lane * 4 < P.BN && n < P.Cout) {
+                    if (P.bias) v4 = *reinterpret_cast<const float4*>(P.bias + n);
+                    if (P.emb) {
+                        const float4 e4 = *reinterpret_cast<const float4*>(P.emb + (size_t)b * P.emb_stride + n);
+                        v4.x += e4.x; v4.y += e4.y; v4.z += e4.z; v4.w += e4.w;
+                    }
+                }
+                __syncwarp();
+                sts128(smem_u32(be + lane * 4), v4);
+                __syncwarp();
+            }
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int cb = 0; cb < P.BN; cb += 16) {
+                uint32_t r[16];
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * 2 + sub) * P.BN + cb);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (cb + 16 >= P.BN) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive_remote(&tmem_empty[acc], 0);   // this warp's part of the accumulators is read
+                }
+                if (!valid) continue;
+                const int buf = step & 1;
+                const uint32_t sba = smem_u32(stg + buf * kStgBuf), bea = smem_u32(be + cb);
+                // 1. pixel pass: thread = pixel row `lane` of the buffer (64 B); 16-byte chunk j sits at j ^ ((row >> 1) & 3)
+                float4 rs[4];
+                if (has_res) {
+                    mbar_wait(&rbar[buf], (step >> 1) & 1);
+                    const int srow = P.res_mode == 3 ? ((lane >> 4) * 4 + ((lane & 7) >> 1)) : lane;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) rs[j] = lds128(sba + srow * 64 + ((j ^ ((srow >> 1) & 3)) << 4));
+                    __syncwarp();   // upsampled mode: rows are shared between lanes, all reads precede the writes
+                } else {
+                    // the TMA store that last read this buffer (two steps ago) must be done with it
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 be4 = lds128(bea + 16 * j);
+                    float4 v4 = make_float4(__uint_as_float(r[4 * j]) + be4.x, __uint_as_float(r[4 * j + 1]) + be4.y,
+                                            __uint_as_float(r[4 * j + 2]) + be4.z, __uint_as_float(r[4 * j + 3]) + be4.w);
+                    if (has_res) { v4.x += rs[j].x; v4.y += rs[j].y; v4.z += rs[j].z; v4.w += rs[j].w; }
+                    sts128(sba + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), v4);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                // 2. the buffer is the output box (16 ch, 8 px, 4 rows): one TMA store
+                if (lane == 0) {
+                    tma_store_4d(&map_out, stg + buf * kStgBuf, n0 + cb, xbase + 8 * sub, ybase + 4 * quarter, b);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                // 3. column pass: lane owns channels cc..cc+3 of rows (lane >> 2) + 8k -> per-channel statistics
+                if (P.gn_stats) {   // warp-uniform; all pixels of the CTA's region belong to sample b
+                    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int row = 8 * k + (lane >> 2);
+                        const float4 t4 = lds128(sba + row * 64 + (((lane & 3) ^ ((row >> 1) & 3)) << 4));
+                        s1[0] += t4.x; s1[1] += t4.y; s1[2] += t4.z; s1[3] += t4.w;
+                        s2[0] += t4.x * t4.x; s2[1] += t4.y * t4.y; s2[2] += t4.z * t4.z; s2[3] += t4.w * t4.w;
+                    }
+                    // lanes with equal (lane & 3) hold the same 4 channels for different pixel rows
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+#pragma unroll
+                        for (int o = 4; o < 32; o <<= 1) {
+                            s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
+                            s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
+                        }
+                    }
+                    if ((lane >> 2) == (cb >> 4)) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { keep1[e] += s1[e]; keep2[e] += s2[e]; }
+                    }
+                }
+                if (has_res) {
+                    // buffer free once the store has read it: fetch the residual of step + 2
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        if (cb + 32 < P.BN) issue_res(tile, cb + 32, buf);
+                        else issue_res(tile + tile_step, cb + 32 - P.BN, buf);
+                    }
+                }
+                ++step;
+            }
         }
+        if (P.gn_stats) flush_stats();
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // buffers outlive the stores
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();
@@ -448,6 +541,24 @@ int make_act_map3(CUtensorMap* m, const void* p, int f16, int C, int W, int H, i
     return ANODDPM_OK;
 }
 
+// fp32 NHWC epilogue map: dims (C, W, H, B), box (16 ch, px, rows, 1), 64-byte swizzle
+int make_epi_map3(CUtensorMap* m, const void* p, int C, int W, int H, int B, int px, int rows) {
+    EncodeTiledFn enc = get_encode3();
+    if (!enc) { anoddpm_set_error("cuTensorMapEncodeTiled entry point not available"); return ANODDPM_ERR_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {16u, (cuuint32_t)px, (cuuint32_t)rows, 1u};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(p), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        anoddpm_set_error("cuTensorMapEncodeTiled(epilogue C=%d W=%d H=%d B=%d) failed: %d", C, W, H, B, (int)r);
+        return ANODDPM_ERR_CUDA;
+    }
+    return ANODDPM_OK;
+}
+
 int make_w_map3(CUtensorMap* m, const void* p, int f16, int Ktot, int Cout, int rows) {
     EncodeTiledFn enc = get_encode3();
     if (!enc) { anoddpm_set_error("cuTensorMapEncodeTiled entry point not available"); return ANODDPM_ERR_CUDA; }
@@ -475,14 +586,18 @@ extern "C" int anoddpm_conv_tc3_supported(const anoddpm_conv_desc* d) {
     if (d->H % 16 || d->W % 16) return 0;
     const int ke = d->operand_f16 ? 64 : 32;
     if (d->Ca % ke || d->Cr1 % ke || d->Cr2 % ke) return 0;
-    if (d->Cout % 16) return 0;
+    if (d->Cout % 32) return 0;
     if (d->Cout > 128 && d->Cout % 128) return 0;
+    if (d->res && d->res_mode == 2) return 0;   // avg-pooled residual: pool it in anoddpm_gn_apply (or use impl 2)
     return 1;
 }
 
 int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
-    ADP_REQUIRE(anoddpm_conv_tc3_supported(d), "anoddpm_conv(impl=3): needs ksize 3, H,W %% 16 == 0, channels %% 32 == 0 "
-                "(Ca=%d Cr1=%d Cr2=%d Cout=%d H=%d W=%d)", d->Ca, d->Cr1, d->Cr2, d->Cout, d->H, d->W);
+    ADP_REQUIRE(anoddpm_conv_tc3_supported(d), "anoddpm_conv(impl=3): needs ksize 3, H,W %% 16 == 0, channels %% 32 == 0, res_mode "
+                "!= 2 (Ca=%d Cr1=%d Cr2=%d Cout=%d H=%d W=%d res_mode=%d)", d->Ca, d->Cr1, d->Cr2, d->Cout, d->H, d->W,
+                d->res ? d->res_mode : 0);
+    ADP_REQUIRE(!d->res || d->res_mode == 1 || d->res_mode == 3, "anoddpm_conv(impl=3): res_mode must be 1 or 3");
+    ADP_REQUIRE(!d->res || d->res_mode != 3 || (d->H % 2 == 0 && d->W % 2 == 0), "anoddpm_conv(impl=3): odd size");
     Tc3Args P;
     P.out = d->out; P.bias = d->bias; P.emb = d->emb; P.res = d->res;
     P.M = d->B * d->H * d->W; P.H = d->H; P.W = d->W; P.Cout = d->Cout;
@@ -508,6 +623,7 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     P.n_tiles = adp_ceil_div(P.n_regions, 2) * P.n_tiles_n;
     P.gn_stats = d->gn_stats;
     P.stat_replica_stride = (long long)d->B * d->Cout * 2;
+    P.tile_order = 1;   // contiguous run of tiles per cluster (statistics stay in registers across a sample's tiles)
 
     CUtensorMap ma, m1, m2, mw;
     int rc;
@@ -516,8 +632,17 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     if (d->r1 && (rc = make_act_map3(&m1, d->r1, f16, d->Cr1, d->W, d->H, d->B, 16))) return rc;
     if (d->r2 && (rc = make_act_map3(&m2, d->r2, f16, d->Cr2, d->W, d->H, d->B, 16))) return rc;
     if ((rc = make_w_map3(&mw, d->w, f16, Ktot, d->Cout, P.BN / 2))) return rc;
+    // epilogue store box: (16 ch fp32, 8 px, 4 rows) of the output
+    CUtensorMap mres, mout;
+    if ((rc = make_epi_map3(&mout, d->out, d->Cout, d->W, d->H, d->B, 8, 4))) return rc;
+    mres = mout;
+    if (d->res) {   // residual boxes: (16, 8, 4) at the same resolution, (16, 4, 2) of a half-resolution source
+        if (d->res_mode == 3) rc = make_epi_map3(&mres, d->res, d->Cout, d->W / 2, d->H / 2, d->B, 4, 2);
+        else rc = make_epi_map3(&mres, d->res, d->Cout, d->W, d->H, d->B, 8, 4);
+        if (rc) return rc;
+    }
 
-    const size_t smem = (size_t)stages * (kABytes + 3 * b_bytes) + 256 + 4 * 64 * kStgPitch * 4 + 1024;
+    const size_t smem = (size_t)stages * (kABytes + 3 * b_bytes) + kStgBytes + kBeBytes + 256 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -526,8 +651,8 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     }
     const int sms = 148;
     const int n_clusters = P.n_tiles < sms / 2 ? P.n_tiles : sms / 2;
-    if (f16) conv_tc3_kernel<true><<<dim3(2 * n_clusters), kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, P);
-    else conv_tc3_kernel<false><<<dim3(2 * n_clusters), kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, P);
+    if (f16) conv_tc3_kernel<true><<<dim3(2 * n_clusters), kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, mres, mout, P);
+    else conv_tc3_kernel<false><<<dim3(2 * n_clusters), kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, mres, mout, P);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }

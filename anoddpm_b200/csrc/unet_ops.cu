@@ -259,7 +259,15 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(float* __restrict__ out, 
                     }
                     if (f16) gn_store_h<V>(dsth + (size_t)po * C, acc);
                     else gn_store<V>(dst + (size_t)po * C, acc);
-                    if (rdst) {   // mode 0 only: rounded concatenated copy of the INPUT for the fused skip conv
+                    if (mode == 1) {
+                        if (raw_out) {   // fp32 avg-pooled copy of the INPUT: the residual of a downsampling ResBlock
+                            float pr[V];
+#pragma unroll
+                            for (int j = 0; j < V; ++j)
+                                pr[j] = (v[u][0][j] + v[u][1 % NT][j] + v[u][2 % NT][j] + v[u][3 % NT][j]) * 0.25f;
+                            gn_store<V>(raw_out + (size_t)b * npo * C + c + (size_t)po * C, pr);
+                        }
+                    } else if (rdst) {   // mode 0: rounded concatenated copy of the INPUT for the fused skip conv
                         if (f16) {
                             gn_store_h<V>(rdsth + (size_t)po * C, v[u][0]);
                         } else {
@@ -691,7 +699,7 @@ extern "C" int anoddpm_gn_apply(void* out_v, void* raw_out_v, const float* x1, i
     ADP_REQUIRE(groups > 0 && groups * ANODDPM_STAT_REPLICAS <= 256 && C % groups == 0, "anoddpm_gn_apply: bad groups (at most 32)");
     ADP_REQUIRE(mode >= 0 && mode <= 2, "anoddpm_gn_apply: bad mode %d", mode);
     ADP_REQUIRE(mode != 1 || (H % 2 == 0 && W % 2 == 0), "anoddpm_gn_apply: avg-pool needs even H, W");
-    ADP_REQUIRE(raw_out == nullptr || mode == 0, "anoddpm_gn_apply: raw_out needs mode 0");
+    ADP_REQUIRE(raw_out == nullptr || mode == 0 || (mode == 1 && C2 == 0), "anoddpm_gn_apply: raw_out needs mode 0, or mode 1 with one source");
     ADP_REQUIRE(rtf32 >= 0 && rtf32 <= 2, "anoddpm_gn_apply: out_mode must be 0 (fp32), 1 (tf32-rounded fp32) or 2 (fp16)");
     const int V = (gn_vec(C1, C2, groups, x1, x2) == 4 && al16(out) && (!raw_out || al16(raw_out))) ? 4 : 1;
     const int Ho = mode == 1 ? H / 2 : (mode == 2 ? H * 2 : H), Wo = mode == 1 ? W / 2 : (mode == 2 ? W * 2 : W);

@@ -198,7 +198,9 @@ class UNetEngine:
         Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
         odt = torch.float16 if out_mode == 2 else torch.float32
         out = torch.empty((B, Ho, Wo, C), device=x1.t.device, dtype=odt)
-        raw = torch.empty((B, H, W, C), device=x1.t.device, dtype=odt) if want_raw else None
+        raw = None
+        if want_raw:      # mode 0: rounded concatenated copy of the input; mode 1: fp32 avg-pooled input
+            raw = torch.empty((B, Ho, Wo, C), device=x1.t.device, dtype=odt if mode == 0 else torch.float32)
         call("anoddpm_gn_apply", ptr(out), ptr(raw), ptr(x1.t), C1, ptr(x2.t) if x2 is not None else None, C2,
              ptr(st1), ptr(st2), ptr(gn.weight), ptr(gn.bias), B, H, W, 32, float(gn.eps), int(silu), mode,
              int(out_mode), stream())
@@ -272,8 +274,12 @@ class UNetEngine:
         # tensor-core path: the fused 1x1 skip conv reads a rounded (TF32 / fp16), channel-concatenated copy of x that
         # is written by the same pass that normalises x (round to nearest instead of the MMA's operand truncation)
         raw = None
+        pooled = None
         if e["skip_conv"] and plan2[0] and self._out_mode(plan1) == self._out_mode(plan2):
             a1, raw = self._gn_apply(srcs, e["gn1"], B, H, W, True, mode, self._out_mode(plan1), want_raw=True)
+        elif mode == 1 and not e["skip_conv"] and plan2[0] == 3:
+            # the halo-reuse kernel takes a same-resolution residual: the pass that normalises x also avg-pools it
+            a1, pooled = self._gn_apply(srcs, e["gn1"], B, H, W, True, mode, self._out_mode(plan1), want_raw=True)
         else:
             if e["skip_conv"] and plan2[1]:
                 plan2 = (plan2[0], False)      # no fp16 raw copy available: run conv2 with TF32 operands
@@ -287,6 +293,8 @@ class UNetEngine:
             rs = [raw] if raw is not None else [x.t for x in srcs]
             return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], plan2, r=rs), Ho, Wo
         assert len(srcs) == 1
+        if pooled is not None:
+            return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], plan2, res=pooled, res_mode=1), Ho, Wo
         return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], plan2, res=srcs[0].t,
                           res_mode=_RES_FOR_MODE[e["mode"]]), Ho, Wo
 

@@ -115,8 +115,9 @@ int anoddpm_gn_stats(double* stats /* REPLICAS x B x C x 2 (replica 0 written) *
  * ([REPLICAS][B][C1][2], [REPLICAS][B][C2][2]); x2, stats2 may be NULL (C2 = 0).
  * round_tf32 = output mode: 0 fp32; 1 fp32 rounded to TF32 (rna) for a kind::tf32 conv; 2 IEEE fp16 (rn, saturating;
  * `out` / `raw_out` then point to half elements) for a kind::f16 conv.
- * raw_out (optional, mode 0 only): also writes the rounded, channel-concatenated copy of the INPUT, which the
- * fused 1x1 skip convolution of the same ResBlock reads as its K-major operand (one pass over x for both). */
+ * raw_out (optional): mode 0: also writes the rounded, channel-concatenated copy of the INPUT, which the fused 1x1
+ * skip convolution of the same ResBlock reads as its K-major operand (one pass over x for both); mode 1 (single
+ * source): also writes the fp32 avg-pooled INPUT, the residual of a downsampling ResBlock (UNet.py:178,216). */
 int anoddpm_gn_apply(void* out, void* raw_out, const float* x1, int C1, const float* x2, int C2,
                      const double* stats1, const double* stats2, const float* gamma, const float* beta, int B, int H,
                      int W, int groups, float eps, int silu, int mode, int round_tf32, void* stream);

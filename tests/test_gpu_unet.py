@@ -35,7 +35,8 @@ def nchw(x):
     return x.permute(0, 3, 1, 2).contiguous()
 
 
-def run_conv(a, w_main, bias, ksize, impl, r=(), w_r=(), emb=None, res=None, res_mode=0, gn_stats=None, f16=False):
+def run_conv(a, w_main, bias, ksize, impl, r=(), w_r=(), emb=None, res=None, res_mode=0, gn_stats=None, f16=False,
+             skip_unsupported=True):
     """a, r*: NCHW torch tensors; returns NCHW output of anoddpm_conv."""
     from anoddpm_b200 import _lib
     from anoddpm_b200.engine import pack_conv_weight, round_tf32_
@@ -63,7 +64,7 @@ def run_conv(a, w_main, bias, ksize, impl, r=(), w_r=(), emb=None, res=None, res
     d.impl = impl
     d.operand_f16 = 1 if f16 else 0
     d.gn_stats = gn_stats.data_ptr() if gn_stats is not None else None
-    if impl == 3 and not _lib.lib().anoddpm_conv_tc3_supported(ctypes.byref(d)):
+    if impl == 3 and skip_unsupported and not _lib.lib().anoddpm_conv_tc3_supported(ctypes.byref(d)):
         pytest.skip("shape not covered by the halo-reuse kernel (needs 3x3, H,W % 16 == 0)")
     if impl >= 1:
         assert _lib.lib().anoddpm_conv_tc_supported(ctypes.byref(d))
@@ -108,6 +109,11 @@ def test_conv_fused_skip_sources_and_residual_modes(impl):
     for mode, res in ((1, torch.randn(B, Co, H, W, generator=g)), (2, torch.randn(B, Co, 2 * H, 2 * W, generator=g)),
                       (3, torch.randn(B, Co, H // 2, W // 2, generator=g))):
         res = res.to(DEV)
+        if impl == 3 and mode == 2:
+            # the halo-reuse kernel takes same-resolution / upsampled residuals only (anoddpm_gn_apply pools): loud error
+            with pytest.raises(RuntimeError, match="res_mode"):
+                run_conv(a, w, b, 3, impl, res=res, res_mode=mode, skip_unsupported=False)
+            continue
         out = run_conv(a, w, b, 3, impl, res=res, res_mode=mode)
         rr = res if mode == 1 else (F.avg_pool2d(res, 2, 2) if mode == 2 else F.interpolate(res, scale_factor=2, mode="nearest"))
         ref = F.conv2d(a.double(), w.double(), b.double(), padding=1).float() + rr
@@ -227,6 +233,15 @@ def test_groupnorm_silu_resample_vs_torch():
                 ref = F.silu(ref)
             ref = F.avg_pool2d(ref, 2, 2) if mode == 1 else (F.interpolate(ref, scale_factor=2, mode="nearest") if mode == 2 else ref)
             assert rel(nchw(out), ref.float()) < 1e-5, (B, C1, C2, H, W, mode)
+            if mode == 1 and not C2:
+                # the same pass can emit the avg-pooled INPUT (the residual of a downsampling ResBlock), fp32
+                for om, dt in ((0, torch.float32), (2, torch.float16)):
+                    out2 = torch.empty(B, Ho, Wo, C, device=DEV, dtype=dt)
+                    pooled = torch.full((B, Ho, Wo, C), float("nan"), device=DEV)
+                    _lib.call("anoddpm_gn_apply", _lib.ptr(out2), _lib.ptr(pooled), _lib.ptr(x1n), C1, None, 0, _lib.ptr(st1),
+                              None, _lib.ptr(gamma), _lib.ptr(beta), B, H, W, 32, 1e-5, silu, mode, om, _lib.stream())
+                    assert rel(nchw(pooled), F.avg_pool2d(x1, 2, 2)) < 1e-6
+                    assert rel(nchw(out2.float()), ref.float()) < (1e-5 if om == 0 else 2e-3)
 
 
 def test_attention_vs_reference_formula():

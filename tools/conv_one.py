@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Time one tensor-core conv configuration through the C ABI (CUDA events), for epilogue attribution and ncu captures.
+
+  python tools/conv_one.py --ci 128 --co 128 --hw 256 --variants          # table over epilogue variants
+  ncu --set full --import-source on -k regex:conv_tc3 -s 3 -c 1 -o gpurun_out/x python tools/conv_one.py --res 1 --stats
+"""
+import argparse
+import ctypes
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from anoddpm_b200 import _lib          # noqa: E402
+
+
+def run(a, B, Ci, Co, HW, res, stats, emb, cr=0, n=10):
+    dev = torch.device("cuda:0")
+    x = torch.randn(B, HW, HW, Ci, device=dev).half()
+    w = (torch.randn(Co, 9 * Ci + cr, device=dev) * 0.03).half()
+    r1 = torch.randn(B, HW, HW, cr, device=dev).half() if cr else None
+    bias = torch.randn(Co, device=dev)
+    out = torch.empty(B, HW, HW, Co, device=dev)
+    d = _lib.ConvDesc()
+    d.out, d.a, d.w, d.bias = out.data_ptr(), x.data_ptr(), w.data_ptr(), bias.data_ptr()
+    d.B, d.H, d.W, d.Ca, d.Cout, d.ksize, d.impl = B, HW, HW, Ci, Co, 3, a.impl
+    d.operand_f16 = 1
+    if cr:
+        d.r1, d.Cr1 = r1.data_ptr(), cr
+    keep = []
+    if res:
+        shape = {1: (B, HW, HW, Co), 2: (B, 2 * HW, 2 * HW, Co), 3: (B, HW // 2, HW // 2, Co)}[res]
+        rt = torch.randn(*shape, device=dev)
+        keep.append(rt)
+        d.res, d.res_mode = rt.data_ptr(), res
+    if emb:
+        et = torch.randn(B, Co, device=dev)
+        keep.append(et)
+        d.emb, d.emb_stride = et.data_ptr(), Co
+    if stats:
+        st = torch.zeros(8 * B * Co * 2, device=dev, dtype=torch.float64)
+        keep.append(st)
+        d.gn_stats = st.data_ptr()
+    f = lambda: _lib.call("anoddpm_conv", ctypes.byref(d), _lib.stream())   # noqa: E731
+    for _ in range(3):
+        f()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        f()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    flop = 2.0 * B * HW * HW * Co * (9 * Ci + cr)
+    return ms, flop / ms / 1e9
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--ci", type=int, default=128)
+    ap.add_argument("--co", type=int, default=128)
+    ap.add_argument("--cr", type=int, default=0)
+    ap.add_argument("--hw", type=int, default=256)
+    ap.add_argument("--res", type=int, default=0)
+    ap.add_argument("--impl", type=int, default=3)
+    ap.add_argument("--stats", action="store_true")
+    ap.add_argument("--emb", action="store_true")
+    ap.add_argument("--variants", action="store_true")
+    a = ap.parse_args()
+    if a.variants:
+        print(f"| conv {a.ci}->{a.co} @{a.hw}^2 bs{a.batch} impl{a.impl} fp16 | ms | TFLOP/s |\n|---|---:|---:|")
+        for name, res, stats, emb, cr in (("plain", 0, False, False, 0), ("+stats", 0, True, False, 0),
+                                          ("+emb+stats", 0, True, True, 0), ("+res1", 1, False, False, 0),
+                                          ("+res1+stats", 1, True, False, 0), ("+res3+stats", 3, True, False, 0),
+                                          ("+skip1x1(256)+stats", 0, True, False, 256)):
+            ms, tf = run(a, a.batch, a.ci, a.co, a.hw, res, stats, emb, cr)
+            print(f"| {name} | {ms:.3f} | {tf:.0f} |")
+    else:
+        ms, tf = run(a, a.batch, a.ci, a.co, a.hw, a.res, a.stats, a.emb, a.cr)
+        print(f"{ms:.3f} ms  {tf:.0f} TFLOP/s")
+
+
+if __name__ == "__main__":
+    main()
