@@ -398,7 +398,7 @@ int anoddpm_conv_tc2(const anoddpm_conv_desc* d, void* stream) {
     ADP_REQUIRE(anoddpm_conv_tc_supported(d), "anoddpm_conv(impl=2): shape not covered by the tensor-core tiling "
                 "(Ca=%d Cr1=%d Cr2=%d Cout=%d H=%d W=%d); use impl=0", d->Ca, d->Cr1, d->Cr2, d->Cout, d->H, d->W);
     Tc2Args P;
-    P.out = d->out; P.bias = d->bias; P.emb = d->emb; P.res = d->res;
+    P.out = static_cast<float*>(d->out); P.bias = d->bias; P.emb = d->emb; P.res = d->res;
     P.M = d->B * d->H * d->W; P.H = d->H; P.W = d->W; P.Cout = d->Cout;
     P.emb_stride = d->emb_stride; P.res_mode = d->res_mode;
     const int TW = d->W < 128 ? d->W : 128;

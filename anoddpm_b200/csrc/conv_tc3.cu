@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "anoddpm_b200.h"
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -42,7 +43,7 @@ constexpr int kStgBytes = kEpiWarps * 2 * kStgBuf;  // 8 epilogue warps x 2 buff
 constexpr int kBeBytes = kEpiWarps * 128 * 4;       // per-warp (bias + embedding) row of the current tile
 
 struct Tc3Args {
-    float* out;
+    void* out;
     const float* bias;
     const float* emb;
     const float* res;
@@ -138,6 +139,18 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
 __device__ __forceinline__ void sts128(uint32_t a, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+__device__ __forceinline__ uint4 lds128u(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128u(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
+    const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
 // plain (per-CTA) TMA load / store used by the epilogue
 __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
                                             int c3) {
@@ -186,7 +199,7 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-template <bool F16>
+template <bool F16, bool OUT16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_r1,
                 const __grid_constant__ CUtensorMap map_r2, const __grid_constant__ CUtensorMap map_w,
@@ -347,6 +360,135 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             return tile < tile_end && R < P.n_regions;
         };
         const int cc = (lane & 3) * 4;      // channel quad of the column pass
+        if constexpr (OUT16) {
+            // ---- fp16 output: the convolution sum only (no bias / embedding, no residual), statistics of sum + bias + emb.
+            // Steps of (32 pixels x 32 channels): 64-byte fp16 rows in the same SWIZZLE_64B buffers.
+            const int cq = (lane & 3) * 8;      // 8 channels per lane in the column pass
+            float keep1[8], keep2[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) keep1[e] = keep2[e] = 0.f;
+            int cur_b = -1, cur_n0 = 0, kept = 0;
+            auto flush_stats = [&]() {
+                if (cur_b >= 0 && 32 * (lane >> 2) < P.BN) {
+                    double* st = P.gn_stats + (size_t)(cluster_id % ANODDPM_STAT_REPLICAS) * P.stat_replica_stride +
+                                 ((size_t)cur_b * P.Cout + cur_n0 + 32 * (lane >> 2) + cq) * 2;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        atomicAdd(st + 2 * e, (double)keep1[e]);
+                        atomicAdd(st + 2 * e + 1, (double)keep2[e]);
+                        keep1[e] = 0.f;
+                        keep2[e] = 0.f;
+                    }
+                }
+            };
+            int it = 0, step = 0;
+            for (int tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
+                const int acc = it & 1;
+                int b, ybase, xbase, n0;
+                const bool valid = tile_region(tile, b, ybase, xbase, n0);
+                if (P.gn_stats && valid) {
+                    if (b != cur_b || n0 != cur_n0 || kept == 8) {
+                        flush_stats();
+                        cur_b = b;
+                        cur_n0 = n0;
+                        kept = 0;
+                    }
+                    ++kept;
+                }
+                {   // (bias + timestep embedding) row of this tile: enters the statistics only
+                    const int n = n0 + lane * 4;
+                    float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid && lane * 4 < P.BN && n < P.Cout) {
+                        if (P.bias) v4 = *reinterpret_cast<const float4*>(P.bias + n);
+                        if (P.emb) {
+                            const float4 e4 = *reinterpret_cast<const float4*>(P.emb + (size_t)b * P.emb_stride + n);
+                            v4.x += e4.x; v4.y += e4.y; v4.z += e4.z; v4.w += e4.w;
+                        }
+                    }
+                    __syncwarp();
+                    sts128(smem_u32(be + lane * 4), v4);
+                    __syncwarp();
+                }
+                mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int cb = 0; cb < P.BN; cb += 32) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * 2 + sub) * P.BN + cb);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+                          "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+                          "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+                          "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (cb + 32 >= P.BN) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        mbar_arrive_remote(&tmem_empty[acc], 0);
+                    }
+                    if (!valid) continue;
+                    const int buf = step & 1;
+                    const uint32_t sba = smem_u32(stg + buf * kStgBuf), bea = smem_u32(be + cb);
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    // pixel pass: thread = pixel row, 32 channels -> 4 chunks of 8 halves
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 w;
+                        w.x = pack_half2_sat(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1]));
+                        w.y = pack_half2_sat(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+                        w.z = pack_half2_sat(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+                        w.w = pack_half2_sat(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+                        sts128u(sba + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), w);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d(&map_out, stg + buf * kStgBuf, n0 + cb, xbase + 8 * sub, ybase + 4 * quarter, b);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    if (P.gn_stats) {
+                        // column pass over the STORED halves (+ bias + embedding): lane owns channels cq..cq+7 of rows (lane >> 2) + 8k
+                        const float4 b0 = lds128(bea + cq * 4), b1 = lds128(bea + cq * 4 + 16);
+                        const float bev[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        float s1[8], s2[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int row = 8 * k + (lane >> 2);
+                            const uint4 u = lds128u(sba + row * 64 + (((lane & 3) ^ ((row >> 1) & 3)) << 4));
+                            const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&uw[e]));
+                                const float v0 = f.x + bev[2 * e], v1 = f.y + bev[2 * e + 1];
+                                s1[2 * e] += v0; s2[2 * e] += v0 * v0;
+                                s1[2 * e + 1] += v1; s2[2 * e + 1] += v1 * v1;
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+#pragma unroll
+                            for (int o = 4; o < 32; o <<= 1) {
+                                s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
+                                s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
+                            }
+                        }
+                        if ((lane >> 2) == (cb >> 5)) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) { keep1[e] += s1[e]; keep2[e] += s2[e]; }
+                        }
+                    }
+                    ++step;
+                }
+            }
+            if (P.gn_stats) flush_stats();
+        } else {
         // residual box of step (tile, cb) -> buffer buf (one lane issues; the warp's 4 image rows x 8 px x 16 ch).
         // TMA, not register loads: measured, global loads issued by the epilogue warps (pixel-per-lane or coalesced, one
         // or two steps ahead) are 15-25% slower -- they queue behind the operand bursts of the main loop
@@ -496,6 +638,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
         }
         if (P.gn_stats) flush_stats();
+        }   // !OUT16
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // buffers outlive the stores
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -541,15 +684,16 @@ int make_act_map3(CUtensorMap* m, const void* p, int f16, int C, int W, int H, i
     return ANODDPM_OK;
 }
 
-// fp32 NHWC epilogue map: dims (C, W, H, B), box (16 ch, px, rows, 1), 64-byte swizzle
-int make_epi_map3(CUtensorMap* m, const void* p, int C, int W, int H, int B, int px, int rows) {
+// NHWC epilogue map: dims (C, W, H, B), box (16 fp32 / 32 fp16 channels = 64 B, px, rows, 1), 64-byte swizzle
+int make_epi_map3(CUtensorMap* m, const void* p, int C, int W, int H, int B, int px, int rows, int f16 = 0) {
     EncodeTiledFn enc = get_encode3();
     if (!enc) { anoddpm_set_error("cuTensorMapEncodeTiled entry point not available"); return ANODDPM_ERR_CUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    cuuint32_t box[4] = {16u, (cuuint32_t)px, (cuuint32_t)rows, 1u};
+    const cuuint64_t es = f16 ? 2 : 4;
+    cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
+    cuuint32_t box[4] = {f16 ? 32u : 16u, (cuuint32_t)px, (cuuint32_t)rows, 1u};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(p), dims, strides, box, estr,
+    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(p), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -589,6 +733,7 @@ extern "C" int anoddpm_conv_tc3_supported(const anoddpm_conv_desc* d) {
     if (d->Cout % 32) return 0;
     if (d->Cout > 128 && d->Cout % 128) return 0;
     if (d->res && d->res_mode == 2) return 0;   // avg-pooled residual: pool it in anoddpm_gn_apply (or use impl 2)
+    if (d->out_f16 && d->res) return 0;         // fp16 output is for tensors that feed a GroupNorm only
     return 1;
 }
 
@@ -634,7 +779,7 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     if ((rc = make_w_map3(&mw, d->w, f16, Ktot, d->Cout, P.BN / 2))) return rc;
     // epilogue store box: (16 ch fp32, 8 px, 4 rows) of the output
     CUtensorMap mres, mout;
-    if ((rc = make_epi_map3(&mout, d->out, d->Cout, d->W, d->H, d->B, 8, 4))) return rc;
+    if ((rc = make_epi_map3(&mout, d->out, d->Cout, d->W, d->H, d->B, 8, 4, d->out_f16 ? 1 : 0))) return rc;
     mres = mout;
     if (d->res) {   // residual boxes: (16, 8, 4) at the same resolution, (16, 4, 2) of a half-resolution source
         if (d->res_mode == 3) rc = make_epi_map3(&mres, d->res, d->Cout, d->W / 2, d->H / 2, d->B, 4, 2);
@@ -645,14 +790,23 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     const size_t smem = (size_t)stages * (kABytes + 3 * b_bytes) + kStgBytes + kBeBytes + 256 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const int sms = 148;
     const int n_clusters = P.n_tiles < sms / 2 ? P.n_tiles : sms / 2;
-    if (f16) conv_tc3_kernel<true><<<dim3(2 * n_clusters), kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, mres, mout, P);
-    else conv_tc3_kernel<false><<<dim3(2 * n_clusters), kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, mres, mout, P);
+    const dim3 grid(2 * n_clusters);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d->out_f16) {
+        if (f16) conv_tc3_kernel<true, true><<<grid, kThreads, smem, st>>>(ma, m1, m2, mw, mres, mout, P);
+        else conv_tc3_kernel<false, true><<<grid, kThreads, smem, st>>>(ma, m1, m2, mw, mres, mout, P);
+    } else {
+        if (f16) conv_tc3_kernel<true, false><<<grid, kThreads, smem, st>>>(ma, m1, m2, mw, mres, mout, P);
+        else conv_tc3_kernel<false, false><<<grid, kThreads, smem, st>>>(ma, m1, m2, mw, mres, mout, P);
+    }
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }

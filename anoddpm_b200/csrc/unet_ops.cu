@@ -283,6 +283,112 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(float* __restrict__ out, 
     }
 }
 
+// ---------------------------------------------------------------- GroupNorm apply, fp16 input (+ per-channel shift)
+// x holds fp16 values of (h - shift), shift[b][c] = shift_c[c] + shift_bc[b][c] (conv bias + timestep embedding, which
+// the producing conv left out so that the stored half carries only the convolution sum); stats are those of h.
+// y = act((x + shift - mean) * rstd * gamma + beta), same resolution, one source.  Thread = 8 channels (16 B in).
+template <int OM>   // output mode: 0 fp32, 1 fp32 rounded to TF32, 2 fp16
+__global__ void __launch_bounds__(256) gn_apply_h_kernel(void* __restrict__ out_v, const __half* __restrict__ x, int C,
+                                                         const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, const float* __restrict__ shift_c,
+                                                         const float* __restrict__ shift_bc, int shift_stride, int HW,
+                                                         int groups, float eps, int do_silu, int pix_per_cta) {
+    __shared__ float s_mean[64], s_rstd[64];
+    const int b = blockIdx.y, gs = C / groups, ncv = C / 8;
+    {
+        const int g = threadIdx.x / ANODDPM_STAT_REPLICAS, r = threadIdx.x % ANODDPM_STAT_REPLICAS;
+        const int nb = gridDim.y;
+        double s = 0.0, q = 0.0;
+        if (g < groups) {
+            for (int c = g * gs; c < (g + 1) * gs; ++c) {
+                const double* st = stats + (size_t)r * nb * C * 2 + ((size_t)b * C + c) * 2;
+                s += st[0];
+                q += st[1];
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < ANODDPM_STAT_REPLICAS; o <<= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (g < groups && r == 0) {
+            const double n = (double)HW * gs;
+            const double m = s / n;
+            double var = q / n - m * m;
+            if (var < 0) var = 0;
+            s_mean[g] = (float)m;
+            s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+        }
+    }
+    __syncthreads();
+    const int p0 = blockIdx.x * pix_per_cta;
+    const int p1 = min(HW, p0 + pix_per_cta);
+    int tpr, rows;
+    if (ncv >= 256) { tpr = 256; rows = 1; }
+    else { tpr = ncv; rows = 256 / ncv; }
+    const int r = threadIdx.x / tpr, lane = threadIdx.x - r * tpr;
+    if (r >= rows) return;
+    for (int cv = lane; cv < ncv; cv += tpr) {
+        const int c = cv * 8;
+        float sc[8], bi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c + j) / gs;
+            float sh = shift_c ? shift_c[c + j] : 0.f;
+            if (shift_bc) sh += shift_bc[(size_t)b * shift_stride + c + j];
+            sc[j] = s_rstd[g] * gamma[c + j];
+            bi[j] = beta[c + j] + sc[j] * (sh - s_mean[g]);
+        }
+        const __half* src = x + (size_t)b * HW * C + c;
+        constexpr int U = 4;
+        for (int pb = p0 + r; pb < p1; pb += rows * U) {
+            uint4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int po = pb + u * rows;
+                if (po < p1) v[u] = *reinterpret_cast<const uint4*>(src + (size_t)po * C);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int po = pb + u * rows;
+                if (po >= p1) continue;
+                const __half2* h2 = reinterpret_cast<const __half2*>(&v[u]);
+                float y[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h2[j]);
+                    y[2 * j] = f.x * sc[2 * j] + bi[2 * j];
+                    y[2 * j + 1] = f.y * sc[2 * j + 1] + bi[2 * j + 1];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (do_silu) y[j] = OM ? silu_fast(y[j]) : silu(y[j]);
+                    if (OM == 1) y[j] = round_tf32(y[j]);
+                }
+                const size_t o = ((size_t)b * HW + po) * C + c;
+                if (OM == 2) {
+                    uint4 w;
+                    uint32_t* wp = reinterpret_cast<uint32_t*>(&w);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const __half2 hh = __floats2half2_rn(fminf(fmaxf(y[2 * j], -65504.f), 65504.f),
+                                                             fminf(fmaxf(y[2 * j + 1], -65504.f), 65504.f));
+                        wp[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
+                    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out_v) + o) = w;
+                } else {
+                    float* op = reinterpret_cast<float*>(out_v) + o;
+                    F4 a, bq;
+                    a.x = y[0]; a.y = y[1]; a.z = y[2]; a.w = y[3];
+                    bq.x = y[4]; bq.y = y[5]; bq.z = y[6]; bq.w = y[7];
+                    st4(op, a);
+                    st4(op + 4, bq);
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- exact fp32 implicit-GEMM conv
 // CTA tile 64 pixels x 64 output channels, K chunks of 16 input channels of one tap.
 constexpr int CBM = 64, CBN = 64, CBK = 16;
@@ -384,7 +490,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs A) {
             v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
         }
         F4 o; o.x = v[0]; o.y = v[1]; o.z = v[2]; o.w = v[3];
-        st4(d.out + (size_t)q * d.Cout + n, o);
+        st4(static_cast<float*>(d.out) + (size_t)q * d.Cout + n, o);
     }
 }
 
@@ -718,6 +824,30 @@ extern "C" int anoddpm_gn_apply(void* out_v, void* raw_out_v, const float* x1, i
     return ANODDPM_OK;
 }
 
+extern "C" int anoddpm_gn_apply_f16in(void* out, const void* x_f16, int C, const double* stats, const float* gamma,
+                                      const float* beta, const float* shift_c, const float* shift_bc, int shift_stride,
+                                      int B, int H, int W, int groups, float eps, int do_silu, int out_mode, void* stream) {
+    ADP_REQUIRE(out && x_f16 && stats && gamma && beta && B > 0 && B <= 65535 && H > 0 && W > 0,
+                "anoddpm_gn_apply_f16in: bad arguments");
+    ADP_REQUIRE(groups > 0 && groups * ANODDPM_STAT_REPLICAS <= 256 && C % groups == 0 && C % 8 == 0,
+                "anoddpm_gn_apply_f16in: needs C %% 8 == 0 and at most 32 groups dividing C (C=%d groups=%d)", C, groups);
+    ADP_REQUIRE(out_mode >= 0 && out_mode <= 2, "anoddpm_gn_apply_f16in: out_mode must be 0, 1 or 2");
+    ADP_REQUIRE(al16(out) && al16(x_f16), "anoddpm_gn_apply_f16in: pointers must be 16-byte aligned");
+    ADP_REQUIRE(!shift_bc || shift_stride >= C, "anoddpm_gn_apply_f16in: shift stride smaller than C");
+    const int HW = H * W;
+    int wpc = 512;
+    while (wpc > 32 && (long long)adp_ceil_div(HW, wpc) * B < 148 * 4) wpc >>= 1;
+    dim3 grid((unsigned)adp_ceil_div(HW, wpc), B);
+    cudaStream_t st = (cudaStream_t)stream;
+    const __half* x = static_cast<const __half*>(x_f16);
+#define ADP_GN_H(OM) gn_apply_h_kernel<OM><<<grid, 256, 0, st>>>(out, x, C, stats, gamma, beta, shift_c, shift_bc, shift_stride, \
+                                                                HW, groups, eps, do_silu, wpc)
+    if (out_mode == 2) ADP_GN_H(2); else if (out_mode == 1) ADP_GN_H(1); else ADP_GN_H(0);
+#undef ADP_GN_H
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}
+
 extern "C" int anoddpm_conv(const anoddpm_conv_desc* d, void* stream) {
     ADP_REQUIRE(d && d->out && d->a && d->w, "anoddpm_conv: null pointer");
     ADP_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cout > 0 && d->Ca > 0, "anoddpm_conv: bad shape");
@@ -734,6 +864,7 @@ extern "C" int anoddpm_conv(const anoddpm_conv_desc* d, void* stream) {
                     (!d->res || al16(d->res)),
                 "anoddpm_conv: pointers must be 16-byte aligned");
     ADP_REQUIRE(!d->operand_f16 || d->impl == 2 || d->impl == 3, "anoddpm_conv: fp16 operands need impl 2 or 3");
+    ADP_REQUIRE(!d->out_f16 || d->impl == 3, "anoddpm_conv: fp16 output needs impl 3");
     if (d->impl == 3) return anoddpm_conv_tc3(d, stream);
     ADP_REQUIRE(d->gn_stats == nullptr, "anoddpm_conv: fused GroupNorm statistics need impl 3");
     if (d->impl == 1) return anoddpm_conv_tc(d, stream);

@@ -42,11 +42,13 @@ def pack_conv_weight(w):
 
 
 class _T:
-    """An NHWC activation and (optionally) its per-channel statistics [B][C][2] fp64 (sum, sum of squares)."""
-    __slots__ = ("t", "st")
+    """An NHWC activation and (optionally) its per-channel statistics [B][C][2] fp64 (sum, sum of squares).
+    shift = (bias, emb_rows): an fp16 conv output that stores the convolution sum only; the statistics describe
+    t + bias[c] + emb_rows[b, c], and the GroupNorm pass adds that offset back in fp32."""
+    __slots__ = ("t", "st", "shift")
 
-    def __init__(self, t, st=None):
-        self.t, self.st = t, st
+    def __init__(self, t, st=None, shift=None):
+        self.t, self.st, self.shift = t, st, shift
 
 
 class _Conv:
@@ -190,6 +192,16 @@ class UNetEngine:
         """srcs: one or two _T (channel-concatenated).  out_mode: 0 fp32, 1 fp32 rounded to TF32, 2 fp16."""
         x1 = srcs[0]
         x2 = srcs[1] if len(srcs) > 1 else None
+        if x1.shift is not None:
+            assert x2 is None and mode == 0 and not want_raw and x1.st is not None and x1.t.dtype == torch.float16
+            C = x1.t.shape[-1]
+            bias, emb = x1.shift
+            out = torch.empty((B, H, W, C), device=x1.t.device, dtype=torch.float16 if out_mode == 2 else torch.float32)
+            call("anoddpm_gn_apply_f16in", ptr(out), ptr(x1.t), C, ptr(x1.st), ptr(gn.weight), ptr(gn.bias), ptr(bias),
+                 ptr(emb), self.emb_all.shape[1] if emb is not None else 0, B, H, W, 32, float(gn.eps), int(silu),
+                 int(out_mode), stream())
+            self.launches += 1
+            return out
         st1 = self._stats_of(x1, B, H * W)
         st2 = self._stats_of(x2, B, H * W) if x2 is not None else None
         C1 = x1.t.shape[-1]
@@ -207,7 +219,7 @@ class UNetEngine:
         self.launches += 1
         return (out, raw) if want_raw else out
 
-    def _conv(self, site, a, B, H, W, cout, plan, r=(), emb=None, res=None, res_mode=0, want_stats=True):
+    def _conv(self, site, a, B, H, W, cout, plan, r=(), emb=None, res=None, res_mode=0, want_stats=True, out_f16=False):
         impl, f16 = plan
         d = ConvDesc()
         d.B, d.H, d.W = B, H, W
@@ -217,7 +229,8 @@ class UNetEngine:
         d.operand_f16 = 1 if f16 else 0
         assert a.dtype == (torch.float16 if f16 else torch.float32)
         w, b = site.packed(impl, f16)
-        out = torch.empty((B, H, W, cout), device=a.device, dtype=torch.float32)
+        out = torch.empty((B, H, W, cout), device=a.device, dtype=torch.float16 if out_f16 else torch.float32)
+        d.out_f16 = 1 if out_f16 else 0
         d.out, d.a, d.w, d.bias = out.data_ptr(), a.data_ptr(), w.data_ptr(), b.data_ptr()
         d.r1 = r[0].data_ptr() if len(r) > 0 else None
         d.r2 = r[1].data_ptr() if len(r) > 1 else None
@@ -240,6 +253,10 @@ class UNetEngine:
         self.launches += 1
         self.tc_convs += 1 if impl else 0
         self.f16_convs += 1 if f16 else 0
+        if out_f16:
+            assert st is not None and res is None
+            self.f16_outputs += 1
+            return _T(out, st, shift=(b, emb))
         return _T(out, st)
 
     def _plan(self, H, W, Ca, Cr, cout, ksize):
@@ -285,7 +302,9 @@ class UNetEngine:
                 plan2 = (plan2[0], False)      # no fp16 raw copy available: run conv2 with TF32 operands
             a1 = self._gn_apply(srcs, e["gn1"], B, H, W, True, mode, self._out_mode(plan1))
         emb = self.emb_all[:, e["emb_off"]:]
-        h = self._conv(e["conv1"], a1, B, Ho, Wo, e["cout"], plan1, emb=emb)
+        # conv1's output feeds GroupNorm 2 only: stored as fp16 without its per-channel offset where the fast kernel runs
+        h = self._conv(e["conv1"], a1, B, Ho, Wo, e["cout"], plan1, emb=emb,
+                       out_f16=self.h1_f16 and plan1[0] == 3 and plan1[1])
         del a1
         a2 = self._gn_apply([h], e["gn2"], B, Ho, Wo, True, 0, self._out_mode(plan2))
         del h
@@ -350,6 +369,8 @@ class UNetEngine:
         # the rate and half the bytes) wherever every channel count is a multiple of 64; the others use kind::tf32.
         self.tc_impl = {"tc": 3, "tc_tf32": 3, "tc2": 2, "tc1": 1, "exact": 0}[m.conv_impl]
         self.allow_f16 = m.conv_impl == "tc"
+        self.h1_f16 = self.allow_f16 and getattr(m, "h1_fp16", True)
+        self.f16_outputs = 0
         self.f16_convs = 0
         self.fused_stats = 0
         self.stats_passes = 0

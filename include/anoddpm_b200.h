@@ -122,6 +122,13 @@ int anoddpm_gn_apply(void* out, void* raw_out, const float* x1, int C1, const fl
                      const double* stats1, const double* stats2, const float* gamma, const float* beta, int B, int H,
                      int W, int groups, float eps, int silu, int mode, int round_tf32, void* stream);
 
+/* The same GroupNorm (+SiLU) for an fp16 input produced by anoddpm_conv with out_f16 (same resolution, one source,
+ * C % 8 == 0): y = act((x + shift - mean) * rstd * gamma + beta) with shift[b][c] = shift_c[c] + shift_bc[b][c]
+ * (either may be NULL) -- the conv bias and timestep-embedding row the producer left out; stats are those of x + shift. */
+int anoddpm_gn_apply_f16in(void* out, const void* x_f16, int C, const double* stats, const float* gamma,
+                           const float* beta, const float* shift_c, const float* shift_bc, int shift_stride, int B, int H,
+                           int W, int groups, float eps, int silu, int out_mode, void* stream);
+
 /* Convolution as implicit GEMM over NHWC pixels.  out[b,y,x,:] =
  *     conv_k(a)[..] (k = ksize 3 pad 1, or 1)  +  r1 . W_r1  +  r2 . W_r2      (1x1 "skip" sources, optional)
  *   + bias  +  emb[b, :] (optional)  +  residual (optional)
@@ -134,7 +141,7 @@ int anoddpm_gn_apply(void* out, void* raw_out, const float* x1, int C1, const fl
  * 3 = as 2 with halo reuse (16x16 spatial regions, vertical taps share one TMA box, two M-subtiles share each weight
  *     tile) -- 3x3 convs with H, W % 16 == 0; cuts L2->SM operand traffic ~2.5x.  The fast path. */
 typedef struct anoddpm_conv_desc {
-    float* out;
+    void* out;         /* fp32 NHWC; fp16 when out_f16 */
     const void* a;     /* fp32, or fp16 when operand_f16 (same for r1, r2, w) */
     const void* r1;
     const void* r2;
@@ -152,6 +159,10 @@ typedef struct anoddpm_conv_desc {
                            mantissa as TF32 at twice the tensor rate and half the operand bytes; channels % 64 == 0 */
     double* gn_stats;   /* optional, impl 3 only: += (sum, sum of squares) of the OUTPUT per (sample, channel), layout
                            [ANODDPM_STAT_REPLICAS][B][Cout][2] fp64 (sum over replicas = what anoddpm_gn_stats computes) */
+    int out_f16;        /* impl 3 only, no residual: `out` holds fp16 and receives the convolution sum WITHOUT bias and
+                           embedding (the half then carries no per-channel offset); gn_stats still describes
+                           h = out + bias + emb, and anoddpm_gn_apply_f16in adds the offset back in fp32.  For an output
+                           that is consumed by a GroupNorm only (conv1 of a ResBlock, UNet.py:190-200). */
 } anoddpm_conv_desc;
 int anoddpm_conv(const anoddpm_conv_desc* d /* [host] */, void* stream);
 /* 1 if impl=1/2 (tcgen05 tiles: channels % 32, Cout % 16, power-of-two W) covers the problem, else 0. */

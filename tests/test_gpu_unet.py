@@ -244,6 +244,47 @@ def test_groupnorm_silu_resample_vs_torch():
                     assert rel(nchw(out2.float()), ref.float()) < (1e-5 if om == 0 else 2e-3)
 
 
+def test_conv_fp16_output_and_shifted_groupnorm():
+    """conv1 of a ResBlock on the fast path: out = fp16(conv sum), statistics of (out + bias + emb), and the GroupNorm
+    pass that adds the offset back -- against torch group_norm(silu) of the fp32 conv output."""
+    from anoddpm_b200 import _lib
+    from anoddpm_b200.engine import pack_conv_weight
+    g = torch.Generator().manual_seed(21)
+    for (B, Ci, Co, H, W) in [(2, 64, 128, 32, 32), (3, 128, 64, 16, 16), (1, 128, 128, 64, 64), (5, 64, 256, 16, 16)]:
+        a = torch.randn(B, Ci, H, W, generator=g).to(DEV).half()
+        w = (torch.randn(Co, Ci, 3, 3, generator=g) * (9 * Ci) ** -0.5).to(DEV).half()
+        bias = (torch.randn(Co, generator=g) * 3).to(DEV)          # large offsets: must not cost fp16 precision
+        emb = (torch.randn(B, Co + 64, generator=g) * 3).to(DEV)
+        gamma, beta = torch.randn(Co, generator=g).to(DEV), torch.randn(Co, generator=g).to(DEV)
+        wp = pack_conv_weight(w.float()).half().contiguous()
+        an = nhwc(a.float()).half()
+        out = torch.full((B, H, W, Co), float("nan"), device=DEV, dtype=torch.float16)
+        st = torch.zeros(REPL, B, Co, 2, dtype=torch.float64, device=DEV)
+        d = _lib.ConvDesc()
+        d.out, d.a, d.w, d.bias = out.data_ptr(), an.data_ptr(), wp.data_ptr(), bias.data_ptr()
+        d.B, d.H, d.W, d.Ca, d.Cout, d.ksize, d.impl = B, H, W, Ci, Co, 3, 3
+        d.emb, d.emb_stride = emb.data_ptr(), emb.shape[1]
+        d.operand_f16, d.out_f16, d.gn_stats = 1, 1, st.data_ptr()
+        assert _lib.lib().anoddpm_conv_tc3_supported(ctypes.byref(d))
+        _lib.call("anoddpm_conv", ctypes.byref(d), _lib.stream())
+        conv = F.conv2d(a.double(), w.double(), None, padding=1)
+        assert rel(nchw(out.float()), conv.float()) < 1e-3                      # fp16 rounding of the stored sum
+        hfull = nchw(out.float()).double() + bias.double()[None, :, None, None] + emb[:, :Co].double()[:, :, None, None]
+        xg = hfull.reshape(B, Co, -1)
+        exact = torch.stack([xg.sum(-1), (xg * xg).sum(-1)], dim=-1)
+        assert torch.allclose(st.sum(0), exact, rtol=2e-5, atol=1e-2), (st.sum(0) - exact).abs().max()
+        ref = F.silu(F.group_norm(hfull, 32, gamma.double(), beta.double(), 1e-5)).float()
+        for om, dt, tol in ((0, torch.float32, 1e-5), (2, torch.float16, 2e-3), (1, torch.float32, 2e-3)):
+            y = torch.full((B, H, W, Co), float("nan"), device=DEV, dtype=dt)
+            _lib.call("anoddpm_gn_apply_f16in", _lib.ptr(y), _lib.ptr(out), Co, _lib.ptr(st), _lib.ptr(gamma), _lib.ptr(beta),
+                      _lib.ptr(bias), _lib.ptr(emb), emb.shape[1], B, H, W, 32, 1e-5, 1, om, _lib.stream())
+            assert rel(nchw(y.float()), ref) < tol, (B, Ci, Co, H, W, om, rel(nchw(y.float()), ref))
+        # a residual cannot be combined with the fp16 output: loud error
+        d.res, d.res_mode = an.data_ptr(), 1
+        with pytest.raises(RuntimeError):
+            _lib.call("anoddpm_conv", ctypes.byref(d), _lib.stream())
+
+
 def test_attention_vs_reference_formula():
     from anoddpm_b200 import _lib
     from oracle import unet_oracle  # noqa: F401  (attention formula restated inline below)
