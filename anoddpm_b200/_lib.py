@@ -52,6 +52,8 @@ SIGNATURES = {
     "anoddpm_conv_tc3_supported": (c_int, [ctypes.POINTER(ConvDesc)]),
     "anoddpm_conv_stem": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "anoddpm_conv_head": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "anoddpm_conv_head_gn": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32,
+                             c_vp]),
     "anoddpm_attention": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "anoddpm_attention_tc_supported": (c_int, [c_int, c_int, c_int]),
     "anoddpm_attention_tc_workspace_bytes": (ctypes.c_longlong, [c_int, c_int, c_int]),

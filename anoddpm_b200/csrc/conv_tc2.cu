@@ -43,6 +43,8 @@ struct Tc2Args {
     int stages;
     int ke;                    // elements per 128-byte K-block row: 32 (fp32 operands) or 64 (fp16 operands)
     int n_tiles_n, n_tiles;   // tiles along N, total pair tiles
+    double* gn_stats;          // optional [REPLICAS][B][Cout][2]: per-channel (sum, sum of squares) of the output
+    long long stat_replica_stride;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -291,13 +293,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive_remote(&tmem_empty[acc], 0);
                 }
-                if (!valid) continue;
                 const int nb = n0 + cb;
+                // statistics: the 32 rows of a warp belong to one sample (host checks H*W % 32 == 0)
+                const int q0 = m0 + quarter * 32;
+                const bool wvalid = q0 < P.M;
+                const int bw = wvalid ? q0 / (P.W * P.H) : 0;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const int n = nb + j;
                     if (n >= P.Cout) break;
-                    float v[4];
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (valid) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         v[e] = __uint_as_float(r[j + e]);
@@ -325,6 +331,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
                     }
                     *reinterpret_cast<float4*>(P.out + (size_t)q * P.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                    if (P.gn_stats) {   // warp-uniform
+                        float sv[8] = {v[0], v[1], v[2], v[3], v[0] * v[0], v[1] * v[1], v[2] * v[2], v[3] * v[3]};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) sv[e] += __shfl_xor_sync(0xffffffffu, sv[e], o);
+                        }
+                        if (wvalid && lane < 8) {
+                            float mine = 0.f;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) if (lane == e) mine = sv[e];
+                            // lane e < 4: sum of channel n + e; lane 4 + e: its sum of squares
+                            double* st = P.gn_stats + (size_t)(cluster_id % ANODDPM_STAT_REPLICAS) * P.stat_replica_stride +
+                                         ((size_t)bw * P.Cout + n + (lane & 3)) * 2 + (lane >> 2);
+                            atomicAdd(st, (double)mine);
+                        }
+                    }
                 }
             }
         }
@@ -401,6 +425,9 @@ int anoddpm_conv_tc2(const anoddpm_conv_desc* d, void* stream) {
     P.out = static_cast<float*>(d->out); P.bias = d->bias; P.emb = d->emb; P.res = d->res;
     P.M = d->B * d->H * d->W; P.H = d->H; P.W = d->W; P.Cout = d->Cout;
     P.emb_stride = d->emb_stride; P.res_mode = d->res_mode;
+    ADP_REQUIRE(!d->gn_stats || (d->H * d->W) % 32 == 0, "anoddpm_conv(impl=2): fused statistics need H*W %% 32 == 0");
+    P.gn_stats = d->gn_stats;
+    P.stat_replica_stride = (long long)d->B * d->Cout * 2;
     const int TW = d->W < 128 ? d->W : 128;
     int TH = 128 / TW; if (TH > d->H) TH = d->H;
     const int TB = 128 / (TW * TH);

@@ -37,24 +37,46 @@ __global__ void tembed_kernel(float* __restrict__ emb, const long long* __restri
 }
 
 // ---------------------------------------------------------------- linear: one warp per (b, n)
+// warp = (output feature n, group of LB samples): the weight row is read once per group instead of once per sample; per
+// (b, n) the summation order is unchanged (lane-strided partial sums, then a butterfly).  act: bit 0 = SiLU on the
+// input, bit 1 = SiLU on the output.
+constexpr int LB = 8;
 __global__ void __launch_bounds__(256) linear_kernel(float* __restrict__ y, int ldy, const float* __restrict__ x,
                                                      int ldx, const float* __restrict__ w,
-                                                     const float* __restrict__ bias, int B, int N, int K,
-                                                     int silu_in) {
+                                                     const float* __restrict__ bias, int B, int N, int K, int act) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= B * N) return;
-    const int b = warp / N, n = warp - b * N;
-    const float* xr = x + (size_t)b * ldx;
+    const int ngroups = (B + LB - 1) / LB;
+    if (warp >= ngroups * N) return;
+    const int bg = warp / N, n = warp - bg * N;
+    const int b0 = bg * LB;
     const float* wr = w + (size_t)n * K;
-    float acc = 0.f;
+    float acc[LB];
+#pragma unroll
+    for (int i = 0; i < LB; ++i) acc[i] = 0.f;
     for (int k = lane; k < K; k += 32) {
-        float xv = xr[k];
-        if (silu_in) xv = silu(xv);
-        acc = fmaf(xv, wr[k], acc);
+        const float wv = wr[k];
+#pragma unroll
+        for (int i = 0; i < LB; ++i) {
+            if (b0 + i < B) {
+                float xv = x[(size_t)(b0 + i) * ldx + k];
+                if (act & 1) xv = silu(xv);
+                acc[i] = fmaf(xv, wv, acc[i]);
+            }
+        }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) y[(size_t)b * ldy + n] = acc + (bias ? bias[n] : 0.f);
+    for (int i = 0; i < LB; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    }
+    if (lane < LB && b0 + lane < B) {
+        float v = 0.f;
+#pragma unroll
+        for (int i = 0; i < LB; ++i) if (lane == i) v = acc[i];
+        v += bias ? bias[n] : 0.f;
+        if (act & 2) v = silu(v);
+        y[(size_t)(b0 + lane) * ldy + n] = v;
+    }
 }
 
 // ---------------------------------------------------------------- GroupNorm statistics (per channel)
@@ -606,15 +628,55 @@ __global__ void __launch_bounds__(256) conv_stem4_kernel(float* __restrict__ out
 // chunk as [co][tap][16].  Each thread owns one output pixel (all COUT <= 4 channels, compile-time).  The input is
 // read once from HBM (+33% halo); inner loop = 2 LDS.128 + 4*COUT FFMA per 4 channels.
 constexpr int HT_H = 8, HT_W = 32, HT_C = 16, HT_P = 20;
-template <int COUT>
+// GN = true: `a` is the raw tensor and GroupNorm + SiLU (UNet.py:384-386) are applied while the tile is staged (each
+// element once per CTA), from per-channel statistics -- no normalised copy of the last feature map is written at all.
+constexpr int HT_MAXC = 512;
+template <int COUT, bool GN>
 __global__ void __launch_bounds__(256) conv_head_kernel(float* __restrict__ out, const float* __restrict__ a,
                                                         const float* __restrict__ w, const float* __restrict__ bias,
-                                                        int B, int Cin, int H, int W) {
+                                                        int B, int Cin, int H, int W, const double* __restrict__ stats,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        int groups, float eps) {
     __shared__ __align__(16) float st[(HT_H + 2) * (HT_W + 2) * HT_P];
     __shared__ __align__(16) float swt[COUT * 9 * HT_C];
+    __shared__ __align__(16) float s_sc[GN ? HT_MAXC : 4], s_bi[GN ? HT_MAXC : 4];
+    __shared__ float s_mean[64], s_rstd[64];
     const int tiles_x = (W + HT_W - 1) / HT_W, tiles_y = (H + HT_H - 1) / HT_H;
     const int tile = blockIdx.x;
     const int b = tile / (tiles_x * tiles_y), tr = tile - b * tiles_x * tiles_y;
+    if (GN) {
+        // group statistics exactly as gn_apply_kernel: thread (g, r) adds up replica r of group g
+        const int gs = Cin / groups;
+        const int g = threadIdx.x / ANODDPM_STAT_REPLICAS, r = threadIdx.x % ANODDPM_STAT_REPLICAS;
+        double s = 0.0, q = 0.0;
+        if (g < groups) {
+            for (int c = g * gs; c < (g + 1) * gs; ++c) {
+                const double* sp = stats + (size_t)r * B * Cin * 2 + ((size_t)b * Cin + c) * 2;
+                s += sp[0];
+                q += sp[1];
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < ANODDPM_STAT_REPLICAS; o <<= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (g < groups && r == 0) {
+            const double n = (double)H * W * gs;
+            const double m = s / n;
+            double var = q / n - m * m;
+            if (var < 0) var = 0;
+            s_mean[g] = (float)m;
+            s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
+            const int gg = c / gs;
+            const float sc = s_rstd[gg] * gamma[c];
+            s_sc[c] = sc;
+            s_bi[c] = beta[c] - sc * s_mean[gg];
+        }
+    }
     const int y0 = (tr / tiles_x) * HT_H, x0 = (tr % tiles_x) * HT_W;
     const int py = threadIdx.x / HT_W, px = threadIdx.x % HT_W;
     float acc[COUT];
@@ -627,8 +689,16 @@ __global__ void __launch_bounds__(256) conv_head_kernel(float* __restrict__ out,
             const int ly = pix / (HT_W + 2), lx = pix - ly * (HT_W + 2);
             const int gy = y0 + ly - 1, gx = x0 + lx - 1;
             F4 v = {0.f, 0.f, 0.f, 0.f};
-            if (gy >= 0 && gy < H && gx >= 0 && gx < W && c0 + q < Cin)
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W && c0 + q < Cin) {
                 v = ld4(a + (((size_t)b * H + gy) * W + gx) * Cin + c0 + q);
+                if (GN) {   // the zero padding applies to the ACTIVATED tensor: out-of-image taps stay 0
+                    const F4 sc = ld4(&s_sc[c0 + q]), bi = ld4(&s_bi[c0 + q]);
+                    v.x = silu(v.x * sc.x + bi.x);
+                    v.y = silu(v.y * sc.y + bi.y);
+                    v.z = silu(v.z * sc.z + bi.z);
+                    v.w = silu(v.w * sc.w + bi.w);
+                }
+            }
             st4(&st[pix * HT_P + q], v);
         }
         for (int i = threadIdx.x; i < COUT * 9 * HT_C; i += blockDim.x) {
@@ -761,11 +831,10 @@ extern "C" int anoddpm_timestep_embedding(float* emb, const int64_t* t, const fl
 }
 
 extern "C" int anoddpm_linear(float* y, int ldy, const float* x, int ldx, const float* w, const float* bias, int B,
-                              int N, int K, int silu_in, void* stream) {
-    ADP_REQUIRE(y && x && w && B > 0 && N > 0 && K > 0, "anoddpm_linear: bad arguments");
-    const long long warps = (long long)B * N;
-    linear_kernel<<<adp_ceil_div(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(y, ldy, x, ldx, w, bias, B, N, K,
-                                                                                   silu_in);
+                              int N, int K, int act, void* stream) {
+    ADP_REQUIRE(y && x && w && B > 0 && N > 0 && K > 0 && act >= 0 && act <= 3, "anoddpm_linear: bad arguments");
+    const long long warps = (long long)adp_ceil_div(B, LB) * N;
+    linear_kernel<<<adp_ceil_div(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(y, ldy, x, ldx, w, bias, B, N, K, act);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }
@@ -866,7 +935,7 @@ extern "C" int anoddpm_conv(const anoddpm_conv_desc* d, void* stream) {
     ADP_REQUIRE(!d->operand_f16 || d->impl == 2 || d->impl == 3, "anoddpm_conv: fp16 operands need impl 2 or 3");
     ADP_REQUIRE(!d->out_f16 || d->impl == 3, "anoddpm_conv: fp16 output needs impl 3");
     if (d->impl == 3) return anoddpm_conv_tc3(d, stream);
-    ADP_REQUIRE(d->gn_stats == nullptr, "anoddpm_conv: fused GroupNorm statistics need impl 3");
+    ADP_REQUIRE(d->gn_stats == nullptr || d->impl == 2, "anoddpm_conv: fused GroupNorm statistics need impl 2 or 3");
     if (d->impl == 1) return anoddpm_conv_tc(d, stream);
     if (d->impl == 2) return anoddpm_conv_tc2(d, stream);
     ADP_REQUIRE(d->impl == 0, "anoddpm_conv: unknown impl %d", d->impl);
@@ -910,10 +979,33 @@ extern "C" int anoddpm_conv_head(float* out, const float* a, const float* w, con
     ADP_REQUIRE(tiles < (1LL << 31), "anoddpm_conv_head: too many tiles");
     cudaStream_t st = (cudaStream_t)stream;
     switch (Cout) {
-        case 1: conv_head_kernel<1><<<(unsigned)tiles, 256, 0, st>>>(out, a, w, bias, B, Cin, H, W); break;
-        case 2: conv_head_kernel<2><<<(unsigned)tiles, 256, 0, st>>>(out, a, w, bias, B, Cin, H, W); break;
-        case 3: conv_head_kernel<3><<<(unsigned)tiles, 256, 0, st>>>(out, a, w, bias, B, Cin, H, W); break;
-        default: conv_head_kernel<4><<<(unsigned)tiles, 256, 0, st>>>(out, a, w, bias, B, Cin, H, W); break;
+        case 1: conv_head_kernel<1, false><<<(unsigned)tiles, 256, 0, st>>>(out, a, w, bias, B, Cin, H, W, nullptr, nullptr, nullptr, 1, 0.f); break;
+        case 2: conv_head_kernel<2, false><<<(unsigned)tiles, 256, 0, st>>>(out, a, w, bias, B, Cin, H, W, nullptr, nullptr, nullptr, 1, 0.f); break;
+        case 3: conv_head_kernel<3, false><<<(unsigned)tiles, 256, 0, st>>>(out, a, w, bias, B, Cin, H, W, nullptr, nullptr, nullptr, 1, 0.f); break;
+        default: conv_head_kernel<4, false><<<(unsigned)tiles, 256, 0, st>>>(out, a, w, bias, B, Cin, H, W, nullptr, nullptr, nullptr, 1, 0.f); break;
+    }
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}
+
+extern "C" int anoddpm_conv_head_gn(float* out, const float* x, const double* stats, const float* gamma, const float* beta,
+                                    const float* w, const float* bias, int B, int Cin, int H, int W, int Cout, int groups,
+                                    float eps, void* stream) {
+    ADP_REQUIRE(out && x && stats && gamma && beta && w && B > 0 && Cin > 0 && H > 0 && W > 0,
+                "anoddpm_conv_head_gn: bad arguments");
+    ADP_REQUIRE(Cout >= 1 && Cout <= 4, "anoddpm_conv_head_gn: Cout must be 1..4 (got %d)", Cout);
+    ADP_REQUIRE(Cin % 4 == 0 && Cin <= HT_MAXC && al16(x), "anoddpm_conv_head_gn: Cin must be a multiple of 4, at most %d",
+                HT_MAXC);
+    ADP_REQUIRE(groups > 0 && groups * ANODDPM_STAT_REPLICAS <= 256 && Cin % groups == 0,
+                "anoddpm_conv_head_gn: bad groups (at most 32, dividing Cin)");
+    const long long tiles = (long long)B * adp_ceil_div(H, HT_H) * adp_ceil_div(W, HT_W);
+    ADP_REQUIRE(tiles < (1LL << 31), "anoddpm_conv_head_gn: too many tiles");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (Cout) {
+        case 1: conv_head_kernel<1, true><<<(unsigned)tiles, 256, 0, st>>>(out, x, w, bias, B, Cin, H, W, stats, gamma, beta, groups, eps); break;
+        case 2: conv_head_kernel<2, true><<<(unsigned)tiles, 256, 0, st>>>(out, x, w, bias, B, Cin, H, W, stats, gamma, beta, groups, eps); break;
+        case 3: conv_head_kernel<3, true><<<(unsigned)tiles, 256, 0, st>>>(out, x, w, bias, B, Cin, H, W, stats, gamma, beta, groups, eps); break;
+        default: conv_head_kernel<4, true><<<(unsigned)tiles, 256, 0, st>>>(out, x, w, bias, B, Cin, H, W, stats, gamma, beta, groups, eps); break;
     }
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;

@@ -243,7 +243,7 @@ class UNetEngine:
         d.impl = impl
         d.gn_stats = None
         st = None
-        if want_stats and impl == 3:
+        if want_stats and (impl == 3 or (impl == 2 and (H * W) % 32 == 0)):
             # the epilogue also accumulates the per-channel statistics of its output: no statistics pass for any
             # GroupNorm that later consumes this tensor (alone or concatenated with a skip tensor)
             st = self._stats_slot(B, cout)
@@ -393,11 +393,11 @@ class UNetEngine:
         l1, l2 = m.time_embedding[1], m.time_embedding[3]
         e1 = torch.empty((B, E), device=dev, dtype=torch.float32)
         call("anoddpm_linear", ptr(e1), E, ptr(temb), base, ptr(l1.weight), ptr(l1.bias), B, E, base, 0, stream())
-        emb = torch.empty((B, E), device=dev, dtype=torch.float32)
-        call("anoddpm_linear", ptr(emb), E, ptr(e1), E, ptr(l2.weight), ptr(l2.bias), B, E, E, 1, stream())
+        emb = torch.empty((B, E), device=dev, dtype=torch.float32)      # SiLU(time embedding): every ResBlock applies it
+        call("anoddpm_linear", ptr(emb), E, ptr(e1), E, ptr(l2.weight), ptr(l2.bias), B, E, E, 3, stream())
         S = self.emb_cat_w.shape[0]
         self.emb_all = torch.empty((B, S), device=dev, dtype=torch.float32)
-        call("anoddpm_linear", ptr(self.emb_all), S, ptr(emb), E, ptr(self.emb_cat_w), ptr(self.emb_cat_b), B, S, E, 1,
+        call("anoddpm_linear", ptr(self.emb_all), S, ptr(emb), E, ptr(self.emb_cat_w), ptr(self.emb_cat_b), B, S, E, 0,
              stream())
         self.launches += 4
         # per-channel statistics of every activation that feeds a GroupNorm, bump-allocated, one memset per forward
@@ -420,10 +420,17 @@ class UNetEngine:
             assert (sh, sw) == (H, W)
             h, H, W = self._entry(entry, [h, sk], B, H, W)
         hd = self.head
-        a = self._gn_apply([h], hd["gn"], B, H, W, True, 0, 0)
         out = torch.empty((B, m.out_channels, H, W), device=dev, dtype=torch.float32)
-        call("anoddpm_conv_head", ptr(out), ptr(a), ptr(self.head_w), ptr(hd["conv"].bias), B, a.shape[-1], H, W,
-             m.out_channels, stream())
+        C = h.t.shape[-1]
+        if C <= 512 and m.out_channels <= 4:
+            # GroupNorm + SiLU applied while the head conv stages its tiles: the last feature map is read once
+            gn = hd["gn"]
+            call("anoddpm_conv_head_gn", ptr(out), ptr(h.t), ptr(self._stats_of(h, B, H * W)), ptr(gn.weight), ptr(gn.bias),
+                 ptr(self.head_w), ptr(hd["conv"].bias), B, C, H, W, m.out_channels, 32, float(gn.eps), stream())
+        else:
+            a = self._gn_apply([h], hd["gn"], B, H, W, True, 0, 0)
+            call("anoddpm_conv_head", ptr(out), ptr(a), ptr(self.head_w), ptr(hd["conv"].bias), B, C, H, W,
+                 m.out_channels, stream())
         self.launches += 1
         self.emb_all = None
         self.stats_pool = None

@@ -98,10 +98,10 @@ int anoddpm_detection_counts(double* counts /* B x 6 */, const float* image, con
 int anoddpm_timestep_embedding(float* emb /* B x dim */, const int64_t* t, const float* freq /* dim/2 */, int B,
                                int dim, void* stream);
 
-/* y[b, n] = sum_k act(x[b,k]) * w[n,k] + bias[n], act = SiLU if silu_in.  UNet.py:271-276, :185-188 (nn.Linear).
- * ldx / ldy: row strides of x / y (elements). */
+/* y[b, n] = g(sum_k f(x[b,k]) * w[n,k] + bias[n]); act bit 0: f = SiLU (else identity), bit 1: g = SiLU.
+ * UNet.py:271-276, :185-188 (nn.Linear between nn.SiLU).  ldx / ldy: row strides of x / y (elements). */
 int anoddpm_linear(float* y, int ldy, const float* x, int ldx, const float* w, const float* bias, int B, int N, int K,
-                   int silu_in, void* stream);
+                   int act, void* stream);
 
 /* Per-channel statistics of an NHWC tensor: stats[b][c] += (sum, sum of squares) over the HW pixels, fp64 (caller
  * zeroes).  Per-channel sums are grouping-agnostic: a GroupNorm over this tensor, or over its concatenation with another
@@ -157,7 +157,7 @@ typedef struct anoddpm_conv_desc {
     int impl;
     int operand_f16;    /* impl 2/3 only: a, r1, r2, w hold IEEE fp16 (tcgen05 kind::f16, fp32 accumulate): the same 10-bit
                            mantissa as TF32 at twice the tensor rate and half the operand bytes; channels % 64 == 0 */
-    double* gn_stats;   /* optional, impl 3 only: += (sum, sum of squares) of the OUTPUT per (sample, channel), layout
+    double* gn_stats;   /* optional, impl 3 (or impl 2 with H*W % 32 == 0): += (sum, sum of squares) of the OUTPUT per (sample, channel), layout
                            [ANODDPM_STAT_REPLICAS][B][Cout][2] fp64 (sum over replicas = what anoddpm_gn_stats computes) */
     int out_f16;        /* impl 3 only, no residual: `out` holds fp16 and receives the convolution sum WITHOUT bias and
                            embedding (the half then carries no per-channel offset); gn_stats still describes
@@ -176,6 +176,12 @@ int anoddpm_conv_stem(float* out_nhwc, const float* x_nchw, const float* w_oihw,
 /* Head: NHWC activated features -> NCHW image (Cout small), 3x3 pad 1, w packed [Cout][9*Cin] tap-major. UNet.py:384-388 */
 int anoddpm_conv_head(float* out_nchw, const float* a_nhwc, const float* w_packed, const float* bias, int B, int Cin,
                       int H, int W, int Cout, void* stream);
+/* The whole output head in one pass: out = conv3x3(SiLU(GroupNorm(x))) (UNet.py:384-388).  x is the raw last feature map
+ * (NHWC fp32), stats its per-channel statistics ([REPLICAS][B][Cin][2]); the normalisation is applied while the tile is
+ * staged, so no normalised copy is written.  Cin <= 512. */
+int anoddpm_conv_head_gn(float* out_nchw, const float* x_nhwc, const double* stats, const float* gamma, const float* beta,
+                         const float* w_packed, const float* bias, int B, int Cin, int H, int W, int Cout, int groups,
+                         float eps, void* stream);
 
 /* QKV attention on qkv[B][T][3*C] (channel layout [head][q|k|v][ch], UNet.py:146-147):
  * out[b][t][h*ch + c] = sum_s softmax_s( (q_t . k_s) / sqrt(ch) ) v_s[c].   UNet.py:137-153. */

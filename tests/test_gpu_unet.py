@@ -207,6 +207,24 @@ def test_conv_fused_groupnorm_statistics(shape):
     assert torch.allclose(ref.sum(0), exact, rtol=1e-5, atol=1e-3) and float(ref[1:].abs().sum()) == 0.0
 
 
+@pytest.mark.parametrize("shape", [(4, 512, 512, 8, 8, 3), (3, 256, 768, 16, 16, 1), (2, 512, 512, 8, 8, 1), (5, 64, 32, 8, 4, 3)])
+def test_conv_tc2_fused_groupnorm_statistics(shape):
+    """impl 2 (small maps, 1x1 convs) emits the same per-channel statistics when every warp's 32 rows share a sample."""
+    from anoddpm_b200 import _lib
+    B, Ci, Co, H, W, ks = shape
+    g = torch.Generator().manual_seed(Ci + Co + ks)
+    a = torch.randn(B, Ci, H, W, generator=g).to(DEV)
+    w = (torch.randn(Co, Ci, ks, ks, generator=g) * (ks * ks * Ci) ** -0.5).to(DEV)
+    b = torch.randn(Co, generator=g).to(DEV)
+    res = torch.randn(B, Co, H, W, generator=g).to(DEV)
+    fused = torch.zeros(REPL, B, Co, 2, dtype=torch.float64, device=DEV)
+    out = run_conv(a, w if ks == 3 else w[:, :, 0], b, ks, 2, res=res, res_mode=1, gn_stats=fused)
+    torch.cuda.synchronize()
+    xg = out.double().reshape(B, Co, -1)
+    exact = torch.stack([xg.sum(-1), (xg * xg).sum(-1)], dim=-1)
+    assert torch.allclose(fused.sum(0), exact, rtol=1e-5, atol=1e-3), (fused.sum(0) - exact).abs().max()
+
+
 def test_groupnorm_silu_resample_vs_torch():
     from anoddpm_b200 import _lib
     g = torch.Generator().manual_seed(5)
@@ -349,6 +367,35 @@ def test_timestep_embedding_and_linear():
     y = torch.empty(5, 300, device=DEV)
     _lib.call("anoddpm_linear", _lib.ptr(y), 300, _lib.ptr(x), 128, _lib.ptr(w), _lib.ptr(b), 5, 300, 128, 1, _lib.stream())
     assert rel(y, F.linear(F.silu(x.double()), w.double(), b.double()).float()) < 1e-5
+    for act in (0, 2, 3):       # bit 0: SiLU on the input, bit 1: SiLU on the output
+        _lib.call("anoddpm_linear", _lib.ptr(y), 300, _lib.ptr(x), 128, _lib.ptr(w), _lib.ptr(b), 5, 300, 128, act, _lib.stream())
+        ref = F.linear(F.silu(x.double()) if act & 1 else x.double(), w.double(), b.double())
+        assert rel(y, (F.silu(ref) if act & 2 else ref).float()) < 1e-5, act
+    xb = torch.randn(37, 64, generator=g).to(DEV)                     # batch not a multiple of the sample group
+    yb = torch.empty(37, 300, device=DEV)
+    _lib.call("anoddpm_linear", _lib.ptr(yb), 300, _lib.ptr(xb), 64, _lib.ptr(w[:, :64].contiguous()), None, 37, 300, 64, 0, _lib.stream())
+    assert rel(yb, F.linear(xb.double(), w[:, :64].double()).float()) < 1e-5
+
+
+def test_head_conv_with_fused_groupnorm_silu():
+    """anoddpm_conv_head_gn = conv3x3(SiLU(GroupNorm(x))) in one pass (UNet.py:384-388)."""
+    from anoddpm_b200 import _lib
+    from anoddpm_b200.engine import pack_conv_weight
+    g = torch.Generator().manual_seed(31)
+    for (B, C, H, W, Co) in [(2, 128, 32, 64, 1), (1, 64, 16, 16, 3), (3, 32, 40, 24, 1)]:
+        x = (torch.randn(B, C, H, W, generator=g) * 2 + 0.7).to(DEV)
+        w = (torch.randn(Co, C, 3, 3, generator=g) * 0.1).to(DEV)
+        bias = torch.randn(Co, generator=g).to(DEV)
+        gamma, beta = torch.randn(C, generator=g).to(DEV), torch.randn(C, generator=g).to(DEV)
+        xn = nhwc(x)
+        st = torch.zeros(REPL, B, C, 2, dtype=torch.float64, device=DEV)
+        _lib.call("anoddpm_gn_stats", _lib.ptr(st), _lib.ptr(xn), C, B, H * W, _lib.stream())
+        out = torch.full((B, Co, H, W), float("nan"), device=DEV)
+        wp = pack_conv_weight(w).contiguous()
+        _lib.call("anoddpm_conv_head_gn", _lib.ptr(out), _lib.ptr(xn), _lib.ptr(st), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(wp),
+                  _lib.ptr(bias), B, C, H, W, Co, 32, 1e-5, _lib.stream())
+        ref = F.conv2d(F.silu(F.group_norm(x.double(), 32, gamma.double(), beta.double(), 1e-5)), w.double(), bias.double(), padding=1)
+        assert rel(out, ref.float()) < 2e-5, (B, C, H, W, Co, rel(out, ref.float()))
 
 
 UNET_CASES = {
