@@ -240,8 +240,8 @@ def _time_ms(fn, n=10, warm=3):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel/shape (conv 128->128 @256^2 bs 32,
-# fp16 operands, fp32 output) from the committed `ncu --set full` capture profiles/r01b_ncu_conv_tc3.md
-NCU_TRAFFIC_DOMINANT = {"bytes": 0.538801e9 + 1.016694e9, "source": "profiles/r01b_ncu_conv_tc3.md (launch 1)"}
+# fp16 operands, fp32 output) from the committed `ncu --set full` capture profiles/r01e_ncu_conv_tc3.md
+NCU_TRAFFIC_DOMINANT = {"bytes": 0.600476e9 + 1.023989e9, "source": "profiles/r01e_ncu_conv_tc3.md"}
 
 
 def roofline(model, dev, B):
@@ -277,7 +277,7 @@ def roofline(model, dev, B):
         tot_ms += ms * count
         del a, w, out
     dom = res[0]
-    kname = {3: "conv_tc3_kernel (tcgen05.mma.cta_group::2 kind::%s, halo-reuse persistent CTA pairs, TMA-fed implicit GEMM)" % ("f16" if f16 else "tf32"),
+    kname = {3: "conv_tc3_kernel (tcgen05.mma.cta_group::2 kind::%s, halo-reuse persistent CTA pairs, TMA-fed implicit GEMM, TMA-store epilogue)" % ("f16" if f16 else "tf32"),
              2: "conv_tc2_kernel (tcgen05.mma.cta_group::2, persistent CTA pairs)", 1: "conv_tc_kernel (tcgen05.mma kind::tf32)",
              0: "conv_simt_kernel"}[impl]
     peak = pk["bf16_burst"]      # the kernel is timed alone here -> burst figure (B200_PROFILING.md)
@@ -328,7 +328,43 @@ def aux_rooflines(dev):
     gb = 6.0 * xa.numel() / 1e9
     out["gn_apply"] = {"bound": "hbm", "shape": "(32,256,256,128) fp32 -> fp16", "bytes": gb * 1e9, "ms": ms,
                        "achieved": gb / ms * 1e3, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / ms * 1e3 / pk["hbm_gbs"]}
-    del xa, oa
+    # the same pass on an fp16 conv1 output (4 B/elem)
+    xh = xa.half()
+    shc = torch.zeros(128, device=dev)
+    ms = _time_ms(lambda: _lib.call("anoddpm_gn_apply_f16in", _lib.ptr(oa), _lib.ptr(xh), 128, _lib.ptr(st), _lib.ptr(g1), _lib.ptr(b1),
+                                    _lib.ptr(shc), None, 0, 32, 256, 256, 32, 1e-5, 1, 2, _lib.stream()))
+    gb = 4.0 * xa.numel() / 1e9
+    out["gn_apply_f16in"] = {"bound": "hbm", "shape": "(32,256,256,128) fp16 -> fp16", "bytes": gb * 1e9, "ms": ms,
+                             "achieved": gb / ms * 1e3, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / ms * 1e3 / pk["hbm_gbs"]}
+    del xa, oa, xh
+    # tcgen05 attention at the BASELINE shape (T=256, C=512, 2 heads): tiny (4.3 GFLOP), latency- not pipe-bound
+    L = _lib.lib()
+    qkv = torch.randn(32, 256, 3 * 512, device=dev)
+    ao = torch.empty(32, 256, 512, device=dev, dtype=torch.float16)
+    ws = torch.empty(L.anoddpm_attention_tc_workspace_bytes(32, 256, 512), device=dev, dtype=torch.uint8)
+    ms = _time_ms(lambda: _lib.call("anoddpm_attention_tc", _lib.ptr(ao), _lib.ptr(qkv), _lib.ptr(ws), 32, 256, 512, 2, 2, _lib.stream()))
+    fl = 4.0 * 32 * 2 * 256 * 256 * 256
+    out["attention_tc"] = {"bound": "tensor (latency-bound at this size)", "shape": "B32 T256 C512 heads2 (pack + attention kernel)",
+                           "ms": ms, "flop": fl, "achieved": fl / ms / 1e9, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                           "frac": fl / ms / 1e9 / pk["bf16_sustained"],
+                           "bytes": 32 * 256 * 512 * (12 + 2) , "gbs": 32 * 256 * 512 * 14 / ms / 1e6}
+    del qkv, ao, ws
+    # fused clip + AdamW + EMA step (training row T1): 4 B/param (norm pass) + 20 B read + 16 B written per parameter
+    npar = 131_650_000
+    pp, gg, mm, vv, ee = (torch.randn(npar, device=dev) * 0.01 for _ in range(5))
+    vv.abs_()
+    ssq = torch.zeros(1, device=dev, dtype=torch.float64)
+
+    def opt_step():
+        ssq.zero_()
+        _lib.call("anoddpm_sumsq", _lib.ptr(ssq), _lib.ptr(gg), npar, _lib.stream())
+        _lib.call("anoddpm_adamw_ema_step", _lib.ptr(pp), _lib.ptr(gg), _lib.ptr(mm), _lib.ptr(vv), _lib.ptr(ee), _lib.ptr(ssq), npar,
+                  1e-4, 0.9, 0.999, 1e-8, 0.0, 10, 1.0, 0.9999, _lib.stream())
+    ms = _time_ms(opt_step)
+    gb = 40.0 * npar / 1e9
+    out["adamw_ema_step"] = {"bound": "hbm", "shape": "131.65 M parameters (clip + AdamW + EMA, 2 kernels)", "bytes": gb * 1e9, "ms": ms,
+                             "achieved": gb / ms * 1e3, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gb / ms * 1e3 / pk["hbm_gbs"]}
+    del pp, gg, mm, vv, ee
     # simplex: BASELINE config 5 = 3-D field (32,256,256) x 8 octaves (there is no 4-D generator in the reference)
     tabs = torch.from_numpy(init_tables([12345])).to(dev)
     vol = torch.empty(32, 256, 256, device=dev)
