@@ -442,8 +442,68 @@ def run_reference(args):
                       "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+# ------------------------------------------------------------------------------------------------ training step (config 2)
+def run_train(args):
+    """BASELINE configs[1] / SURVEY 8(d) config 2: one training step at bs 8 per GPU, 256x256, simplex noise.
+    NOT the headline metric (never run by default).  The UNet forward/backward of this step is PyTorch autograd
+    (UNetModel.allow_autograd_fallback, library kernels) -- native backward kernels are not built; the noise, q_sample
+    and the optimiser side (one all-reduce of the flat gradient + clip + AdamW + EMA, csrc/optim.cu) are native."""
+    import copy
+    from anoddpm_b200 import GaussianDiffusionModel, UNetModel, dist as D, get_beta_schedule
+    from anoddpm_b200.optim import FusedAdamWEMA
+    rank, world, local = D.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = 8
+    UNetModel.allow_autograd_fallback = True
+    model = build_unet(dev).train()
+    ema = copy.deepcopy(model)
+    opt = FusedAdamWEMA(model, ema, lr=1e-4, weight_decay=0.0, betas=(0.9, 0.999), max_norm=1.0, ema_decay=0.9999)
+    diff = GaussianDiffusionModel([256, 256], get_beta_schedule(1000, "linear"), loss_weight="none", noise="simplex")
+    targs = {"train_start": True, "sample_distance": 800, "Batch_Size": B}
+    np.random.seed(rank)
+    g = torch.Generator().manual_seed(2000 + rank)
+    x_host = (torch.rand(B, 1, 256, 256, generator=g) * 2 - 1).pin_memory()
+    losses = []
+
+    def step():
+        x = x_host.to(dev, non_blocking=True)
+        opt.zero_grad()
+        loss, _ = diff.p_loss(model, x, targs)
+        loss.backward()
+        opt.step()
+        losses.append(loss.detach())
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    D.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    clk = sampler.stop()
+    ms = D.max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
+    D.barrier()
+    if rank == 0:
+        print(json.dumps({"metric": "training px/s (256x256 bs 8 per GPU, simplex, AdamW + EMA)", "value": world * B * 65536 / (ms / 1e3),
+                          "unit": "px/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32 (TF32 library convs in the autograd fallback) / native f32 optimiser",
+                          "data": "synthetic", "config": {"workload": "BASELINE configs[1]: train step bs 8 per GPU", "global_batch": world * B},
+                          "native_parts": "simplex noise, q_sample, gradient all-reduce + clip + AdamW + EMA (2 kernels)",
+                          "library_parts": "UNet forward + backward (PyTorch autograd: native backward kernels not built)",
+                          "loss_first_last": [float(losses[0]), float(losses[-1])], "clocks": clk}))
+    D.barrier()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--train", action="store_true", help="secondary metric: BASELINE configs[1] training step (see run_train)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
@@ -459,6 +519,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.train:
+        run_train(args)
     else:
         run_native(args)
 
