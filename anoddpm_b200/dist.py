@@ -68,3 +68,9 @@ def sum_over_ranks(value, device):
 def barrier():
     if dist.is_available() and dist.is_initialized():
         dist.barrier()
+
+
+def shutdown():
+    """tear the process group down (no-op when torch.distributed was never initialised)"""
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()

@@ -58,11 +58,16 @@ class ClockSampler:
         self.idx = gpu_index
         self.proc = None
         self.rows = []
+        self.mark_at = 0
+
+    def mark(self):
+        """the timed region starts here (start() is called before the warm-up so that nvidia-smi is already streaming)"""
+        self.mark_at = len(self.rows)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -76,7 +81,10 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows, note = self.rows[self.mark_at:], None
+        if not rows and self.rows:      # timed region shorter than the sampling interval: last warm-up samples (same load)
+            rows, note = self.rows[-2:], "timed region shorter than the 100 ms sampling interval: last warm-up samples (same load)"
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -87,8 +95,11 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def build_unet(device):
@@ -147,13 +158,14 @@ def run_native(args):
         return y.cpu()
 
     clocks = ClockSampler(local)
+    clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     host_enqueue_ms = None
     if args.full_chain:
         for _ in range(args.warmup):
             chain(x_host, T_DISTANCE)
         torch.cuda.synchronize(); D.barrier()
-        clocks.start(); l0, e0 = launches["n"], eng.launches
+        clocks.mark(); l0, e0 = launches["n"], eng.launches
         ev0.record()
         for _ in range(args.steps):
             chain(x_host, T_DISTANCE)
@@ -166,7 +178,7 @@ def run_native(args):
         launches["n"] += 1
         x = reverse_steps(x, T_DISTANCE - 1, args.warmup)
         torch.cuda.synchronize(); D.barrier()
-        clocks.start(); l0, e0 = launches["n"], eng.launches
+        clocks.mark(); l0, e0 = launches["n"], eng.launches
         ev0.record()
         h0 = time.perf_counter()
         x = reverse_steps(x, T_DISTANCE - 1 - args.warmup, args.steps)
@@ -474,13 +486,14 @@ def run_train(args):
         opt.step()
         losses.append(loss.detach())
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     D.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.mark()
     e0.record()
     for _ in range(args.steps):
         step()
@@ -523,6 +536,8 @@ def main():
         run_train(args)
     else:
         run_native(args)
+    from anoddpm_b200 import dist as D
+    D.shutdown()
 
 
 if __name__ == "__main__":
