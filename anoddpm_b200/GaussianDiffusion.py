@@ -456,7 +456,35 @@ class GaussianDiffusionModel:
     p_sample_loop = forward_backward
 
     # ---- VLB / loss (plain torch; SURVEY 8(f) N2) --------------------------------------------------
+    def _vlb_logvars(self, device):
+        """[2][T] fp32 = fp32(posterior_log_variance_clipped), fp32(log model variance): what extract() hands calc_vlb_xt"""
+        key = "vlb" + str(device)
+        if key not in self._dev_tables:
+            _, logvar = self._model_var()
+            rows = [torch.from_numpy(np.asarray(self.posterior_log_variance_clipped, dtype=np.float64)).float(),
+                    torch.from_numpy(logvar).float()]
+            self._dev_tables[key] = torch.stack(rows).contiguous().to(device)
+        return self._dev_tables[key]
+
     def calc_vlb_xt(self, model, x_0, x_t, t, estimate_noise=None):
+        """bits/dim of one step (GaussianDiffusion.py:384-397).  Without autograd (calc_total_vlb, evaluation) the KL and
+        the decoder NLL come out of one fused kernel; with a gradient flowing into the noise estimate (hybrid loss) the
+        torch formulas below are used."""
+        if estimate_noise is None:
+            estimate_noise = model(x_t, t)
+        if x_t.is_cuda and not (torch.is_grad_enabled() and estimate_noise.requires_grad):
+            x0c, xtc = self._prep(x_0, "x_0"), self._prep(x_t, "x_t")
+            epc = self._prep(estimate_noise.detach(), "noise estimate")
+            tt = self._t(t, xtc)
+            B = xtc.shape[0]
+            per = xtc.numel() // B
+            acc = torch.zeros(B, 2, device=xtc.device, dtype=torch.float64)
+            pred = torch.empty_like(xtc)
+            _lib.call("anoddpm_vlb_terms", _lib.ptr(acc), _lib.ptr(pred), _lib.ptr(x0c), _lib.ptr(xtc), _lib.ptr(epc), _lib.ptr(tt),
+                      _lib.ptr(self._tables(xtc.device)[4:]), _lib.ptr(self._vlb_logvars(xtc.device)), self.num_timesteps, B, per,
+                      _lib.stream())
+            terms = (acc / (per * np.log(2.0))).float()
+            return {"output": torch.where(tt == 0, terms[:, 1], terms[:, 0]), "pred_x_0": pred}
         true_mean, _, true_log_var = self.q_posterior_mean_variance(x_0, x_t, t)
         output = self.p_mean_variance(model, x_t, t, estimate_noise)
         kl = mean_flat(normal_kl(true_mean, true_log_var, output["mean"], output["log_variance"])) / np.log(2.0)

@@ -37,6 +37,7 @@ SIGNATURES = {
     "anoddpm_q_sample": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp]),
     "anoddpm_p_sample": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
     "anoddpm_detection_counts": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_int, c_i64, c_vp]),
+    "anoddpm_vlb_terms": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
     "anoddpm_sumsq": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "anoddpm_adamw_ema_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_int,
                                        c_f32, c_f32, c_vp]),

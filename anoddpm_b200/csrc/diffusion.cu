@@ -193,6 +193,72 @@ extern "C" int anoddpm_p_sample(float* sample, float* pred_x0, const float* x_t,
     return ANODDPM_OK;
 }
 
+// ---- variational-bound term (reference GaussianDiffusion.py:43-93, 384-397) --------------------------
+// acc[b] += {sum of KL(q(x_{t-1}|x_t,x_0) || p(x_{t-1}|x_t)), sum of -log p(x_0|x_1) (discretised Gaussian)} over the
+// sample's elements, from x_0, x_t and the model's noise estimate in ONE pass (the reference materialises ~20
+// intermediate tensors).  The caller divides by n*ln 2 and selects by t == 0.  Optionally writes pred_x_0.
+__device__ __forceinline__ float std_normal_cdf_tanh(float x) {
+    return 0.5f * (1.0f + tanhf(0.7978845608028654f * (x + 0.044715f * (x * x * x))));
+}
+__global__ void __launch_bounds__(256) vlb_terms_kernel(double* __restrict__ acc, float* __restrict__ pred_x0,
+                                                        const float* __restrict__ x_0, const float* __restrict__ x_t,
+                                                        const float* __restrict__ eps, const long long* __restrict__ t,
+                                                        const float* __restrict__ tab, const float* __restrict__ logvars,
+                                                        int T, long long per_sample) {
+    const int b = blockIdx.y;
+    const long long tb = t[b];
+    const float ra = tab[tb], rm1 = tab[T + tb], c1 = tab[2 * T + tb], c2 = tab[3 * T + tb];
+    const float lv1 = logvars[tb], lv2 = logvars[T + tb];     // true posterior / model log-variance
+    const float e12 = expf(lv1 - lv2), em2 = expf(-lv2), inv_std = expf(-(0.5f * lv2));
+    const size_t base = (size_t)b * per_sample;
+    float kl_sum = 0.f, nll_sum = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x) {
+        const float x0 = x_0[base + i], xt = x_t[base + i];
+        const float p = fminf(fmaxf(ra * xt - rm1 * eps[base + i], -1.0f), 1.0f);
+        if (pred_x0) pred_x0[base + i] = p;
+        const float mean = c1 * p + c2 * xt, tmean = c1 * x0 + c2 * xt;
+        const float d = tmean - mean;
+        kl_sum += 0.5f * (-1.0f + lv2 - lv1 + e12 + (d * d) * em2);
+        const float c = x0 - mean;
+        const float cdf_plus = std_normal_cdf_tanh(inv_std * (c + 1.0f / 255.0f));
+        const float cdf_min = std_normal_cdf_tanh(inv_std * (c - 1.0f / 255.0f));
+        float lp;
+        if (x0 < -0.999f) lp = logf(fmaxf(cdf_plus, 1e-12f));
+        else if (x0 > 0.999f) lp = logf(fmaxf(1.0f - cdf_min, 1e-12f));
+        else lp = logf(fmaxf(cdf_plus - cdf_min, 1e-12f));
+        nll_sum -= lp;
+    }
+    __shared__ float red[8][2];
+    float v[2] = {kl_sum, nll_sum};
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[warp][0] = v[0]; red[warp][1] = v[1]; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += (double)red[w][threadIdx.x];
+        atomicAdd(&acc[(size_t)b * 2 + threadIdx.x], s);
+    }
+}
+
+extern "C" int anoddpm_vlb_terms(double* acc, float* pred_x0, const float* x_0, const float* x_t, const float* eps,
+                                 const int64_t* t, const float* tables, const float* logvars, int T, int B,
+                                 int64_t per_sample, void* stream) {
+    ADP_REQUIRE(acc && x_0 && x_t && eps && t && tables && logvars, "anoddpm_vlb_terms: null pointer");
+    ADP_REQUIRE(B > 0 && B <= 65535 && per_sample > 0 && T > 0, "anoddpm_vlb_terms: bad sizes");
+    long long bx = (per_sample + 256 * 4 - 1) / (256 * 4);
+    if (bx > 64) bx = 64;
+    if (bx < 1) bx = 1;
+    vlb_terms_kernel<<<dim3((unsigned)bx, (unsigned)B), 256, 0, (cudaStream_t)stream>>>(acc, pred_x0, x_0, x_t, eps,
+                                                                                        (const long long*)t, tables,
+                                                                                        logvars, T, per_sample);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}
+
 extern "C" int anoddpm_detection_counts(double* counts, const float* image, const float* recon, const float* mask,
                                         float threshold, int B, int64_t per_sample, void* stream) {
     ADP_REQUIRE(counts && image && recon && mask, "anoddpm_detection_counts: null pointer");

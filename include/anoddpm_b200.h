@@ -91,6 +91,15 @@ int anoddpm_p_sample(float* sample, float* pred_x0, const float* x_t, const floa
 int anoddpm_detection_counts(double* counts /* B x 6 */, const float* image, const float* recon, const float* mask,
                              float threshold, int B, int64_t per_sample, void* stream);
 
+/* Variational-bound term of one (x_0, x_t, eps, t) batch (GaussianDiffusion.py:384-397 calc_vlb_xt with :43-93):
+ * acc[b] += {sum over the sample of KL(q(x_{t-1}|x_t,x_0) || p), sum of the discretised-Gaussian decoder NLL} (fp64, caller
+ * zeroes); vlb[b] = (t[b] == 0 ? acc[b][1] : acc[b][0]) / (per_sample * ln 2).  tables = the (sqrt_recip_alphas_cumprod,
+ * sqrt_recipm1_alphas_cumprod, posterior_mean_coef1, posterior_mean_coef2) rows as for anoddpm_p_sample; logvars =
+ * [2][T] fp32: posterior_log_variance_clipped, log(model variance).  pred_x0 (optional) receives clamp(x_0 estimate). */
+int anoddpm_vlb_terms(double* acc /* B x 2 */, float* pred_x0, const float* x_0, const float* x_t, const float* eps,
+                      const int64_t* t, const float* tables, const float* logvars, int T, int B, int64_t per_sample,
+                      void* stream);
+
 /* ------------------------------------------------------------------ UNet denoiser ops --------- */
 
 /* emb[b, :] = cat(sin(t_b*w), cos(t_b*w)), w = freq[0..dim/2) = exp(-i*ln(1e4)/half) (built once by the caller

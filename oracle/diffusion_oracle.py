@@ -12,6 +12,7 @@ Reference lines followed (all /root/reference/GaussianDiffusion.py):
   p_mean_variance      <- :228-230, :253-267, :269-296
   sample_p             <- :298-318
   forward_backward     <- :320-359 (see_whole_sequence=None / "half" / "whole")
+  normal_kl, disc_ll, vlb_xt, prior_vlb <- :43-93, :384-397, :436-447 (pinned by tests/golden/vlb.npz)
 """
 import numpy as np
 import torch
@@ -105,3 +106,48 @@ def forward_backward(tab, model, x, t_distance, noise_fn, denoise_fn, see_whole_
         if see_whole_sequence:
             seq.append(x.clone())
     return seq if see_whole_sequence else x
+
+
+# ---- variational-bound helpers ------------------------------------------------------------------
+def normal_kl(mean1, logvar1, mean2, logvar2):
+    """KL(N(mean1, e^logvar1) || N(mean2, e^logvar2)) elementwise (:43-52)."""
+    return 0.5 * (-1 + logvar2 - logvar1 + torch.exp(logvar1 - logvar2) + ((mean1 - mean2) ** 2) * torch.exp(-logvar2))
+
+
+def _cdf(x):
+    """tanh approximation of the standard normal cdf (:55-60)"""
+    return 0.5 * (1.0 + torch.tanh(np.sqrt(2.0 / np.pi) * (x + 0.044715 * torch.pow(x, 3))))
+
+
+def disc_ll(x, means, log_scales):
+    """log-likelihood of x under a Gaussian discretised to 1/255 bins, open-ended at +-0.999 (:64-93)"""
+    c = x - means
+    inv = torch.exp(-log_scales)
+    plus, minus = _cdf(inv * (c + 1.0 / 255.0)), _cdf(inv * (c - 1.0 / 255.0))
+    log_plus = torch.log(plus.clamp(min=1e-12))
+    log_one_minus = torch.log((1.0 - minus).clamp(min=1e-12))
+    mid = torch.log((plus - minus).clamp(min=1e-12))
+    return torch.where(x < -0.999, log_plus, torch.where(x > 0.999, log_one_minus, mid))
+
+
+def _mean_flat(v):
+    return torch.mean(v, dim=list(range(1, v.dim())))
+
+
+def vlb_xt(tab, x_0, x_t, t, eps):
+    """per-sample bits/dim term: decoder NLL at t == 0, else KL(q(x_{t-1}|x_t,x_0) || p(x_{t-1}|x_t)) (:384-397)"""
+    true_mean = coef(tab.posterior_mean_coef1, t) * x_0 + coef(tab.posterior_mean_coef2, t) * x_t
+    true_logvar = coef(tab.posterior_log_variance_clipped, t).expand(x_t.shape)
+    out = p_mean_variance(tab, x_t, t, eps)
+    kl = _mean_flat(normal_kl(true_mean, true_logvar, out["mean"], out["log_variance"])) / np.log(2.0)
+    nll = _mean_flat(-disc_ll(x_0, out["mean"], 0.5 * out["log_variance"])) / np.log(2.0)
+    return {"output": torch.where(t == 0, nll, kl), "pred_x_0": out["pred_x_0"]}
+
+
+def prior_vlb(tab, x_0):
+    """KL(q(x_T | x_0) || N(0, 1)) in bits/dim (:436-447)"""
+    T = len(tab.betas)
+    t = torch.full((x_0.shape[0],), T - 1, dtype=torch.long)
+    mean = coef(tab.sqrt_alphas_cumprod, t) * x_0
+    logvar = coef(tab.log_one_minus_alphas_cumprod, t).expand(x_0.shape)
+    return _mean_flat(normal_kl(mean, logvar, torch.tensor(0.0), torch.tensor(0.0))) / np.log(2.0)

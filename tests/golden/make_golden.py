@@ -198,7 +198,34 @@ def gen_loop():
     print("loop.npz", len(out), "arrays")
 
 
+def gen_vlb():
+    """VLB helpers (GaussianDiffusion.py:43-93, 384-397, 436-447): calc_vlb_xt with a given noise estimate, its two
+    elementwise ingredients, prior_vlb."""
+    out = {}
+    for T, name in [(100, "linear"), (1000, "linear"), (1000, "cosine")]:
+        D = GD.GaussianDiffusionModel([24, 40], GD.get_beta_schedule(T, name))
+        g = torch.Generator().manual_seed(7 * T + len(name))
+        x0 = torch.rand(5, 1, 24, 40, generator=g) * 2 - 1
+        x0[0, 0, :4] = 1.0          # saturated pixels exercise the x > 0.999 / x < -0.999 branches
+        x0[1, 0, :4] = -1.0
+        noise = torch.randn(5, 1, 24, 40, generator=g)
+        eps = noise + 0.3 * torch.randn(5, 1, 24, 40, generator=g)
+        t = torch.tensor([0, 0, 1, T // 2, T - 1])
+        x_t = D.sample_q(x0, t, noise)
+        k = f"{name}{T}"
+        out[f"{k}/x0"], out[f"{k}/x_t"], out[f"{k}/eps"], out[f"{k}/t"] = x0.numpy(), x_t.numpy(), eps.numpy(), t.numpy()
+        r = D.calc_vlb_xt(None, x0, x_t, t, eps)
+        out[f"{k}/vlb"], out[f"{k}/pred_x_0"] = r["output"].numpy(), r["pred_x_0"].numpy()
+        pmv = D.p_mean_variance(None, x_t, t, eps)
+        tm, _, tlv = D.q_posterior_mean_variance(x0, x_t, t)
+        out[f"{k}/normal_kl"] = GD.normal_kl(tm, tlv, pmv["mean"], pmv["log_variance"]).numpy()
+        out[f"{k}/disc_ll"] = GD.discretised_gaussian_log_likelihood(x0, pmv["mean"], log_scales=0.5 * pmv["log_variance"]).numpy()
+        out[f"{k}/prior_vlb"] = D.prior_vlb(x0, {"Batch_Size": 5}).numpy()
+    np.savez_compressed(os.path.join(HERE, "vlb.npz"), **out)
+    print("vlb.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["simplex", "diffusion", "unet", "loop"]
+    which = sys.argv[1:] or ["simplex", "diffusion", "unet", "loop", "vlb"]
     for w in which:
         globals()["gen_" + w]()

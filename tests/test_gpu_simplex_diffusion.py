@@ -174,3 +174,25 @@ def test_fused_detection_metrics_match_reference_formulas():
     c = E.detection_counts(torch.zeros(32, 1, 256, 256, device=DEV), torch.ones(32, 1, 256, 256, device=DEV),
                            torch.ones(32, 1, 256, 256, device=DEV))
     assert torch.equal(c[:, 0], torch.full((32,), 65536.0, device=DEV, dtype=torch.float64)) and float(c[:, 1:4].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("T,name", [(100, "linear"), (1000, "linear"), (1000, "cosine")])
+def test_vlb_term_fused_kernel_vs_reference_golden(golden, T, name):
+    """calc_vlb_xt (GaussianDiffusion.py:384-397): fused KL / decoder-NLL kernel under no_grad, torch formulas with autograd."""
+    from anoddpm_b200 import GaussianDiffusionModel, get_beta_schedule
+    g = golden("vlb")
+    k = f"{name}{T}/"
+    D = GaussianDiffusionModel([24, 40], get_beta_schedule(T, name))
+    x0, x_t, eps, t = (torch.from_numpy(g[k + n]).to(DEV) for n in ("x0", "x_t", "eps", "t"))
+    ref = torch.from_numpy(g[k + "vlb"])
+    with torch.no_grad():
+        r = D.calc_vlb_xt(None, x0, x_t, t, eps)
+    assert r["output"].dtype == torch.float32 and r["output"].shape == (5,)
+    assert torch.allclose(r["output"].cpu(), ref, rtol=2e-5, atol=1e-6), (r["output"].cpu() - ref).abs().max()
+    assert np.array_equal(r["pred_x_0"].cpu().numpy(), g[k + "pred_x_0"])            # same mul / sub / clamp, no contraction
+    e2 = eps.clone().requires_grad_(True)                                             # hybrid-loss path: gradient w.r.t. the estimate
+    r2 = D.calc_vlb_xt(None, x0, x_t, t, e2)
+    assert torch.allclose(r2["output"].detach().cpu(), ref, rtol=2e-5, atol=1e-6)
+    r2["output"].sum().backward()
+    assert bool(torch.isfinite(e2.grad).all()) and float(e2.grad.abs().max()) > 0
+    assert torch.allclose(D.prior_vlb(x0, {"Batch_Size": 5}).cpu(), torch.from_numpy(g[k + "prior_vlb"]), rtol=1e-5, atol=1e-7)

@@ -29,6 +29,25 @@ def test_tables_and_steps_bit_exact(golden, T, name):
     assert np.array_equal(sp["pred_x_0"].numpy(), g[k + "sample_p_pred_x_0"])
 
 
+@pytest.mark.parametrize("T,name", [(100, "linear"), (1000, "linear"), (1000, "cosine")])
+def test_vlb_helpers_bit_exact(golden, T, name):
+    """normal_kl / discretised log-likelihood / calc_vlb_xt / prior_vlb of the oracle == the unmodified reference."""
+    g = golden("vlb")
+    tab = DO.Tables(DO.beta_schedule(T, name))
+    k = f"{name}{T}/"
+    x0, x_t, eps, t = (torch.from_numpy(g[k + n]) for n in ("x0", "x_t", "eps", "t"))
+    r = DO.vlb_xt(tab, x0, x_t, t, eps)
+    assert np.array_equal(r["output"].numpy(), g[k + "vlb"])
+    assert np.array_equal(r["pred_x_0"].numpy(), g[k + "pred_x_0"])
+    pmv = DO.p_mean_variance(tab, x_t, t, eps)
+    tm = DO.coef(tab.posterior_mean_coef1, t) * x0 + DO.coef(tab.posterior_mean_coef2, t) * x_t
+    tlv = DO.coef(tab.posterior_log_variance_clipped, t).expand(x_t.shape)
+    assert np.array_equal(DO.normal_kl(tm, tlv, pmv["mean"], pmv["log_variance"]).numpy(), g[k + "normal_kl"])
+    assert np.array_equal(DO.disc_ll(x0, pmv["mean"], 0.5 * pmv["log_variance"]).numpy(), g[k + "disc_ll"])
+    assert np.array_equal(DO.prior_vlb(tab, x0).numpy(), g[k + "prior_vlb"])
+    assert float((x0 > 0.999).float().mean()) > 0 and float((x0 < -0.999).float().mean()) > 0   # both open-ended bins hit
+
+
 def test_survey_table_sanity():
     tab = DO.Tables(DO.beta_schedule(100, "linear"))    # SURVEY App. B
     assert np.allclose(tab.sqrt_alphas_cumprod[:2], [0.99949987, 0.99799444], atol=1e-8)
