@@ -120,3 +120,52 @@ def test_ema_update():
     update_ema_params(a, b, 0.9)
     w0 = UNetModel(32, 32).out[0].weight      # GroupNorm weight = 1 at init
     assert torch.allclose(a.out[0].weight, 0.9 * w0 + 0.1 * (w0 + 1))
+
+
+def test_support_predicates_and_argument_checks_without_gpu():
+    """Host-side contract of the tensor-core entry points: the predicates the engine plans with, workspace sizes, and the
+    loud argument errors -- all decided before any CUDA call, so they run on the build container."""
+    import ctypes
+    from anoddpm_b200 import _lib
+    L = _lib.lib()
+
+    def desc(**kw):
+        d = _lib.ConvDesc()
+        d.B, d.H, d.W, d.Ca, d.Cr1, d.Cr2, d.Cout, d.ksize = 1, 256, 256, 128, 0, 0, 128, 3
+        for k, v in kw.items():
+            setattr(d, k, v)
+        return d
+
+    ok3 = lambda **kw: L.anoddpm_conv_tc3_supported(ctypes.byref(desc(**kw)))     # noqa: E731
+    assert ok3() == 1 and ok3(operand_f16=1) == 1 and ok3(Ca=256, Cr1=128, Cr2=128) == 1
+    assert ok3(H=8, W=8) == 0 and ok3(H=24, W=32) == 0            # 16x16 regions
+    assert ok3(ksize=1) == 0                                      # 1x1 convs run on impl 2
+    assert ok3(Ca=96, operand_f16=1) == 0 and ok3(Ca=96) == 1     # fp16 K-blocks are 64 channels, fp32 ones 32
+    assert ok3(Cout=48) == 0 and ok3(Cout=160) == 0 and ok3(Cout=512) == 1
+    res = ctypes.c_void_p(256)
+    assert ok3(res=res, res_mode=1) == 1 and ok3(res=res, res_mode=3) == 1 and ok3(res=res, res_mode=2) == 0
+    assert ok3(out_f16=1) == 1 and ok3(out_f16=1, res=res, res_mode=1) == 0
+    ok2 = lambda **kw: L.anoddpm_conv_tc_supported(ctypes.byref(desc(**kw)))      # noqa: E731
+    assert ok2(H=8, W=8, Ca=512, Cout=512) == 1 and ok2(ksize=1, H=16, W=16, Ca=512, Cout=1536) == 1
+    assert ok2(Ca=20) == 0 and ok2(W=24, H=24) == 0
+
+    assert L.anoddpm_attention_tc_supported(256, 512, 2) == 1 and L.anoddpm_attention_tc_supported(64, 512, 2) == 1
+    assert L.anoddpm_attention_tc_supported(64, 512, 8) == 1            # head size 64 (num_head_channels=64)
+    assert L.anoddpm_attention_tc_supported(1024, 256, 2) == 0          # T > 256: CUDA-core kernel
+    assert L.anoddpm_attention_tc_supported(256, 512, 1) == 0           # head size 512: CUDA-core kernel
+    assert L.anoddpm_attention_tc_supported(256, 500, 3) == 0
+    assert L.anoddpm_attention_tc_workspace_bytes(32, 256, 512) == 3 * 32 * 256 * 512 * 2
+
+    # argument errors carry a message and never reach the device
+    d = desc(impl=3, res=res, res_mode=2)
+    d.out, d.a, d.w = 256, 256, 256
+    assert L.anoddpm_conv(ctypes.byref(d), None) < 0 and b"res_mode" in L.anoddpm_last_error()
+    d = desc(impl=1, out_f16=1)
+    d.out, d.a, d.w = 256, 256, 256
+    assert L.anoddpm_conv(ctypes.byref(d), None) < 0 and b"fp16 output" in L.anoddpm_last_error()
+    assert L.anoddpm_attention_tc(res, res, res, 1, 1024, 256, 2, 0, None) < 0 and b"not supported" in L.anoddpm_last_error()
+    assert L.anoddpm_gn_apply_f16in(res, res, 100, res, res, res, None, None, 0, 1, 8, 8, 32, 1e-5, 1, 2, None) < 0
+    assert L.anoddpm_linear(res, 8, res, 8, res, None, 1, 8, 8, 7, None) < 0
+    assert L.anoddpm_vlb_terms(None, None, None, None, None, None, None, None, 10, 1, 16, None) < 0
+    assert L.anoddpm_conv_head_gn(res, res, res, res, res, res, None, 1, 1024, 8, 8, 1, 32, 1e-5, None) < 0
+    assert b"at most" in L.anoddpm_last_error()
