@@ -211,8 +211,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int S = P.stages;
     uint8_t* sA = smem;                            // [S][2 subtiles][kSubBytes]
     uint8_t* sB = smem + S * kABytes;              // [S][3 taps][b_bytes]
-    uint8_t* stg_all = sB + S * 3 * b_bytes;       // [4 warps][2][kStgBuf], 1024-byte aligned (ring sizes are multiples)
-    float* be_all = reinterpret_cast<float*>(stg_all + kStgBytes);   // [4 warps][128]
+    uint8_t* stg_all = sB + S * 3 * b_bytes;       // [8 warps][2][kStgBuf], 1024-byte aligned (ring sizes are multiples)
+    float* be_all = reinterpret_cast<float*>(stg_all + kStgBytes);   // [8 warps][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + kStgBytes + kBeBytes);
     uint64_t* full = bars;                         // [S]   leader only
     uint64_t* empty = bars + kMaxStages;           // [S]   both CTAs (multicast commit)
