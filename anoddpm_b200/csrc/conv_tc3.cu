@@ -10,6 +10,11 @@
 //   * CTA pairs (tcgen05.mma.cta_group::2, UMMA M = 256) split the weight tile in halves, persistent clusters,
 //     3-stage smem ring (60 KB/stage), 2 TMEM accumulator stages x 2 subtiles x BN columns (512 columns).
 // 1x1 "skip" sources (raw ResBlock input, centre tap only) are extra stages with a (32, 8, 16) box.
+// Single-box main loop (default when there are no skip sources): tcgen05.mma swizzles on absolute shared-memory address
+// bits (profiles/r01_umma_desc_probe.md), so ONE (K-block, 18 px, 18 rows) box per channel chunk serves all nine taps of
+// both subtiles -- tap (dy, dx) of subtile s is the descriptor that starts at row 18 dy + 8 s + dx with 8-row groups
+// 18 rows (2304 B) apart.  Two A buffers (41.5 KB each) + a 4-stage ring of (chunk, dy) weight stages; A-operand
+// L2->SM traffic and TMA writes drop by 62 % against the box-per-(subtile, dx) loop.
 // Epilogue (8 warps: TMEM lane quarter x subtile; two per scheduler -- the work is a chain of short-latency steps), in
 // steps of (32 pixels x 16 channels) per warp through two 2 KB shared-memory buffers in the TMA SWIZZLE_64B layout:
 // the residual box of step s+2 is TMA-loaded into the buffer once the store of step s has read it, the
@@ -25,6 +30,7 @@
 #include "anoddpm_b200.h"
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -35,6 +41,8 @@ constexpr int kThreads = 384;       // warps 0-3: TMA producer, MMA issuer, TMEM
 constexpr int kSubRows = 18;                        // 16 output rows + 1 halo row above and below
 constexpr int kSubBytes = kSubRows * 8 * kRowBytes;   // one (32 ch, 8 px, 18 rows) box = 18432 B
 constexpr int kABytes = 2 * kSubBytes;              // two subtiles per CTA
+constexpr int kBoxBytes = 18 * 18 * kRowBytes;      // single-box main loop: one (K-block, 18 px, 18 rows) box = both subtiles + halo
+constexpr int kBoxStride = 41 * 1024;               // 1024-byte aligned buffer stride (41,472 B used)
 constexpr int kAccStages = 2;
 constexpr int kMaxStages = 4;
 constexpr int kEpiWarps = 8;
@@ -60,6 +68,7 @@ struct Tc3Args {
     double* gn_stats;          // optional [REPLICAS][B][Cout][2]: per-channel (sum, sum of squares) of the output
     long long stat_replica_stride;   // B*Cout*2
     int tile_order;
+    int single_box;            // main loop variant: ONE (K-block, 18 px, 18 rows) A box per chunk, nine taps by descriptor offsets
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -198,6 +207,11 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
 __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// the same with an explicit stride between 8-row groups.  The MMA swizzles on absolute shared-memory address bits
+// (profiles/r01_umma_desc_probe.md): any 128-byte start row and any group stride address the rows TMA wrote there.
+__device__ __forceinline__ uint64_t make_sdesc_sbo(uint32_t saddr, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
 
 template <bool F16, bool OUT16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -209,8 +223,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_bytes = (P.BN / 2) * kRowBytes;      // one weight tile (this CTA's half of the N rows)
     const int S = P.stages;
-    uint8_t* sA = smem;                            // [S][2 subtiles][kSubBytes]
-    uint8_t* sB = smem + S * kABytes;              // [S][3 taps][b_bytes]
+    // multi-box: [S][2 subtiles][kSubBytes] then [S][3 taps][b_bytes]; single-box: [2][kBoxStride] then [S][3 taps][b_bytes]
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (P.single_box ? 2 * kBoxStride : S * kABytes);
     uint8_t* stg_all = sB + S * 3 * b_bytes;       // [8 warps][2][kStgBuf], 1024-byte aligned (ring sizes are multiples)
     float* be_all = reinterpret_cast<float*>(stg_all + kStgBytes);   // [8 warps][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + kStgBytes + kBeBytes);
@@ -219,7 +234,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]   both CTAs (multicast commit)
     uint64_t* tmem_empty = tmem_full + kAccStages; // [2]   leader only, 2 x 256 arrivals
     uint64_t* res_bar = tmem_empty + kAccStages;   // [8 warps][2] residual box landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 2 * kEpiWarps);
+    uint64_t* a_full = res_bar + 2 * kEpiWarps;    // [2]   single-box main loop: A box landed (leader only)
+    uint64_t* a_empty = a_full + 2;                // [2]   both CTAs (multicast commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
@@ -248,6 +265,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int i = 0; i < S; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
         for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * 32 * kEpiWarps); }
         for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -263,7 +281,54 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 
     if (warp == 0) {
         // ---------------- TMA producer (both CTAs) ----------------
-        if (elect_one()) {
+        const bool elected = elect_one();
+        if (elected && P.single_box) {
+            // one (K-block, 18 px, 18 rows) box per chunk (2 buffers) + a ring of (chunk, dy) weight stages
+            int bc = 0, ac = 0;
+            for (int tile = tile_first; tile < tile_end; tile += tile_step) {
+                const int pair = tile / P.n_tiles_n, nt = tile - pair * P.n_tiles_n;
+                const int R = pair * 2 + (int)rank;
+                const int b0 = R / P.regions_per_img, rr = R - b0 * P.regions_per_img;
+                const int y0 = (rr / P.regions_x) * 16, x0 = (rr % P.regions_x) * 16;
+                const int n0 = nt * P.BN + (int)rank * (P.BN / 2);
+                const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
+                for (int c = 0; c < nchunks; ++c, ++ac) {
+                    const int ab = ac & 1;
+                    uint8_t* a_dst = sA + ab * kBoxStride;
+                    mbar_wait(&a_empty[ab], ((ac >> 1) & 1) ^ 1);
+                    if (c < P.chunks_a) {
+                        if (leader) mbar_expect_tx(&a_full[ab], 2u * (uint32_t)kBoxBytes);
+                        else mbar_arrive_remote(&a_full[ab], 0);
+                        tma2_load_4d(a_dst, &map_a, &a_full[ab], c * P.ke, x0 - 1, y0 - 1, b0);
+                        for (int dy = 0; dy < 3; ++dy, ++bc) {
+                            const int s = bc % S;
+                            mbar_wait(&empty[s], ((bc / S) & 1) ^ 1);
+                            uint8_t* b_dst = sB + s * 3 * b_bytes;
+                            if (leader) mbar_expect_tx(&full[s], 2u * 3u * (uint32_t)b_bytes);
+                            else mbar_arrive_remote(&full[s], 0);
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx)
+                                tma2_load_2d(b_dst + dx * b_bytes, &map_w, &full[s], (dy * 3 + dx) * P.Ca + c * P.ke, n0);
+                        }
+                    } else {
+                        const int cs = c - P.chunks_a;
+                        const bool first = cs < P.chunks_r1;
+                        const CUtensorMap* am = first ? &map_r1 : &map_r2;
+                        const int c0 = (first ? cs : cs - P.chunks_r1) * P.ke;
+                        if (leader) mbar_expect_tx(&a_full[ab], 2u * 2u * (16 * 8 * kRowBytes));
+                        else mbar_arrive_remote(&a_full[ab], 0);
+                        tma2_load_4d(a_dst, am, &a_full[ab], c0, x0, y0, b0);
+                        tma2_load_4d(a_dst + 16 * 8 * kRowBytes, am, &a_full[ab], c0, x0 + 8, y0, b0);
+                        const int s = bc % S;
+                        mbar_wait(&empty[s], ((bc / S) & 1) ^ 1);
+                        if (leader) mbar_expect_tx(&full[s], 2u * (uint32_t)b_bytes);
+                        else mbar_arrive_remote(&full[s], 0);
+                        tma2_load_2d(sB + s * 3 * b_bytes, &map_w, &full[s], 9 * P.Ca + cs * P.ke, n0);
+                        ++bc;
+                    }
+                }
+            }
+        } else if (elected) {
             int kbc = 0;
             for (int tile = tile_first; tile < tile_end; tile += tile_step) {
                 const int pair = tile / P.n_tiles_n, nt = tile - pair * P.n_tiles_n;
@@ -308,6 +373,60 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.BN >> 3) << 17) |
                                    ((uint32_t)(256 >> 4) << 24);
             int kbc = 0, it = 0;
+            if (P.single_box) {
+                int bc = 0, ac = 0;
+                const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
+                for (int tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
+                    const int acc = it & 1;
+                    mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t tmem_d0 = tmem_base + (uint32_t)((acc * 2 + 0) * P.BN);
+                    const uint32_t tmem_d1 = tmem_base + (uint32_t)((acc * 2 + 1) * P.BN);
+                    for (int c = 0; c < nchunks; ++c, ++ac) {
+                        const int ab = ac & 1;
+                        mbar_wait(&a_full[ab], (ac >> 1) & 1);
+                        const uint32_t a_base = smem_u32(sA + ab * kBoxStride);
+                        const bool main_src = c < P.chunks_a;
+                        const int ndy = main_src ? 3 : 1;
+                        for (int dy = 0; dy < ndy; ++dy, ++bc) {
+                            const int s = bc % S;
+                            mbar_wait(&full[s], (bc / S) & 1);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            if (elect_one()) {
+                                const uint32_t b_addr = smem_u32(sB + s * 3 * b_bytes);
+                                if (main_src) {
+                                    // tap (dy, dx) of subtile sub = rows 18 dy + 8 sub + dx .. of the box, 8-row groups 18 rows apart
+                                    for (int dx = 0; dx < 3; ++dx) {
+                                        const uint64_t bd = make_sdesc(b_addr + dx * b_bytes);
+                                        const uint64_t ad0 = make_sdesc_sbo(a_base + (uint32_t)(18 * dy + dx) * kRowBytes, 18 * kRowBytes);
+                                        const uint64_t ad1 = make_sdesc_sbo(a_base + (uint32_t)(18 * dy + 8 + dx) * kRowBytes, 18 * kRowBytes);
+#pragma unroll
+                                        for (int k = 0; k < kKSteps; ++k) {
+                                            const uint32_t accum = (c | dy | dx | k) ? 1u : 0u;
+                                            umma2<F16>(tmem_d0, ad0 + 2 * k, bd + 2 * k, idesc, accum);
+                                            umma2<F16>(tmem_d1, ad1 + 2 * k, bd + 2 * k, idesc, accum);
+                                        }
+                                    }
+                                } else {
+                                    const uint64_t bd = make_sdesc(b_addr);
+                                    const uint64_t ad0 = make_sdesc(a_base), ad1 = make_sdesc(a_base + 16 * 8 * kRowBytes);
+#pragma unroll
+                                    for (int k = 0; k < kKSteps; ++k) {
+                                        umma2<F16>(tmem_d0, ad0 + 2 * k, bd + 2 * k, idesc, 1u);
+                                        umma2<F16>(tmem_d1, ad1 + 2 * k, bd + 2 * k, idesc, 1u);
+                                    }
+                                }
+                                umma2_commit(&empty[s]);
+                                if (dy == ndy - 1) {
+                                    umma2_commit(&a_empty[ab]);
+                                    if (c == nchunks - 1) umma2_commit(&tmem_full[acc]);
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+            } else
             for (int tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
                 const int acc = it & 1;
                 mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
@@ -666,13 +785,13 @@ EncodeTiledFn get_encode3() {
 }
 
 // NHWC activation map: dims (C, W, H, B), box (32 ch, 8 px, rows, 1)
-int make_act_map3(CUtensorMap* m, const void* p, int f16, int C, int W, int H, int B, int rows) {
+int make_act_map3(CUtensorMap* m, const void* p, int f16, int C, int W, int H, int B, int rows, int px = 8) {
     EncodeTiledFn enc = get_encode3();
     if (!enc) { anoddpm_set_error("cuTensorMapEncodeTiled entry point not available"); return ANODDPM_ERR_CUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t es = f16 ? 2 : 4;
     cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)W * C * es, (cuuint64_t)H * W * C * es};
-    cuuint32_t box[4] = {(cuuint32_t)(f16 ? 64 : 32), 8u, (cuuint32_t)rows, 1u};
+    cuuint32_t box[4] = {(cuuint32_t)(f16 ? 64 : 32), (cuuint32_t)px, (cuuint32_t)rows, 1u};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(p), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -758,7 +877,10 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     P.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
     const int Ktot = 9 * d->Ca + d->Cr1 + d->Cr2;
     const int b_bytes = (P.BN / 2) * kRowBytes;
-    int stages = (186 * 1024) / (kABytes + 3 * b_bytes);
+    // single-box main loop unless the conv has fused 1x1 skip sources (their small chunks would each hold one of only two
+    // A buffers for 8 MMAs: measured 4 % slower there, 4-5 % faster everywhere else); ANODDPM_TC3_SINGLEBOX=0/1 forces
+    { const char* e = getenv("ANODDPM_TC3_SINGLEBOX"); P.single_box = e ? atoi(e) : ((d->Cr1 + d->Cr2) == 0 ? 1 : 0); }
+    int stages = P.single_box ? (186 * 1024 - 2 * kBoxStride) / (3 * b_bytes) : (186 * 1024) / (kABytes + 3 * b_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     P.stages = stages;
     P.n_tiles_n = adp_ceil_div(d->Cout, P.BN);
@@ -772,7 +894,7 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
 
     CUtensorMap ma, m1, m2, mw;
     int rc;
-    if ((rc = make_act_map3(&ma, d->a, f16, d->Ca, d->W, d->H, d->B, kSubRows))) return rc;
+    if ((rc = make_act_map3(&ma, d->a, f16, d->Ca, d->W, d->H, d->B, kSubRows, P.single_box ? 18 : 8))) return rc;
     m1 = ma; m2 = ma;
     if (d->r1 && (rc = make_act_map3(&m1, d->r1, f16, d->Cr1, d->W, d->H, d->B, 16))) return rc;
     if (d->r2 && (rc = make_act_map3(&m2, d->r2, f16, d->Cr2, d->W, d->H, d->B, 16))) return rc;
@@ -787,7 +909,8 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
         if (rc) return rc;
     }
 
-    const size_t smem = (size_t)stages * (kABytes + 3 * b_bytes) + kStgBytes + kBeBytes + 256 + 1024;
+    const size_t ring = P.single_box ? (size_t)2 * kBoxStride + (size_t)stages * 3 * b_bytes : (size_t)stages * (kABytes + 3 * b_bytes);
+    const size_t smem = ring + kStgBytes + kBeBytes + 512 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
