@@ -252,8 +252,8 @@ def _time_ms(fn, n=10, warm=3):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel/shape (conv 128->128 @256^2 bs 32,
-# fp16 operands, fp32 output) from the committed `ncu --set full` capture profiles/r01e_ncu_conv_tc3.md
-NCU_TRAFFIC_DOMINANT = {"bytes": 0.600476e9 + 1.023989e9, "source": "profiles/r01e_ncu_conv_tc3.md"}
+# fp16 operands, fp32 output) from the committed `ncu --set full` capture profiles/r01g_ncu_conv_tc3_singlebox.md
+NCU_TRAFFIC_DOMINANT = {"bytes": 0.600577e9 + 1.022959e9, "source": "profiles/r01g_ncu_conv_tc3_singlebox.md"}
 
 
 def roofline(model, dev, B):
@@ -289,7 +289,7 @@ def roofline(model, dev, B):
         tot_ms += ms * count
         del a, w, out
     dom = res[0]
-    kname = {3: "conv_tc3_kernel (tcgen05.mma.cta_group::2 kind::%s, halo-reuse persistent CTA pairs, TMA-fed implicit GEMM, TMA-store epilogue)" % ("f16" if f16 else "tf32"),
+    kname = {3: "conv_tc3_kernel (tcgen05.mma.cta_group::2 kind::%s, single-box halo-reuse main loop, persistent CTA pairs, TMA-fed implicit GEMM, TMA-store epilogue)" % ("f16" if f16 else "tf32"),
              2: "conv_tc2_kernel (tcgen05.mma.cta_group::2, persistent CTA pairs)", 1: "conv_tc_kernel (tcgen05.mma kind::tf32)",
              0: "conv_simt_kernel"}[impl]
     peak = pk["bf16_burst"]      # the kernel is timed alone here -> burst figure (B200_PROFILING.md)
