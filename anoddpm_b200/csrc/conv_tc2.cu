@@ -298,56 +298,63 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const int q0 = m0 + quarter * 32;
                 const bool wvalid = q0 < P.M;
                 const int bw = wvalid ? q0 / (P.W * P.H) : 0;
+                float sv[64];     // [0, 32): final values of this row's 32 channels, [32, 64): their squares (0 for invalid rows)
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     const int n = nb + j;
-                    if (n >= P.Cout) break;
                     float v[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (valid) {
+                    if (valid && n < P.Cout) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        v[e] = __uint_as_float(r[j + e]);
-                        if (P.bias) v[e] += P.bias[n + e];
-                        if (P.emb) v[e] += P.emb[(size_t)b * P.emb_stride + n + e];
-                    }
-                    if (P.res_mode == 1) {
-                        const float4 t = *reinterpret_cast<const float4*>(P.res + (size_t)q * P.Cout + n);
-                        v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
-                    } else if (P.res_mode == 2) {
-                        const int H2 = P.H * 2, W2 = P.W * 2;
-                        const float* rb = P.res + (((size_t)b * H2 + 2 * h) * W2 + 2 * w) * P.Cout + n;
-                        const float4 r0 = *reinterpret_cast<const float4*>(rb);
-                        const float4 r1 = *reinterpret_cast<const float4*>(rb + P.Cout);
-                        const float4 r2 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout);
-                        const float4 r3 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout + P.Cout);
-                        v[0] += (r0.x + r1.x + r2.x + r3.x) * 0.25f;
-                        v[1] += (r0.y + r1.y + r2.y + r3.y) * 0.25f;
-                        v[2] += (r0.z + r1.z + r2.z + r3.z) * 0.25f;
-                        v[3] += (r0.w + r1.w + r2.w + r3.w) * 0.25f;
-                    } else if (P.res_mode == 3) {
-                        const int Hh = P.H / 2, Wh = P.W / 2;
-                        const float4 t = *reinterpret_cast<const float4*>(
-                            P.res + (((size_t)b * Hh + (h >> 1)) * Wh + (w >> 1)) * P.Cout + n);
-                        v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
-                    }
-                    *reinterpret_cast<float4*>(P.out + (size_t)q * P.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
-                    }
-                    if (P.gn_stats) {   // warp-uniform
-                        float sv[8] = {v[0], v[1], v[2], v[3], v[0] * v[0], v[1] * v[1], v[2] * v[2], v[3] * v[3]};
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) sv[e] += __shfl_xor_sync(0xffffffffu, sv[e], o);
+                        for (int e = 0; e < 4; ++e) {
+                            v[e] = __uint_as_float(r[j + e]);
+                            if (P.bias) v[e] += P.bias[n + e];
+                            if (P.emb) v[e] += P.emb[(size_t)b * P.emb_stride + n + e];
                         }
-                        if (wvalid && lane < 8) {
-                            float mine = 0.f;
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) if (lane == e) mine = sv[e];
-                            // lane e < 4: sum of channel n + e; lane 4 + e: its sum of squares
-                            double* st = P.gn_stats + (size_t)(cluster_id % ANODDPM_STAT_REPLICAS) * P.stat_replica_stride +
-                                         ((size_t)bw * P.Cout + n + (lane & 3)) * 2 + (lane >> 2);
-                            atomicAdd(st, (double)mine);
+                        if (P.res_mode == 1) {
+                            const float4 t = *reinterpret_cast<const float4*>(P.res + (size_t)q * P.Cout + n);
+                            v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                        } else if (P.res_mode == 2) {
+                            const int H2 = P.H * 2, W2 = P.W * 2;
+                            const float* rb = P.res + (((size_t)b * H2 + 2 * h) * W2 + 2 * w) * P.Cout + n;
+                            const float4 r0 = *reinterpret_cast<const float4*>(rb);
+                            const float4 r1 = *reinterpret_cast<const float4*>(rb + P.Cout);
+                            const float4 r2 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout);
+                            const float4 r3 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout + P.Cout);
+                            v[0] += (r0.x + r1.x + r2.x + r3.x) * 0.25f;
+                            v[1] += (r0.y + r1.y + r2.y + r3.y) * 0.25f;
+                            v[2] += (r0.z + r1.z + r2.z + r3.z) * 0.25f;
+                            v[3] += (r0.w + r1.w + r2.w + r3.w) * 0.25f;
+                        } else if (P.res_mode == 3) {
+                            const int Hh = P.H / 2, Wh = P.W / 2;
+                            const float4 t = *reinterpret_cast<const float4*>(
+                                P.res + (((size_t)b * Hh + (h >> 1)) * Wh + (w >> 1)) * P.Cout + n);
+                            v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
                         }
+                        *reinterpret_cast<float4*>(P.out + (size_t)q * P.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { sv[j + e] = v[e]; sv[32 + j + e] = v[e] * v[e]; }
+                }
+                if (P.gn_stats) {   // warp-uniform
+                    // column sums over the warp's 32 rows by a reduce-scatter butterfly (62 shuffles for 64 values): each
+                    // step halves the values a lane keeps; lane L ends with entries 2L, 2L+1 (L < 16: sums of channels
+                    // 2L, 2L+1; L >= 16: their sums of squares)
+#pragma unroll
+                    for (int half = 32, o = 16; half >= 2; half >>= 1, o >>= 1) {
+                        const bool up = (lane & o) != 0;
+#pragma unroll
+                        for (int i = 0; i < half; ++i) {
+                            const float send = up ? sv[i] : sv[i + half];
+                            const float keep = up ? sv[i + half] : sv[i];
+                            sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                        }
+                    }
+                    const int ch = nb + 2 * (lane & 15);
+                    if (wvalid && ch < P.Cout) {
+                        double* st = P.gn_stats + (size_t)(cluster_id % ANODDPM_STAT_REPLICAS) * P.stat_replica_stride +
+                                     ((size_t)bw * P.Cout + ch) * 2 + (lane >> 4);
+                        atomicAdd(st, (double)sv[0]);
+                        atomicAdd(st + 2, (double)sv[1]);
                     }
                 }
             }
