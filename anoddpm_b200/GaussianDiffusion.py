@@ -366,6 +366,9 @@ class GaussianDiffusionModel:
         a capturable noise source the step (UNet forward + noise + fused posterior + t -= 1) is captured ONCE as a CUDA
         graph and replayed: no per-step host work (simplex seed tables of all steps are built and uploaded up front,
         consuming the host RNG in the same order as the step-by-step loop)."""
+        if not (0 <= int(t_start) < self.num_timesteps) or int(n_steps) > int(t_start) + 1:
+            raise IndexError(f"reverse_steps: t runs from {int(t_start)} down to {int(t_start) - int(n_steps) + 1}, outside "
+                             f"[0, {self.num_timesteps}) (the reference raises IndexError in extract())")
         mode = self._graph_mode(model, x, denoise_fn)
         if mode is None or n_steps <= 2:
             for t in range(int(t_start), int(t_start) - int(n_steps), -1):

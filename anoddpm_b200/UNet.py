@@ -281,6 +281,10 @@ class UNetModel(nn.Module):
             if not x.is_cuda:
                 raise RuntimeError("anoddpm_b200.UNetModel runs on sm_100a only: move the model and inputs to a CUDA "
                                    "device (no CPU fallback)")
+            if self.training and self.dropout > 0:
+                raise NotImplementedError(
+                    "UNetModel(dropout>0) in train() mode: the reference applies dropout here (UNet.py:190-193) and the "
+                    "native inference engine does not -- call .eval() for sampling")
             return self.engine().forward(x, time)
         if not UNetModel.allow_autograd_fallback:
             raise NotImplementedError(
@@ -303,10 +307,14 @@ class UNetModel(nn.Module):
 
 
 def update_ema_params(target, source, decay_rate=0.9999):
-    """p_target <- decay*p_target + (1-decay)*p_source over named parameters (UNet.py:423-427)."""
+    """p_target <- decay*p_target + (1-decay)*p_source over named parameters (UNet.py:423-427).  In-place on the
+    parameters themselves (bumps their version counters) and the target's packed-weight caches are invalidated."""
     tgt = dict(target.named_parameters())
     src = dict(source.named_parameters())
     with torch.no_grad():
         keys = list(tgt)
-        torch._foreach_mul_([tgt[k].data for k in keys], decay_rate)
-        torch._foreach_add_([tgt[k].data for k in keys], [src[k].data for k in keys], alpha=1 - decay_rate)
+        torch._foreach_mul_([tgt[k] for k in keys], decay_rate)
+        torch._foreach_add_([tgt[k] for k in keys], [src[k].detach() for k in keys], alpha=1 - decay_rate)
+    eng = getattr(target, "_engine", None)
+    if eng is not None:
+        eng.invalidate()

@@ -396,10 +396,12 @@ extern "C" int anoddpm_attention_tc(void* out, const float* qkv, void* workspace
     AttnArgs P;
     P.out = out; P.T = T; P.C = C; P.ch = ch; P.heads = heads; P.out_mode = out_mode;
     const size_t smem = (size_t)kStages * kStageBytes + 4 * kQBytes + 256 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        ADP_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+    static bool attr_dev[64] = {};   // the attribute is per device
+    int dev_ = 0;
+    ADP_CUDA(cudaGetDevice(&dev_));
+    if (!attr_dev[dev_ & 63]) {
+        ADP_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_dev[dev_ & 63] = true;
     }
     attention_tc_kernel<<<dim3((T + 127) / 128, BH), kThreads, smem, st>>>(mq, mk, mv, P);
     ADP_LAUNCH_CHECK();

@@ -359,10 +359,12 @@ int anoddpm_conv_tc(const anoddpm_conv_desc* d, void* stream) {
     if ((rc = make_w_map(&mw, static_cast<const float*>(d->w), Ktot, d->Cout, P.BN))) return rc;
 
     const size_t smem = (size_t)kStages * (kABytes + P.BN * kBK * 4) + (2 * kStages + 1) * 8 + 16 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_dev[64] = {};   // the attribute is per device
+    int dev_ = 0;
+    ADP_CUDA(cudaGetDevice(&dev_));
+    if (!attr_dev[dev_ & 63]) {
         ADP_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        attr_set = true;
+        attr_dev[dev_ & 63] = true;
     }
     dim3 grid(adp_ceil_div(P.M, kBM), adp_ceil_div(d->Cout, P.BN));
     conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, P);

@@ -468,11 +468,13 @@ int anoddpm_conv_tc2(const anoddpm_conv_desc* d, void* stream) {
     if ((rc = make_w_map2(&mw, d->w, f16, Ktot, d->Cout, P.BN / 2))) return rc;
 
     const size_t smem = (size_t)stages * (kABytes + b_bytes) + (2 * kMaxStages + 2 * kAccStages) * 8 + 16 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_dev[64] = {};   // the attribute is per device
+    int dev_ = 0;
+    ADP_CUDA(cudaGetDevice(&dev_));
+    if (!attr_dev[dev_ & 63]) {
         ADP_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ADP_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+        attr_dev[dev_ & 63] = true;
     }
     int sms = 148;
     int n_clusters = P.n_tiles < sms / 2 ? P.n_tiles : sms / 2;

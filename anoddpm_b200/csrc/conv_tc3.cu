@@ -911,13 +911,15 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
 
     const size_t ring = P.single_box ? (size_t)2 * kBoxStride + (size_t)stages * 3 * b_bytes : (size_t)stages * (kABytes + 3 * b_bytes);
     const size_t smem = ring + kStgBytes + kBeBytes + 512 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_dev[64] = {};   // the attribute is per device
+    int dev_ = 0;
+    ADP_CUDA(cudaGetDevice(&dev_));
+    if (!attr_dev[dev_ & 63]) {
         ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
+        attr_dev[dev_ & 63] = true;
     }
     const int sms = 148;
     const int n_clusters = P.n_tiles < sms / 2 ? P.n_tiles : sms / 2;

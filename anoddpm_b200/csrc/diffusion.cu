@@ -65,8 +65,11 @@ __global__ void __launch_bounds__(256) p_sample_kernel(float* __restrict__ sampl
                                                        const float* __restrict__ noise, const long long* __restrict__ t,
                                                        const float* __restrict__ tab, int T, long long per_sample) {
     const int b = blockIdx.y;
-    const long long tb = t[b];
-    const float ra = tab[tb], rm1 = tab[T + tb], c1 = tab[2 * T + tb], c2 = tab[3 * T + tb], sg = tab[4 * T + tb];
+    long long tb = t[b];
+    const bool t_bad = tb < 0 || tb >= T;     // out-of-range timestep (the reference raises IndexError in extract()):
+    if (t_bad) tb = 0;                        // no out-of-bounds read, the sample is poisoned with NaN instead
+    const float poison = t_bad ? __int_as_float(0x7fc00000) : 0.0f;
+    const float ra = tab[tb] + poison, rm1 = tab[T + tb], c1 = tab[2 * T + tb], c2 = tab[3 * T + tb] + poison, sg = tab[4 * T + tb];
     const size_t base = (size_t)b * per_sample;
     if (VEC) {
         const long long n4 = per_sample >> 2;
@@ -206,8 +209,11 @@ __global__ void __launch_bounds__(256) vlb_terms_kernel(double* __restrict__ acc
                                                         const float* __restrict__ tab, const float* __restrict__ logvars,
                                                         int T, long long per_sample) {
     const int b = blockIdx.y;
-    const long long tb = t[b];
-    const float ra = tab[tb], rm1 = tab[T + tb], c1 = tab[2 * T + tb], c2 = tab[3 * T + tb];
+    long long tb = t[b];
+    const bool t_bad = tb < 0 || tb >= T;     // see p_sample_kernel
+    if (t_bad) tb = 0;
+    const float poison = t_bad ? __int_as_float(0x7fc00000) : 0.0f;
+    const float ra = tab[tb] + poison, rm1 = tab[T + tb], c1 = tab[2 * T + tb], c2 = tab[3 * T + tb] + poison;
     const float lv1 = logvars[tb], lv2 = logvars[T + tb];     // true posterior / model log-variance
     const float e12 = expf(lv1 - lv2), em2 = expf(-lv2), inv_std = expf(-(0.5f * lv2));
     const size_t base = (size_t)b * per_sample;

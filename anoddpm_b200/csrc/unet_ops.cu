@@ -1024,12 +1024,14 @@ extern "C" int anoddpm_attention(void* out_v, const float* qkv, int B, int T, in
                       (long long)adp_ceil_div(T, qb) * heads * B < 2 * 148)) qb >>= 1;
     const size_t smem = (size_t)qb * (ch + T) * sizeof(float);
     ADP_REQUIRE(smem <= 200 * 1024, "anoddpm_attention: T=%d ch=%d needs %zu B of shared memory", T, ch, smem);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_dev[64] = {};   // the attribute is per device
+    int dev_ = 0;
+    ADP_CUDA(cudaGetDevice(&dev_));
+    if (!attr_dev[dev_ & 63]) {
         ADP_CUDA(cudaFuncSetAttribute(attention_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         ADP_CUDA(cudaFuncSetAttribute(attention_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         ADP_CUDA(cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        attr_dev[dev_ & 63] = true;
     }
     dim3 grid(adp_ceil_div(T, qb), heads, B);
     cudaStream_t st = (cudaStream_t)stream;

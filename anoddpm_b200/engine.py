@@ -81,11 +81,19 @@ class UNetEngine:
     def __init__(self, model):
         self.model = model
         self._sig = None
+        self._gen = 0               # bumped by invalidate(): raw-pointer / .data writes do not bump p._version
         self.launches = 0           # native kernel launches issued (for bench.py's gpu_launches)
 
     # ------------------------------------------------------------------ packing
+    def invalidate(self):
+        """Forget every derived weight copy (packed / rounded conv weights, concatenated embedding projections, head
+        weights) and every CUDA graph keyed on them.  Called by the update paths that write parameters behind autograd's
+        back (update_ema_params' .data writes, FusedAdamWEMA.step's raw-pointer kernels), which leave p._version
+        unchanged."""
+        self._gen += 1
+
     def _signature(self):
-        return tuple((p.data_ptr(), p._version, p.device) for p in self.model.parameters())
+        return (self._gen,) + tuple((p.data_ptr(), p._version, p.device) for p in self.model.parameters())
 
     def _build(self):
         from .UNet import AttentionBlock, ResBlock
@@ -354,8 +362,12 @@ class UNetEngine:
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
     def forward(self, x, t):
-        m = self.model
         _lib.require_cuda(x, "UNetModel input")
+        with torch.cuda.device(x.device):       # kernels launch on the tensors' device, whichever device is current
+            return self._forward(x, t)
+
+    def _forward(self, x, t):
+        m = self.model
         p0 = next(m.parameters())
         if p0.device != x.device:
             raise RuntimeError(f"UNetModel parameters are on {p0.device} but the input is on {x.device}")
