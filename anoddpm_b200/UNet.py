@@ -255,6 +255,9 @@ class UNetModel(nn.Module):
         # "tc_tf32" (same kernels, TF32 operands only) | "tc2" (persistent CTA pairs, TF32) | "tc1" (single-CTA tiles, TF32) |
         # "exact" (fp32 CUDA cores)
         self.conv_impl = os.environ.get("ANODDPM_CONV_IMPL", "tc")
+        # "tc" only: convolutions with fewer input channels than this run on the exact fp32 kernel (short K: the operand
+        # rounding of the tensor-core path is not averaged enough to stay under 1e-3 on the base-32 models)
+        self.tc_min_channels = int(os.environ.get("ANODDPM_TC_MIN_CHANNELS", "128"))
         # "tc" only: the first conv of a ResBlock (read by GroupNorm 2 alone) stores fp16 sums without their per-channel
         # bias + embedding offset, which the GroupNorm pass adds back in fp32 (halves that tensor's HBM traffic)
         self.h1_fp16 = os.environ.get("ANODDPM_H1_FP16", "1") != "0"

@@ -225,7 +225,88 @@ def gen_vlb():
     print("vlb.npz", len(out), "arrays")
 
 
+def gen_loss():
+    """Training-loss path (GaussianDiffusion.py:140-147, 220-226, 399-478): calc_loss / p_loss for every loss type and
+    weighting, random_noise's branch sequence, simplex_randParam's RNG consumption, calc_total_vlb.  Every random draw
+    is pinned (explicit t, replayed noise, seeded host RNGs) so the GPU run can consume identical numbers."""
+    import random
+    out = {}
+    kw = dict(img_size=32, base_channels=32, n_heads=2)
+    torch.manual_seed(0)
+    m = UNet.UNetModel(**kw).eval()
+    m.load_state_dict(fill_state_dict(m.state_dict(), seed=1))
+    g = torch.Generator().manual_seed(21)
+    x0 = torch.rand(3, 1, 32, 32, generator=g) * 2 - 1
+    noise = torch.randn(3, 1, 32, 32, generator=g)
+    t = torch.tensor([0, 5, 99])
+    out["x0"], out["noise"], out["t"] = x0.numpy(), noise.numpy(), t.numpy()
+    for lt in ("l1", "l2", "hybrid", "other"):
+        D = GD.GaussianDiffusionModel([32, 32], GD.get_beta_schedule(100, "linear"), loss_type=lt, noise="gauss")
+        D.noise_fn = lambda x, tt: noise
+        with torch.no_grad():
+            loss, x_t, eps = D.calc_loss(m, x0, t)
+        for k, v in loss.items():
+            out[f"calc_loss/{lt}/{k}"] = v.numpy()
+        out[f"calc_loss/{lt}/x_t"], out[f"calc_loss/{lt}/eps"] = x_t.numpy(), eps.numpy()
+    # p_loss: weighted timestep sampling (np.random) and uniform sampling (torch.randint on x_0.device)
+    for lw in ("prop-t", "uniform"):
+        D = GD.GaussianDiffusionModel([32, 32], GD.get_beta_schedule(100, "linear"), loss_type="l2", loss_weight=lw, noise="gauss")
+        D.noise_fn = lambda x, tt: noise
+        np.random.seed(11)
+        tt, ww = D.sample_t_with_weights(3, torch.device("cpu"))
+        out[f"p_loss/{lw}/t"], out[f"p_loss/{lw}/w"] = tt.numpy(), ww.numpy()
+        np.random.seed(11)
+        with torch.no_grad():
+            total, (ld, x_t, eps) = D.p_loss(m, x0, {"train_start": True, "sample_distance": 60})
+        out[f"p_loss/{lw}/total"], out[f"p_loss/{lw}/loss"] = total.numpy(), ld["loss"].numpy()
+        out[f"p_loss/{lw}/x_t"] = x_t.numpy()
+    D = GD.GaussianDiffusionModel([32, 32], GD.get_beta_schedule(100, "linear"), loss_type="l2", loss_weight="none", noise="gauss")
+    D.noise_fn = lambda x, tt: noise
+    for tag, args in (("start", {"train_start": True, "sample_distance": 60}), ("full", {"train_start": False, "sample_distance": 60})):
+        torch.manual_seed(5)
+        t_draw = torch.randint(0, 60 if tag == "start" else 100, (3,))
+        torch.manual_seed(5)
+        with torch.no_grad():
+            total, (ld, x_t, eps) = D.p_loss(m, x0, args)
+        out[f"p_loss/none_{tag}/t"], out[f"p_loss/none_{tag}/total"] = t_draw.numpy(), total.numpy()
+        out[f"p_loss/none_{tag}/loss"], out[f"p_loss/none_{tag}/x_t"] = ld["loss"].numpy(), x_t.numpy()
+    # random_noise: branch sequence under pinned RNGs (B = 1)
+    random.seed(3), np.random.seed(4), torch.manual_seed(5)
+    S = simplex.Simplex_CLASS()
+    x1 = torch.zeros(1, 1, 32, 32)
+    t1 = torch.tensor([7])
+    outs, flags = [], []
+    for _ in range(8):
+        before = np.random.get_state()[1].copy(), np.random.get_state()[2]
+        r = GD.random_noise(S, x1, t1)
+        after = np.random.get_state()[1], np.random.get_state()[2]
+        flags.append(not (np.array_equal(before[0], after[0]) and before[1] == after[1]))
+        outs.append(r.numpy())
+    out["random_noise/out"], out["random_noise/is_simplex"] = np.stack(outs), np.array(flags)
+    # simplex_randParam: output and RNG consumption (one random.choice per channel; the drawn parameters are discarded)
+    random.seed(9), np.random.seed(10)
+    x2 = torch.zeros(1, 2, 16, 16)
+    out["randparam/out"] = GD.generate_simplex_noise(simplex.Simplex_CLASS(), x2, torch.tensor([33]), True, in_channels=2).numpy()
+    out["randparam/next_random"] = np.array(random.random())
+    out["randparam/next_np"] = np.array(np.random.randint(-10000000000, 10000000000))
+    # calc_total_vlb with torch.randn_like replayed from a bank (the reference draws it on x_0.device)
+    T = 40          # linear schedule scaled by 1000/T: betas stay below 1 for T >= 21
+    D = GD.GaussianDiffusionModel([32, 32], GD.get_beta_schedule(T, "linear"), noise="gauss")
+    bank = torch.randn(T, 3, 1, 32, 32, generator=torch.Generator().manual_seed(31))
+    it = iter(bank)
+    orig = torch.randn_like
+    torch.randn_like = lambda x, *a, **k: next(it)
+    try:
+        r = D.calc_total_vlb(x0, m, {"Batch_Size": 3})
+    finally:
+        torch.randn_like = orig
+    for k, v in r.items():
+        out[f"total_vlb/{k}"] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "loss.npz"), **out)
+    print("loss.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["simplex", "diffusion", "unet", "loop", "vlb"]
+    which = sys.argv[1:] or ["simplex", "diffusion", "unet", "loop", "vlb", "loss"]
     for w in which:
         globals()["gen_" + w]()

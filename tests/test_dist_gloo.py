@@ -41,3 +41,42 @@ def test_two_rank_sharding_and_reduction(tmp_path):
     assert rows[0]["seeds"] == seeds_for_step(1234, 5, range(0, 4))
     assert [shard_range(10, r, 3) for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
     assert all(-10000000000 <= s < 10000000000 and s != 0 for s in seeds_for_step(7, 0, range(100)))
+
+
+REDUCE_WORKER = textwrap.dedent("""
+    import json, os, sys
+    sys.path.insert(0, %r)
+    import torch
+    from anoddpm_b200 import dist as D
+    from anoddpm_b200.optim import GradReducer
+    rank, world, local = D.init_from_env(backend="gloo")
+    sizes = [100, 200, 300, 300, 100]
+    offsets = [0, 100, 300, 600, 900]
+    g = torch.arange(1000, dtype=torch.float32) * (rank + 1)      # rank r holds (r + 1) * i
+    red = GradReducer(g, offsets, sizes, bucket_elems=350)
+    assert red.buckets == [(600, 1000), (100, 600), (0, 100)], red.buckets
+    launched = []
+    red.mark_ready(900); launched.append(red.next_bucket)         # tail bucket not complete yet
+    red.mark_ready(600); launched.append(red.next_bucket)         # bucket 0 goes out while "backward" continues
+    red.mark_ready(300); launched.append(red.next_bucket)
+    red.finish()                                                  # the rest + wait + divide by the world size
+    with open(os.path.join(os.environ["ADP_OUT"], f"red{rank}.json"), "w") as f:
+        json.dump({"launched": launched, "g": g.tolist()}, f)
+    D.shutdown()
+""") % ROOT
+
+
+def test_two_rank_bucketed_gradient_average(tmp_path):
+    """training row of SURVEY 8(e): the flat gradient is averaged bucket by bucket, tail (last layers) first; both ranks
+    end with bit-identical means."""
+    script = tmp_path / "r.py"
+    script.write_text(REDUCE_WORKER)
+    port = 31500 + os.getpid() % 2000
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, ADP_OUT=str(tmp_path)))
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    rows = [json.load(open(tmp_path / f"red{r}.json")) for r in range(2)]
+    assert rows[0]["launched"] == rows[1]["launched"] == [0, 1, 1]
+    assert rows[0]["g"] == rows[1]["g"] == [1.5 * i for i in range(1000)]
