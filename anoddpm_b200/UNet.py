@@ -261,6 +261,9 @@ class UNetModel(nn.Module):
         # "tc" only: the first conv of a ResBlock (read by GroupNorm 2 alone) stores fp16 sums without their per-channel
         # bias + embedding offset, which the GroupNorm pass adds back in fp32 (halves that tensor's HBM traffic)
         self.h1_fp16 = os.environ.get("ANODDPM_H1_FP16", "1") != "0"
+        # "tc" only: GroupNorm + SiLU are applied to the raw fp16 operand boxes inside the 3x3 convolutions (conv_tc3's
+        # transform warps) wherever the producer left an fp16 copy -- no stand-alone normalisation pass, no normalised copy
+        self.fuse_gn = os.environ.get("ANODDPM_FUSE_GN", "1") != "0"
 
     # -- native inference path ---------------------------------------------------------------------
     def engine(self):

@@ -49,6 +49,9 @@ constexpr int kEpiWarps = 8;
 constexpr int kStgBuf = 32 * 64;                    // one epilogue buffer: 32 pixel rows x 16 fp32 channels, SWIZZLE_64B
 constexpr int kStgBytes = kEpiWarps * 2 * kStgBuf;  // 8 epilogue warps x 2 buffers
 constexpr int kBeBytes = kEpiWarps * 128 * 4;       // per-warp (bias + embedding) row of the current tile
+constexpr int kStg16Buf = 32 * 32;                  // fp16 copy of a step: 32 pixel rows x 16 halves, no swizzle
+constexpr int kStg16Bytes = kEpiWarps * 2 * kStg16Buf;
+constexpr int kThreadsGN = 512;                     // + warps 12-15: operand transform (GroupNorm + SiLU on the landed A box)
 
 struct Tc3Args {
     void* out;
@@ -69,6 +72,12 @@ struct Tc3Args {
     long long stat_replica_stride;   // B*Cout*2
     int tile_order;
     int single_box;            // main loop variant: ONE (K-block, 18 px, 18 rows) A box per chunk, nine taps by descriptor offsets
+    // operand-side GroupNorm (GN kernel variant): the A boxes hold RAW fp16 activations; warps 12-15 rewrite each landed box
+    // to SiLU(v * scale + shift) before the MMA warp may read it
+    const float2* gn_table;    // [B][c_tab] (scale, shift)
+    int c_tab;                 // Ca1 + Ca2
+    int chunks_a1;             // chunks of the first main source; chunks_a - chunks_a1 come from the second (torch.cat)
+    int has_out16;             // the epilogue also stores an fp16 copy of the fp32 output
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -94,6 +103,18 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
         ".reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
         "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+// the same with release semantics at cluster scope: the arriving thread's prior shared-memory writes (made visible to the
+// async proxy by fence.proxy.async) are ordered before the waiter in the other CTA of the pair
+__device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
         "}\n" ::"r"(smem_u32(bar)),
         "r"(cta)
         : "memory");
@@ -213,12 +234,13 @@ __device__ __forceinline__ uint64_t make_sdesc_sbo(uint32_t saddr, uint32_t sbo)
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-template <bool F16, bool OUT16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_r1,
+template <bool F16, bool OUT16, bool GN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN ? kThreadsGN : kThreads, 1)
+conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+                const __grid_constant__ CUtensorMap map_r1,
                 const __grid_constant__ CUtensorMap map_r2, const __grid_constant__ CUtensorMap map_w,
                 const __grid_constant__ CUtensorMap map_res, const __grid_constant__ CUtensorMap map_out,
-                const Tc3Args P) {
+                const __grid_constant__ CUtensorMap map_out16, const Tc3Args P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_bytes = (P.BN / 2) * kRowBytes;      // one weight tile (this CTA's half of the N rows)
@@ -227,8 +249,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint8_t* sA = smem;
     uint8_t* sB = smem + (P.single_box ? 2 * kBoxStride : S * kABytes);
     uint8_t* stg_all = sB + S * 3 * b_bytes;       // [8 warps][2][kStgBuf], 1024-byte aligned (ring sizes are multiples)
-    float* be_all = reinterpret_cast<float*>(stg_all + kStgBytes);   // [8 warps][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stg_all + kStgBytes + kBeBytes);
+    uint8_t* stg16_all = stg_all + kStgBytes;      // [8 warps][2][kStg16Buf] when the fp16 copy is requested
+    float* be_all = reinterpret_cast<float*>(stg16_all + (P.has_out16 ? kStg16Bytes : 0));   // [8 warps][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(be_all) + kBeBytes);
     uint64_t* full = bars;                         // [S]   leader only
     uint64_t* empty = bars + kMaxStages;           // [S]   both CTAs (multicast commit)
     uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]   both CTAs (multicast commit)
@@ -236,7 +259,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint64_t* res_bar = tmem_empty + kAccStages;   // [8 warps][2] residual box landed
     uint64_t* a_full = res_bar + 2 * kEpiWarps;    // [2]   single-box main loop: A box landed (leader only)
     uint64_t* a_empty = a_full + 2;                // [2]   both CTAs (multicast commit)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 2);
+    uint64_t* a_land = a_empty + 2;                // [2]   GN: this CTA's raw A box landed (per CTA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_land + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
@@ -260,12 +284,15 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
         if (P.res) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_res) : "memory");
+        if (P.has_out16) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out16) : "memory");
+        if (GN && P.chunks_a1 < P.chunks_a) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a2) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < S; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
         for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * 32 * kEpiWarps); }
         for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
+        // GN: a_full collects one arrival per transform warp of both CTAs (4 + 4) instead of the two producers
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], GN ? 8 : 2); mbar_init(&a_empty[i], 1); mbar_init(&a_land[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -282,7 +309,56 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (warp == 0) {
         // ---------------- TMA producer (both CTAs) ----------------
         const bool elected = elect_one();
-        if (elected && P.single_box) {
+        if (GN) {
+            // raw A boxes land on this CTA's OWN barrier (the transform warps of this CTA rewrite them, then signal the
+            // leader's a_full); weight stages as in the single-box loop
+            if (elected) {
+                int bc = 0, ac = 0;
+                for (int tile = tile_first; tile < tile_end; tile += tile_step) {
+                    const int pair = tile / P.n_tiles_n, nt = tile - pair * P.n_tiles_n;
+                    const int R = pair * 2 + (int)rank;
+                    const int b0 = R / P.regions_per_img, rr = R - b0 * P.regions_per_img;
+                    const int y0 = (rr / P.regions_x) * 16, x0 = (rr % P.regions_x) * 16;
+                    const int n0 = nt * P.BN + (int)rank * (P.BN / 2);
+                    const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
+                    for (int c = 0; c < nchunks; ++c, ++ac) {
+                        const int ab = ac & 1;
+                        uint8_t* a_dst = sA + ab * kBoxStride;
+                        mbar_wait(&a_empty[ab], ((ac >> 1) & 1) ^ 1);
+                        if (c < P.chunks_a) {
+                            const bool first = c < P.chunks_a1;
+                            mbar_expect_tx(&a_land[ab], (uint32_t)kBoxBytes);
+                            tma_load_4d(a_dst, first ? &map_a : &map_a2, &a_land[ab], (first ? c : c - P.chunks_a1) * P.ke,
+                                        x0 - 1, y0 - 1, b0);
+                            for (int dy = 0; dy < 3; ++dy, ++bc) {
+                                const int s = bc % S;
+                                mbar_wait(&empty[s], ((bc / S) & 1) ^ 1);
+                                uint8_t* b_dst = sB + s * 3 * b_bytes;
+                                if (leader) mbar_expect_tx(&full[s], 2u * 3u * (uint32_t)b_bytes);
+                                else mbar_arrive_remote(&full[s], 0);
+#pragma unroll
+                                for (int dx = 0; dx < 3; ++dx)
+                                    tma2_load_2d(b_dst + dx * b_bytes, &map_w, &full[s], (dy * 3 + dx) * P.Ca + c * P.ke, n0);
+                            }
+                        } else {
+                            const int cs = c - P.chunks_a;
+                            const bool first = cs < P.chunks_r1;
+                            const CUtensorMap* am = first ? &map_r1 : &map_r2;
+                            const int c0 = (first ? cs : cs - P.chunks_r1) * P.ke;
+                            mbar_expect_tx(&a_land[ab], 2u * (16 * 8 * kRowBytes));
+                            tma_load_4d(a_dst, am, &a_land[ab], c0, x0, y0, b0);
+                            tma_load_4d(a_dst + 16 * 8 * kRowBytes, am, &a_land[ab], c0, x0 + 8, y0, b0);
+                            const int s = bc % S;
+                            mbar_wait(&empty[s], ((bc / S) & 1) ^ 1);
+                            if (leader) mbar_expect_tx(&full[s], 2u * (uint32_t)b_bytes);
+                            else mbar_arrive_remote(&full[s], 0);
+                            tma2_load_2d(sB + s * 3 * b_bytes, &map_w, &full[s], 9 * P.Ca + cs * P.ke, n0);
+                            ++bc;
+                        }
+                    }
+                }
+            }
+        } else if (elected && P.single_box) {
             // one (K-block, 18 px, 18 rows) box per chunk (2 buffers) + a ring of (chunk, dy) weight stages
             int bc = 0, ac = 0;
             for (int tile = tile_first; tile < tile_end; tile += tile_step) {
@@ -460,7 +536,58 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (GN && warp >= 12) {
+        // ---------------- operand transform (both CTAs): GroupNorm + SiLU on the landed raw box, in place ----------------
+        // thread = (16-byte chunk j = channels 8j..8j+7 of the K-block, row lane rl); box row r = pixel (r / 18, r % 18) of
+        // the 18x18 halo region sits at r * 128 B, its chunk j at j ^ (r & 7) (SWIZZLE_128B on a 1024-byte aligned buffer).
+        // Pixels outside the image keep TMA's zero fill: the convolution pads AFTER normalisation + activation.
+        const int tid = (warp - 12) * 32 + lane;
+        const int j = tid & 7, rl = tid >> 3;
+        const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
+        int ac = 0;
+        for (int tile = tile_first; tile < tile_end; tile += tile_step) {
+            const int pair = tile / P.n_tiles_n;
+            const int R = pair * 2 + (int)rank;
+            const int b0 = R / P.regions_per_img, rr = R - b0 * P.regions_per_img;
+            const int y0 = (rr / P.regions_x) * 16, x0 = (rr % P.regions_x) * 16;
+            const bool live = R < P.n_regions;
+            for (int c = 0; c < nchunks; ++c, ++ac) {
+                const int ab = ac & 1;
+                const bool work = live && c < P.chunks_a;
+                float4 t4[4];
+                if (work) {   // table row of this thread's 8 channels: issued before the wait, it does not depend on the box
+                    const float4* tp = reinterpret_cast<const float4*>(P.gn_table + (size_t)b0 * P.c_tab + c * 64 + 8 * j);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) t4[q] = __ldg(tp + q);
+                }
+                mbar_wait(&a_land[ab], (ac >> 1) & 1);
+                if (work) {
+                    const uint32_t a_base = smem_u32(sA + ab * kBoxStride);
+                    const float sc[8] = {t4[0].x, t4[0].z, t4[1].x, t4[1].z, t4[2].x, t4[2].z, t4[3].x, t4[3].z};
+                    const float sh[8] = {t4[0].y, t4[0].w, t4[1].y, t4[1].w, t4[2].y, t4[2].w, t4[3].y, t4[3].w};
+#pragma unroll 3
+                    for (int r = rl; r < 18 * 18; r += 16) {
+                        const int py = r / 18, px = r - py * 18;
+                        if ((unsigned)(y0 - 1 + py) < (unsigned)P.H && (unsigned)(x0 - 1 + px) < (unsigned)P.W) {
+                            const uint32_t addr = a_base + (uint32_t)r * kRowBytes + (uint32_t)((j ^ (r & 7)) << 4);
+                            uint4 v = lds128u(addr);
+                            uint32_t* vw = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(&vw[e]));
+                                const float y0f = fmaf(fv.x, sc[2 * e], sh[2 * e]), y1f = fmaf(fv.y, sc[2 * e + 1], sh[2 * e + 1]);
+                                vw[e] = pack_half2_sat(__fdividef(y0f, 1.0f + __expf(-y0f)), __fdividef(y1f, 1.0f + __expf(-y1f)));
+                            }
+                            sts128u(addr, v);
+                        }
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote_release(&a_full[ab], 0);
+            }
+        }
+    } else if (warp >= 4 && warp < 12) {
         // ---------------- epilogue (both CTAs) ----------------
         const int ew = warp - 4;            // 0..7
         const int quarter = warp & 3;       // TMEM lanes 32*quarter.. : image rows 4*quarter..+3 of the subtile
@@ -611,6 +738,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // residual box of step (tile, cb) -> buffer buf (one lane issues; the warp's 4 image rows x 8 px x 16 ch).
         // TMA, not register loads: measured, global loads issued by the epilogue warps (pixel-per-lane or coalesced, one
         // or two steps ahead) are 15-25% slower -- they queue behind the operand bursts of the main loop
+        uint8_t* stg16 = stg16_all + ew * (2 * kStg16Buf);
         uint64_t* rbar = res_bar + ew * 2;
         const uint32_t res_bytes = P.res_mode == 3 ? 8u * 64u : (uint32_t)kStgBuf;
         auto issue_res = [&](int tile, int cb, int buf) {
@@ -705,6 +833,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     __syncwarp();
                 }
+                uint32_t h16[8];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float4 be4 = lds128(bea + 16 * j);
@@ -712,12 +841,21 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                             __uint_as_float(r[4 * j + 2]) + be4.z, __uint_as_float(r[4 * j + 3]) + be4.w);
                     if (has_res) { v4.x += rs[j].x; v4.y += rs[j].y; v4.z += rs[j].z; v4.w += rs[j].w; }
                     sts128(sba + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), v4);
+                    h16[2 * j] = pack_half2_sat(v4.x, v4.y);
+                    h16[2 * j + 1] = pack_half2_sat(v4.z, v4.w);
+                }
+                if (P.has_out16) {   // fp16 copy of the same 32 px x 16 ch step: dense 32-byte rows (same group as the fp32 store)
+                    const uint32_t s16 = smem_u32(stg16 + buf * kStg16Buf) + lane * 32;
+                    sts128u(s16, make_uint4(h16[0], h16[1], h16[2], h16[3]));
+                    sts128u(s16 + 16, make_uint4(h16[4], h16[5], h16[6], h16[7]));
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                // 2. the buffer is the output box (16 ch, 8 px, 4 rows): one TMA store
+                // 2. the buffer is the output box (16 ch, 8 px, 4 rows): one TMA store (+ one for the fp16 copy)
                 if (lane == 0) {
                     tma_store_4d(&map_out, stg + buf * kStgBuf, n0 + cb, xbase + 8 * sub, ybase + 4 * quarter, b);
+                    if (P.has_out16)
+                        tma_store_4d(&map_out16, stg16 + buf * kStg16Buf, n0 + cb, xbase + 8 * sub, ybase + 4 * quarter, b);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 // 3. column pass: lane owns channels cc..cc+3 of rows (lane >> 2) + 8k -> per-channel statistics
@@ -822,6 +960,24 @@ int make_epi_map3(CUtensorMap* m, const void* p, int C, int W, int H, int B, int
     return ANODDPM_OK;
 }
 
+// fp16 copy of the output: dims (C, W, H, B), box (16 halves = 32 B, 8 px, 4 rows, 1), no swizzle
+int make_out16_map3(CUtensorMap* m, const void* p, int C, int W, int H, int B) {
+    EncodeTiledFn enc = get_encode3();
+    if (!enc) { anoddpm_set_error("cuTensorMapEncodeTiled entry point not available"); return ANODDPM_ERR_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {16u, 8u, 4u, 1u};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(p), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        anoddpm_set_error("cuTensorMapEncodeTiled(out16 C=%d W=%d H=%d B=%d) failed: %d", C, W, H, B, (int)r);
+        return ANODDPM_ERR_CUDA;
+    }
+    return ANODDPM_OK;
+}
+
 int make_w_map3(CUtensorMap* m, const void* p, int f16, int Ktot, int Cout, int rows) {
     EncodeTiledFn enc = get_encode3();
     if (!enc) { anoddpm_set_error("cuTensorMapEncodeTiled entry point not available"); return ANODDPM_ERR_CUDA; }
@@ -848,7 +1004,10 @@ extern "C" int anoddpm_conv_tc3_supported(const anoddpm_conv_desc* d) {
     if (d->ksize != 3) return 0;
     if (d->H % 16 || d->W % 16) return 0;
     const int ke = d->operand_f16 ? 64 : 32;
-    if (d->Ca % ke || d->Cr1 % ke || d->Cr2 % ke) return 0;
+    if (d->Ca % ke || d->Cr1 % ke || d->Cr2 % ke || d->Ca2 % ke) return 0;
+    if ((d->gn_table || d->a2) && !d->operand_f16) return 0;   // operand-side GroupNorm rewrites fp16 boxes
+    if (d->a2 && !d->gn_table) return 0;                       // a second main source is loaded by the GN variant only
+    if (d->out16 && d->out_f16) return 0;
     if (d->Cout % 32) return 0;
     if (d->Cout > 128 && d->Cout % 128) return 0;
     if (d->res && d->res_mode == 2) return 0;   // avg-pooled residual: pool it in anoddpm_gn_apply (or use impl 2)
@@ -866,22 +1025,32 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     P.out = d->out; P.bias = d->bias; P.emb = d->emb; P.res = d->res;
     P.M = d->B * d->H * d->W; P.H = d->H; P.W = d->W; P.Cout = d->Cout;
     P.emb_stride = d->emb_stride; P.res_mode = d->res_mode;
-    P.Ca = d->Ca;
+    P.Ca = d->Ca + d->Ca2;                 // concatenated main source: weights are packed over Ca + Ca2 channels per tap
     const int f16 = d->operand_f16 ? 1 : 0;
+    const bool gn = d->gn_table != nullptr;
     P.ke = f16 ? 64 : 32;
-    P.chunks_a = d->Ca / P.ke;
+    P.chunks_a = P.Ca / P.ke;
+    P.chunks_a1 = d->Ca / P.ke;
     P.chunks_r1 = d->Cr1 / P.ke;
     P.chunks_r2 = d->Cr2 / P.ke;
+    P.gn_table = reinterpret_cast<const float2*>(d->gn_table);
+    P.c_tab = P.Ca;
+    P.has_out16 = d->out16 ? 1 : 0;
     P.BN = d->Cout < 128 ? d->Cout : 128;
     const int acc_cols = kAccStages * 2 * P.BN;
     P.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
-    const int Ktot = 9 * d->Ca + d->Cr1 + d->Cr2;
+    const int Ktot = 9 * P.Ca + d->Cr1 + d->Cr2;
     const int b_bytes = (P.BN / 2) * kRowBytes;
     // single-box main loop unless the conv has fused 1x1 skip sources (their small chunks would each hold one of only two
-    // A buffers for 8 MMAs: measured 4 % slower there, 4-5 % faster everywhere else); ANODDPM_TC3_SINGLEBOX=0/1 forces
+    // A buffers for 8 MMAs: measured 4 % slower there, 4-5 % faster everywhere else); ANODDPM_TC3_SINGLEBOX=0/1 forces.
+    // The operand-transform variant always runs the single-box loop.
     { const char* e = getenv("ANODDPM_TC3_SINGLEBOX"); P.single_box = e ? atoi(e) : ((d->Cr1 + d->Cr2) == 0 ? 1 : 0); }
-    int stages = P.single_box ? (186 * 1024 - 2 * kBoxStride) / (3 * b_bytes) : (186 * 1024) / (kABytes + 3 * b_bytes);
+    if (gn) P.single_box = 1;
+    const size_t fixed = (size_t)kStgBytes + (P.has_out16 ? kStg16Bytes : 0) + kBeBytes + 512 + 1024;
+    const size_t budget = 227 * 1024 - fixed;
+    int stages = P.single_box ? (int)((budget - 2 * kBoxStride) / (3 * b_bytes)) : (int)(budget / (kABytes + 3 * b_bytes));
     if (stages > kMaxStages) stages = kMaxStages;
+    ADP_REQUIRE(stages >= 2, "anoddpm_conv(impl=3): shared memory budget leaves fewer than 2 stages");
     P.stages = stages;
     P.n_tiles_n = adp_ceil_div(d->Cout, P.BN);
     P.regions_x = d->W / 16;
@@ -892,17 +1061,19 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     P.stat_replica_stride = (long long)d->B * d->Cout * 2;
     P.tile_order = 1;   // contiguous run of tiles per cluster (statistics stay in registers across a sample's tiles)
 
-    CUtensorMap ma, m1, m2, mw;
+    CUtensorMap ma, ma2, m1, m2, mw;
     int rc;
     if ((rc = make_act_map3(&ma, d->a, f16, d->Ca, d->W, d->H, d->B, kSubRows, P.single_box ? 18 : 8))) return rc;
-    m1 = ma; m2 = ma;
+    ma2 = ma; m1 = ma; m2 = ma;
+    if (d->a2 && (rc = make_act_map3(&ma2, d->a2, f16, d->Ca2, d->W, d->H, d->B, kSubRows, 18))) return rc;
     if (d->r1 && (rc = make_act_map3(&m1, d->r1, f16, d->Cr1, d->W, d->H, d->B, 16))) return rc;
     if (d->r2 && (rc = make_act_map3(&m2, d->r2, f16, d->Cr2, d->W, d->H, d->B, 16))) return rc;
     if ((rc = make_w_map3(&mw, d->w, f16, Ktot, d->Cout, P.BN / 2))) return rc;
     // epilogue store box: (16 ch fp32, 8 px, 4 rows) of the output
-    CUtensorMap mres, mout;
+    CUtensorMap mres, mout, mout16;
     if ((rc = make_epi_map3(&mout, d->out, d->Cout, d->W, d->H, d->B, 8, 4, d->out_f16 ? 1 : 0))) return rc;
-    mres = mout;
+    mres = mout; mout16 = mout;
+    if (d->out16 && (rc = make_out16_map3(&mout16, d->out16, d->Cout, d->W, d->H, d->B))) return rc;
     if (d->res) {   // residual boxes: (16, 8, 4) at the same resolution, (16, 4, 2) of a half-resolution source
         if (d->res_mode == 3) rc = make_epi_map3(&mres, d->res, d->Cout, d->W / 2, d->H / 2, d->B, 4, 2);
         else rc = make_epi_map3(&mres, d->res, d->Cout, d->W, d->H, d->B, 8, 4);
@@ -910,27 +1081,32 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     }
 
     const size_t ring = P.single_box ? (size_t)2 * kBoxStride + (size_t)stages * 3 * b_bytes : (size_t)stages * (kABytes + 3 * b_bytes);
-    const size_t smem = ring + kStgBytes + kBeBytes + 512 + 1024;
+    const size_t smem = ring + fixed;
     static bool attr_dev[64] = {};   // the attribute is per device
     int dev_ = 0;
     ADP_CUDA(cudaGetDevice(&dev_));
     if (!attr_dev[dev_ & 63]) {
-        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_dev[dev_ & 63] = true;
     }
     const int sms = 148;
     const int n_clusters = P.n_tiles < sms / 2 ? P.n_tiles : sms / 2;
     const dim3 grid(2 * n_clusters);
     cudaStream_t st = (cudaStream_t)stream;
-    if (d->out_f16) {
-        if (f16) conv_tc3_kernel<true, true><<<grid, kThreads, smem, st>>>(ma, m1, m2, mw, mres, mout, P);
-        else conv_tc3_kernel<false, true><<<grid, kThreads, smem, st>>>(ma, m1, m2, mw, mres, mout, P);
+    if (gn) {
+        if (d->out_f16) conv_tc3_kernel<true, true, true><<<grid, kThreadsGN, smem, st>>>(ma, ma2, m1, m2, mw, mres, mout, mout16, P);
+        else conv_tc3_kernel<true, false, true><<<grid, kThreadsGN, smem, st>>>(ma, ma2, m1, m2, mw, mres, mout, mout16, P);
+    } else if (d->out_f16) {
+        if (f16) conv_tc3_kernel<true, true, false><<<grid, kThreads, smem, st>>>(ma, ma2, m1, m2, mw, mres, mout, mout16, P);
+        else conv_tc3_kernel<false, true, false><<<grid, kThreads, smem, st>>>(ma, ma2, m1, m2, mw, mres, mout, mout16, P);
     } else {
-        if (f16) conv_tc3_kernel<true, false><<<grid, kThreads, smem, st>>>(ma, m1, m2, mw, mres, mout, P);
-        else conv_tc3_kernel<false, false><<<grid, kThreads, smem, st>>>(ma, m1, m2, mw, mres, mout, P);
+        if (f16) conv_tc3_kernel<true, false, false><<<grid, kThreads, smem, st>>>(ma, ma2, m1, m2, mw, mres, mout, mout16, P);
+        else conv_tc3_kernel<false, false, false><<<grid, kThreads, smem, st>>>(ma, ma2, m1, m2, mw, mres, mout, mout16, P);
     }
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;

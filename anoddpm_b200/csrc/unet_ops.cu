@@ -411,6 +411,52 @@ __global__ void __launch_bounds__(256) gn_apply_h_kernel(void* __restrict__ out_
     }
 }
 
+// ---------------------------------------------------------------- GroupNorm as a per-(sample, channel) affine table
+// table[b][c] = (scale, shift): GroupNorm(x + off)[b, c] = x * scale + shift.  Feeds the operand transform inside the
+// tensor-core convolution (conv_tc3.cu, gn_table): the consumer normalises while it loads, no normalised copy exists.
+// One CTA per sample; thread (g, r) adds up replica r of group g exactly like gn_apply_kernel, over one or two tensors.
+__global__ void __launch_bounds__(256) gn_table_kernel(float2* __restrict__ table, const double* __restrict__ st1, int C1,
+                                                       const double* __restrict__ st2, int C2,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ shift_c, const float* __restrict__ shift_bc,
+                                                       int shift_stride, int HW, int groups, float eps) {
+    __shared__ float s_mean[64], s_rstd[64];
+    const int b = blockIdx.x, nb = gridDim.x, C = C1 + C2, gs = C / groups;
+    {
+        const int g = threadIdx.x / ANODDPM_STAT_REPLICAS, r = threadIdx.x % ANODDPM_STAT_REPLICAS;
+        double s = 0.0, q = 0.0;
+        if (g < groups) {
+            for (int c = g * gs; c < (g + 1) * gs; ++c) {
+                const double* st = c < C1 ? st1 + (size_t)r * nb * C1 * 2 + ((size_t)b * C1 + c) * 2
+                                          : st2 + (size_t)r * nb * C2 * 2 + ((size_t)b * C2 + (c - C1)) * 2;
+                s += st[0];
+                q += st[1];
+            }
+        }
+#pragma unroll
+        for (int o = 1; o < ANODDPM_STAT_REPLICAS; o <<= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (g < groups && r == 0) {
+            const double n = (double)HW * gs;
+            const double m = s / n;
+            double var = q / n - m * m;
+            if (var < 0) var = 0;
+            s_mean[g] = (float)m;
+            s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / gs;
+        float sh = shift_c ? shift_c[c] : 0.f;
+        if (shift_bc) sh += shift_bc[(size_t)b * shift_stride + c];
+        const float sc = s_rstd[g] * gamma[c];
+        table[(size_t)b * C + c] = make_float2(sc, beta[c] + sc * (sh - s_mean[g]));
+    }
+}
+
 // ---------------------------------------------------------------- exact fp32 implicit-GEMM conv
 // CTA tile 64 pixels x 64 output channels, K chunks of 16 input channels of one tap.
 constexpr int CBM = 64, CBN = 64, CBK = 16;
@@ -917,6 +963,20 @@ extern "C" int anoddpm_gn_apply_f16in(void* out, const void* x_f16, int C, const
     return ANODDPM_OK;
 }
 
+extern "C" int anoddpm_gn_table(float* table, const double* stats1, int C1, const double* stats2, int C2,
+                                const float* gamma, const float* beta, const float* shift_c, const float* shift_bc,
+                                int shift_stride, int B, int HW, int groups, float eps, void* stream) {
+    ADP_REQUIRE(table && stats1 && gamma && beta && B > 0 && HW > 0 && C1 > 0 && C2 >= 0, "anoddpm_gn_table: bad arguments");
+    ADP_REQUIRE((C2 == 0) == (stats2 == nullptr), "anoddpm_gn_table: second source / channel mismatch");
+    ADP_REQUIRE(groups > 0 && groups * ANODDPM_STAT_REPLICAS <= 256 && (C1 + C2) % groups == 0,
+                "anoddpm_gn_table: at most 32 groups dividing C (C=%d groups=%d)", C1 + C2, groups);
+    ADP_REQUIRE(!shift_bc || shift_stride >= C1 + C2, "anoddpm_gn_table: shift stride smaller than C");
+    gn_table_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(table), stats1, C1, stats2, C2, gamma, beta,
+                                                         shift_c, shift_bc, shift_stride, HW, groups, eps);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}
+
 extern "C" int anoddpm_conv(const anoddpm_conv_desc* d, void* stream) {
     ADP_REQUIRE(d && d->out && d->a && d->w, "anoddpm_conv: null pointer");
     ADP_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->Cout > 0 && d->Ca > 0, "anoddpm_conv: bad shape");
@@ -934,6 +994,9 @@ extern "C" int anoddpm_conv(const anoddpm_conv_desc* d, void* stream) {
                 "anoddpm_conv: pointers must be 16-byte aligned");
     ADP_REQUIRE(!d->operand_f16 || d->impl == 2 || d->impl == 3, "anoddpm_conv: fp16 operands need impl 2 or 3");
     ADP_REQUIRE(!d->out_f16 || d->impl == 3, "anoddpm_conv: fp16 output needs impl 3");
+    ADP_REQUIRE((d->Ca2 == 0) == (d->a2 == nullptr) && d->Ca2 >= 0, "anoddpm_conv: second main source / channel mismatch");
+    ADP_REQUIRE((!d->a2 && !d->gn_table && !d->out16) || d->impl == 3,
+                "anoddpm_conv: a2 / gn_table / out16 (operand-side GroupNorm) need impl 3");
     if (d->impl == 3) return anoddpm_conv_tc3(d, stream);
     ADP_REQUIRE(d->gn_stats == nullptr || d->impl == 2, "anoddpm_conv: fused GroupNorm statistics need impl 2 or 3");
     if (d->impl == 1) return anoddpm_conv_tc(d, stream);

@@ -45,10 +45,12 @@ class _T:
     """An NHWC activation and (optionally) its per-channel statistics [B][C][2] fp64 (sum, sum of squares).
     shift = (bias, emb_rows): an fp16 conv output that stores the convolution sum only; the statistics describe
     t + bias[c] + emb_rows[b, c], and the GroupNorm pass adds that offset back in fp32."""
-    __slots__ = ("t", "st", "shift")
+    __slots__ = ("t", "st", "shift", "t16")
 
-    def __init__(self, t, st=None, shift=None):
+    def __init__(self, t, st=None, shift=None, t16=None):
         self.t, self.st, self.shift = t, st, shift
+        self.t16 = t16      # optional fp16 copy of an fp32 residual-stream tensor: the raw operand of a conv that applies
+        #                     GroupNorm + SiLU while it loads (gn_table), and of a fused 1x1 skip conv
 
 
 class _Conv:
@@ -229,11 +231,39 @@ class UNetEngine:
         self.launches += 1
         return (out, raw) if want_raw else out
 
-    def _conv(self, site, a, B, H, W, cout, plan, r=(), emb=None, res=None, res_mode=0, want_stats=True, out_f16=False):
+    def _gn_table(self, srcs, gn, B, HW):
+        """[B][C][2] (scale, shift) of GroupNorm over one tensor or the concatenation of two (anoddpm_gn_table): the conv
+        that consumes the tensor(s) normalises + activates its operand boxes with it (no normalised copy in HBM)."""
+        x1 = srcs[0]
+        x2 = srcs[1] if len(srcs) > 1 else None
+        st1 = self._stats_of(x1, B, HW)
+        st2 = self._stats_of(x2, B, HW) if x2 is not None else None
+        C1 = x1.t.shape[-1]
+        C2 = x2.t.shape[-1] if x2 is not None else 0
+        bias, emb = x1.shift if x1.shift is not None else (None, None)
+        assert x1.shift is None or x2 is None
+        tab = torch.empty((B, C1 + C2, 2), device=x1.t.device, dtype=torch.float32)
+        call("anoddpm_gn_table", ptr(tab), ptr(st1), C1, ptr(st2), C2, ptr(gn.weight), ptr(gn.bias), ptr(bias), ptr(emb),
+             self.emb_all.shape[1] if emb is not None else 0, B, HW, 32, float(gn.eps), stream())
+        self.launches += 1
+        self.gn_tables += 1
+        return tab
+
+    def _conv(self, site, a, B, H, W, cout, plan, r=(), emb=None, res=None, res_mode=0, want_stats=True, out_f16=False,
+              a2=None, gn_table=None, want16=False):
         impl, f16 = plan
         d = ConvDesc()
         d.B, d.H, d.W = B, H, W
         d.Ca, d.Cout, d.ksize = a.shape[-1], cout, site.ksize
+        if a2 is not None:
+            d.a2, d.Ca2 = a2.data_ptr(), a2.shape[-1]
+        if gn_table is not None:
+            assert impl == 3 and f16
+            d.gn_table = gn_table.data_ptr()
+        out16 = None
+        if want16 and impl == 3 and not out_f16:
+            out16 = torch.empty((B, H, W, cout), device=a.device, dtype=torch.float16)
+            d.out16 = out16.data_ptr()
         d.Cr1 = r[0].shape[-1] if len(r) > 0 else 0
         d.Cr2 = r[1].shape[-1] if len(r) > 1 else 0
         d.operand_f16 = 1 if f16 else 0
@@ -267,7 +297,7 @@ class UNetEngine:
             assert st is not None and res is None
             self.f16_outputs += 1
             return _T(out, st, shift=(b, emb))
-        return _T(out, st)
+        return _T(out, st, t16=out16)
 
     def _plan(self, H, W, Ca, Cr, cout, ksize):
         """(impl, f16) for a conv with main source Ca channels and (single, concatenated) skip source Cr channels."""
@@ -293,41 +323,60 @@ class UNetEngine:
         return 2 if f16 else (1 if impl else 0)
 
     # ------------------------------------------------------------------ blocks
-    def _res(self, e, srcs, B, H, W):
-        """srcs: one or two _T (the up path concatenates h with a skip tensor)."""
+    def _res(self, e, srcs, B, H, W, need16=False):
+        """srcs: one or two _T (the up path concatenates h with a skip tensor).  need16: a later convolution will read the
+        raw fp16 copy of this block's output (operand-side GroupNorm or fused 1x1 skip conv)."""
         mode = _MODE[e["mode"]]
         Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
         c_src = sum(x.t.shape[-1] for x in srcs)
         plan1 = self._plan(Ho, Wo, e["cin"], 0, e["cout"], 3)
         plan2 = self._plan(Ho, Wo, e["cout"], c_src if e["skip_conv"] else 0, e["cout"], 3)
-        # tensor-core path: the fused 1x1 skip conv reads a rounded (TF32 / fp16), channel-concatenated copy of x that
-        # is written by the same pass that normalises x (round to nearest instead of the MMA's operand truncation)
+        emb = self.emb_all[:, e["emb_off"]:]
+        have16 = all(x.t16 is not None for x in srcs)
+        fuse1 = self.fuse_gn and plan1 == (3, True) and mode == 0 and have16
+        # tensor-core path: the fused 1x1 skip conv reads a rounded (TF32 / fp16), channel-concatenated copy of x: the fp16
+        # copies written by the producers' epilogues, else a copy written by the pass that normalises x
         raw = None
         pooled = None
-        if e["skip_conv"] and plan2[0] and self._out_mode(plan1) == self._out_mode(plan2):
-            a1, raw = self._gn_apply(srcs, e["gn1"], B, H, W, True, mode, self._out_mode(plan1), want_raw=True)
-        elif mode == 1 and not e["skip_conv"] and plan2[0] == 3:
-            # the halo-reuse kernel takes a same-resolution residual: the pass that normalises x also avg-pools it
-            a1, pooled = self._gn_apply(srcs, e["gn1"], B, H, W, True, mode, self._out_mode(plan1), want_raw=True)
+        if fuse1:
+            # GroupNorm 1 + SiLU happen inside conv1: its loader rewrites the raw fp16 boxes of x (and of the skip tensor)
+            tab1 = self._gn_table(srcs, e["gn1"], B, H * W)
+            h = self._conv(e["conv1"], srcs[0].t16, B, Ho, Wo, e["cout"], plan1, emb=emb, gn_table=tab1,
+                           a2=srcs[1].t16 if len(srcs) > 1 else None, out_f16=self.h1_f16)
+            if e["skip_conv"] and plan2 == (3, True):
+                raw = [x.t16 for x in srcs]
         else:
-            if e["skip_conv"] and plan2[1]:
-                plan2 = (plan2[0], False)      # no fp16 raw copy available: run conv2 with TF32 operands
-            a1 = self._gn_apply(srcs, e["gn1"], B, H, W, True, mode, self._out_mode(plan1))
-        emb = self.emb_all[:, e["emb_off"]:]
-        # conv1's output feeds GroupNorm 2 only: stored as fp16 without its per-channel offset where the fast kernel runs
-        h = self._conv(e["conv1"], a1, B, Ho, Wo, e["cout"], plan1, emb=emb,
-                       out_f16=self.h1_f16 and plan1[0] == 3 and plan1[1])
-        del a1
-        a2 = self._gn_apply([h], e["gn2"], B, Ho, Wo, True, 0, self._out_mode(plan2))
-        del h
+            if e["skip_conv"] and plan2[0] and self._out_mode(plan1) == self._out_mode(plan2):
+                a1, raw = self._gn_apply(srcs, e["gn1"], B, H, W, True, mode, self._out_mode(plan1), want_raw=True)
+                raw = [raw]
+            elif mode == 1 and not e["skip_conv"] and plan2[0] == 3:
+                # the halo-reuse kernel takes a same-resolution residual: the pass that normalises x also avg-pools it
+                a1, pooled = self._gn_apply(srcs, e["gn1"], B, H, W, True, mode, self._out_mode(plan1), want_raw=True)
+            else:
+                a1 = self._gn_apply(srcs, e["gn1"], B, H, W, True, mode, self._out_mode(plan1))
+            # conv1's output feeds GroupNorm 2 only: stored as fp16 without its per-channel offset where the fast kernel runs
+            h = self._conv(e["conv1"], a1, B, Ho, Wo, e["cout"], plan1, emb=emb,
+                           out_f16=self.h1_f16 and plan1[0] == 3 and plan1[1])
+            del a1
+        if e["skip_conv"] and raw is None and plan2[1]:
+            plan2 = (plan2[0], False)      # no fp16 raw copy available: run conv2 with TF32 operands
+        fuse2 = self.fuse_gn and plan2 == (3, True) and h.shift is not None
+        if fuse2:
+            # GroupNorm 2 + SiLU inside conv2 (the table carries the bias + embedding offset the fp16 h leaves out)
+            tab2 = self._gn_table([h], e["gn2"], B, Ho * Wo)
+            a2, kw = h.t, {"gn_table": tab2}
+        else:
+            a2, kw = self._gn_apply([h], e["gn2"], B, Ho, Wo, True, 0, self._out_mode(plan2)), {}
+            del h
+        kw["want16"] = need16 and self.fuse_gn
         if e["skip_conv"]:
-            rs = [raw] if raw is not None else [x.t for x in srcs]
-            return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], plan2, r=rs), Ho, Wo
+            rs = raw if raw is not None else [x.t for x in srcs]
+            return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], plan2, r=rs, **kw), Ho, Wo
         assert len(srcs) == 1
         if pooled is not None:
-            return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], plan2, res=pooled, res_mode=1), Ho, Wo
+            return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], plan2, res=pooled, res_mode=1, **kw), Ho, Wo
         return self._conv(e["conv2"], a2, B, Ho, Wo, e["cout"], plan2, res=srcs[0].t,
-                          res_mode=_RES_FOR_MODE[e["mode"]]), Ho, Wo
+                          res_mode=_RES_FOR_MODE[e["mode"]], **kw), Ho, Wo
 
     def _attn(self, e, x, B, H, W):
         C, T = e["c"], H * W
@@ -350,14 +399,17 @@ class UNetEngine:
             self.launches += 1
         return self._conv(e["proj"], a, B, H, W, C, plan_proj, res=x.t, res_mode=1)
 
-    def _entry(self, entry, srcs, B, H, W):
+    def _entry(self, entry, srcs, B, H, W, need16=False):
+        """need16: the entry's OUTPUT will be read as a raw fp16 operand (skip tensor of the up path / next entry's conv1)."""
         h = None
-        for e in entry:
+        for i, e in enumerate(entry):
             cur = srcs if h is None else [h]
             if e["kind"] == "stem":
                 raise RuntimeError("stem handled by forward()")
             if e["kind"] == "res":
-                h, H, W = self._res(e, cur, B, H, W)
+                nxt = entry[i + 1] if i + 1 < len(entry) else None
+                want = need16 if nxt is None else (nxt["kind"] == "res" and nxt["mode"] == "same")
+                h, H, W = self._res(e, cur, B, H, W, need16=want)
             else:
                 assert len(cur) == 1
                 h = self._attn(e, cur[0], B, H, W)
@@ -383,8 +435,8 @@ class UNetEngine:
                                           * B * 2 * STAT_REPLICAS, device=x.device, dtype=torch.float64)
             self.stats_used = 0
             h = _T(x.permute(0, 2, 3, 1).contiguous().float())
-            for e in entries:
-                h, H, W = self._res(e, [h], B, H, W)
+            for i, e in enumerate(entries):
+                h, H, W = self._res(e, [h], B, H, W, need16=i + 1 < len(entries))
         return h.t.permute(0, 3, 1, 2).contiguous()
 
     # ------------------------------------------------------------------ forward
@@ -411,6 +463,9 @@ class UNetEngine:
         self.allow_f16 = m.conv_impl == "tc"
         self.tc_min_channels = int(getattr(m, "tc_min_channels", 0)) if m.conv_impl == "tc" else 0
         self.h1_f16 = self.allow_f16 and getattr(m, "h1_fp16", True)
+        # GroupNorm + SiLU applied to the operand boxes inside the 3x3 convs (no normalised copies in HBM)
+        self.fuse_gn = self.h1_f16 and getattr(m, "fuse_gn", True)
+        self.gn_tables = 0
         self.f16_outputs = 0
         self.f16_convs = 0
         self.fused_stats = 0
@@ -453,13 +508,13 @@ class UNetEngine:
         h = _T(h)
         skips = [(h, H, W)]
         for entry in self.down[1:]:
-            h, H, W = self._entry(entry, [h], B, H, W)
+            h, H, W = self._entry(entry, [h], B, H, W, need16=True)      # every down output is a skip tensor of the up path
             skips.append((h, H, W))
-        h, H, W = self._entry(self.middle, [h], B, H, W)
-        for entry in self.up:
+        h, H, W = self._entry(self.middle, [h], B, H, W, need16=True)
+        for i, entry in enumerate(self.up):
             sk, sh, sw = skips.pop()
             assert (sh, sw) == (H, W)
-            h, H, W = self._entry(entry, [h, sk], B, H, W)
+            h, H, W = self._entry(entry, [h, sk], B, H, W, need16=i + 1 < len(self.up))
         hd = self.head
         out = torch.empty((B, m.out_channels, H, W), device=dev, dtype=torch.float32)
         C = h.t.shape[-1]

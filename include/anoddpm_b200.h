@@ -138,6 +138,15 @@ int anoddpm_gn_apply_f16in(void* out, const void* x_f16, int C, const double* st
                            const float* beta, const float* shift_c, const float* shift_bc, int shift_stride, int B, int H,
                            int W, int groups, float eps, int silu, int out_mode, void* stream);
 
+/* Per-(sample, channel) affine form of GroupNorm for the fused operand transform of anoddpm_conv (gn_table):
+ * table[b][c] = (scale, shift) with scale = rstd[b, g(c)] * gamma[c] and shift = beta[c] + (off[b][c] - mean[b, g(c)]) * scale,
+ * so that GroupNorm(x + off)[b, c] = x * scale + shift.  Statistics as in anoddpm_gn_apply (per-channel fp64 sums in
+ * REPLICAS copies, of one tensor or of the concatenation of two); off = shift_c[c] + shift_bc[b][c] (either may be NULL) is
+ * the bias + timestep-embedding row an fp16 conv output left out (see out_f16).  HW = pixels behind each statistic. */
+int anoddpm_gn_table(float* table /* [B][C1+C2][2] */, const double* stats1, int C1, const double* stats2, int C2,
+                     const float* gamma, const float* beta, const float* shift_c, const float* shift_bc, int shift_stride,
+                     int B, int HW, int groups, float eps, void* stream);
+
 /* Convolution as implicit GEMM over NHWC pixels.  out[b,y,x,:] =
  *     conv_k(a)[..] (k = ksize 3 pad 1, or 1)  +  r1 . W_r1  +  r2 . W_r2      (1x1 "skip" sources, optional)
  *   + bias  +  emb[b, :] (optional)  +  residual (optional)
@@ -172,6 +181,16 @@ typedef struct anoddpm_conv_desc {
                            embedding (the half then carries no per-channel offset); gn_stats still describes
                            h = out + bias + emb, and anoddpm_gn_apply_f16in adds the offset back in fp32.  For an output
                            that is consumed by a GroupNorm only (conv1 of a ResBlock, UNet.py:190-200). */
+    /* ---- impl 3, fp16 operands: GroupNorm + SiLU applied to the A operand inside the convolution (UNet.py:170-172,
+     * 190-193: the GN -> SiLU that precedes every 3x3 conv), so no normalised copy of the activation is ever written ---- */
+    const void* a2;         /* optional second main 3x3 source, channel-concatenated after `a` (torch.cat of the up path,
+                               UNet.py:402); Ca2 channels, % 64 == 0 */
+    int Ca2;
+    const float* gn_table;  /* optional [B][Ca + Ca2][2] fp32 (scale, shift) from anoddpm_gn_table: `a` / `a2` hold the RAW
+                               fp16 tensor(s) and the loader rewrites every landed element to SiLU(v * scale + shift) (fp32
+                               math, rounded to nearest fp16) before the tensor cores read it; zero padding stays zero */
+    void* out16;            /* optional fp16 copy of the fp32 output (same NHWC shape): the raw operand of the next
+                               convolution with gn_table, and of a fused 1x1 skip convolution; not with out_f16 */
 } anoddpm_conv_desc;
 int anoddpm_conv(const anoddpm_conv_desc* d /* [host] */, void* stream);
 /* 1 if impl=1/2 (tcgen05 tiles: channels % 32, Cout % 16, power-of-two W) covers the problem, else 0. */

@@ -223,12 +223,102 @@ def test_resblock_with_fused_skip_conv_residual_stream_scale(scale):
     eng = UNetEngine.__new__(UNetEngine)
     eng.launches = eng.fused_stats = eng.stats_passes = eng.tc_convs = eng.f16_convs = eng.f16_outputs = 0
     eng.use_tc, eng.tc_impl, eng.allow_f16, eng.h1_f16, eng.tc_min_channels = True, 3, True, True, 0
+    eng.fuse_gn, eng.gn_tables = True, 0
     eng.emb_w, eng.emb_b, eng.emb_off = [], [], 0
     y = eng.run_resblocks([net.b1, net.b2], x, emb)
     r = rel(y, ref)
     print(f"[parity] ResBlock chain with fused skip conv, residual stream x{scale:g}: rel={r:.3e}")
-    assert eng.f16_convs >= 3
+    assert eng.f16_convs >= 3 and eng.gn_tables >= 3       # GN2 of both blocks and GN1 of the second ran inside the convs
     assert r < 1.5e-3
+
+
+# ---------------------------------------------------------------------------------------------- operand-side GroupNorm
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("shape", [(2, 128, 64, 128, 32, 32), (1, 128, 0, 128, 64, 64), (3, 256, 128, 256, 16, 48),
+                                   (1, 64, 0, 64, 256, 256)], ids=lambda s: "x".join(map(str, s)))
+def test_conv_with_operand_side_groupnorm_vs_torch(shape):
+    """anoddpm_conv(impl 3, gn_table): y = conv3x3(SiLU(GroupNorm(cat(x1, x2)))) + bias + residual from RAW fp16 copies of
+    x1 / x2, with the fp16 copy of the output and its per-channel statistics from the epilogue."""
+    import ctypes
+    import torch.nn.functional as F
+    from anoddpm_b200 import _lib
+    from anoddpm_b200.engine import pack_conv_weight
+    B, C1, C2, Cout, H, W = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x1 = (torch.randn(B, C1, H, W, generator=g) * 1.7 + 0.3).to(DEV)
+    x2 = (torch.randn(B, C2, H, W, generator=g) * 0.6 - 0.2).to(DEV) if C2 else None
+    C = C1 + C2
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).to(DEV), (torch.randn(C, generator=g) * 0.2).to(DEV)
+    w = (torch.randn(Cout, C, 3, 3, generator=g) * (9 * C) ** -0.5).to(DEV)
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    res = torch.randn(B, Cout, H, W, generator=g).to(DEV)
+    REPL = 8
+    x1n, x2n = _nhwc(x1), (_nhwc(x2) if C2 else None)
+    st1 = torch.zeros(REPL * B * C1 * 2, device=DEV, dtype=torch.float64)
+    _lib.call("anoddpm_gn_stats", _lib.ptr(st1), _lib.ptr(x1n), C1, B, H * W, _lib.stream())
+    st2 = None
+    if C2:
+        st2 = torch.zeros(REPL * B * C2 * 2, device=DEV, dtype=torch.float64)
+        _lib.call("anoddpm_gn_stats", _lib.ptr(st2), _lib.ptr(x2n), C2, B, H * W, _lib.stream())
+    tab = torch.empty(B, C, 2, device=DEV)
+    _lib.call("anoddpm_gn_table", _lib.ptr(tab), _lib.ptr(st1), C1, _lib.ptr(st2), C2, _lib.ptr(gamma), _lib.ptr(beta), None, None,
+              0, B, H * W, 32, 1e-5, _lib.stream())
+    a1, a2 = x1n.half(), (x2n.half() if C2 else None)
+    wp = pack_conv_weight(w).contiguous().half()
+    out = torch.empty(B, H, W, Cout, device=DEV)
+    out16 = torch.empty(B, H, W, Cout, device=DEV, dtype=torch.float16)
+    stats = torch.zeros(REPL * B * Cout * 2, device=DEV, dtype=torch.float64)
+    resn = _nhwc(res)
+    d = _lib.ConvDesc()
+    d.out, d.a, d.w, d.bias = out.data_ptr(), a1.data_ptr(), wp.data_ptr(), bias.data_ptr()
+    d.B, d.H, d.W, d.Ca, d.Cout, d.ksize = B, H, W, C1, Cout, 3
+    if C2:
+        d.a2, d.Ca2 = a2.data_ptr(), C2
+    d.gn_table, d.out16, d.gn_stats = tab.data_ptr(), out16.data_ptr(), stats.data_ptr()
+    d.res, d.res_mode = resn.data_ptr(), 1
+    d.impl, d.operand_f16 = 3, 1
+    assert _lib.lib().anoddpm_conv_tc3_supported(ctypes.byref(d))
+    _lib.call("anoddpm_conv", ctypes.byref(d), _lib.stream())
+    torch.cuda.synchronize()
+    y = out.permute(0, 3, 1, 2)
+    xc = torch.cat([x1] + ([x2] if C2 else []), dim=1)
+    ref = F.conv2d(F.silu(F.group_norm(xc, 32, gamma, beta, 1e-5)), w, bias, padding=1) + res
+    r = rel(y, ref)
+    print(f"[parity] conv with operand-side GroupNorm {shape}: rel={r:.3e}")
+    assert r < 1e-3
+    assert torch.equal(out16, out.half())
+    s = stats.view(REPL, B, Cout, 2).sum(0)
+    assert torch.allclose(s[..., 0], out.double().sum(dim=(1, 2)), rtol=1e-6, atol=1e-3)
+    assert torch.allclose(s[..., 1], (out.double() ** 2).sum(dim=(1, 2)), rtol=1e-6, atol=1e-3)
+
+
+def test_base256_fused_groupnorm_path_matches_unfused_and_golden(golden):
+    """BASELINE model: the default path (GroupNorm + SiLU inside the convs) against the reference golden and against the
+    stand-alone-pass path (ANODDPM_FUSE_GN=0 equivalent)."""
+    g = golden("unet")
+    m = build_model(BASE256, "tc")
+    x = torch.randn(1, 1, 256, 256, generator=torch.Generator().manual_seed(6)).to(DEV)
+    t = torch.from_numpy(g["base256/t"]).to(DEV)
+    crop = torch.from_numpy(g["base256/y_crop"]).to(DEV)
+    scale = float(g["base256/y_stats"][2])
+    errs = {}
+    for fuse in (True, False):
+        m.fuse_gn = fuse
+        with torch.no_grad():
+            y = m(x, t)
+        errs[fuse] = float((y[0, 0, 100:132, 64:128] - crop).abs().max()) / scale
+        eng = m.engine()
+        if fuse:
+            assert eng.gn_tables >= 50, eng.gn_tables
+            launches_fused = eng.launches_per_forward
+        else:
+            assert eng.gn_tables == 0
+    print(f"[parity] base256 tc: fused-GN rel={errs[True]:.3e}  separate-pass rel={errs[False]:.3e}  "
+          f"launches {launches_fused} vs {eng.launches_per_forward}")
+    assert errs[True] < 1e-3 and errs[False] < 1e-3
 
 
 # ---------------------------------------------------------------------------------------------- advisor regressions
