@@ -38,6 +38,8 @@ SIGNATURES = {
     "anoddpm_p_sample": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
     "anoddpm_detection_counts": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_int, c_i64, c_vp]),
     "anoddpm_vlb_terms": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
+    "anoddpm_conv_wgrad_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "anoddpm_conv_wgrad": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp]),
     "anoddpm_sumsq": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "anoddpm_adamw_ema_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_int,
                                        c_f32, c_f32, c_vp]),

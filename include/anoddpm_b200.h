@@ -225,6 +225,19 @@ long long anoddpm_attention_tc_workspace_bytes(int B, int T, int C);
 int anoddpm_attention_tc(void* out, const float* qkv, void* workspace, int B, int T, int C, int heads, int out_mode,
                          void* stream);
 
+/* ------------------------------------------------------------------ training: backward kernels ------------- */
+
+/* Weight gradient of a 3x3 (padding 1) or 1x1 convolution on tcgen05 tensor cores (what autograd computes for
+ * nn.Conv2d / nn.Conv1d weights in loss.backward(), diffusion_training.py:101; UNet.py:170-200, 115-118):
+ *     dw[co][tap][ci] += alpha * sum_{b,y,x} dy[b,y,x,co] * a[b, y+ty-1, x+tx-1, ci]       (tap = 3*ty + tx; 1x1: tap 0)
+ * dy, a: NHWC fp16 (the operands stay channel-contiguous: MN-major UMMA descriptors, no transposed copies); dw: fp32,
+ * packed like the forward weights ([Cout][ksize^2][Cin]), ACCUMULATED (split-K partial sums are added with atomics, so
+ * the caller zeroes it or passes a running gradient).  alpha = 1 / loss scale.
+ * Needs Cin, Cout % 128 == 0, H % 8 == 0 and W == 8 or W % 16 == 0 (anoddpm_conv_wgrad_supported). */
+int anoddpm_conv_wgrad_supported(int B, int H, int W, int Cin, int Cout, int ksize);
+int anoddpm_conv_wgrad(float* dw, const void* dy_f16, const void* a_f16, int B, int H, int W, int Cin, int Cout, int ksize,
+                       float alpha, void* stream);
+
 /* ------------------------------------------------------------------ training: fused optimiser step -------- */
 
 /* *out += sum(g[i]^2) in fp64 (caller zeroes).  First half of torch.nn.utils.clip_grad_norm_ (diffusion_training.py:104). */
