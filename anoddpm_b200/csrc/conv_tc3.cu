@@ -51,7 +51,8 @@ constexpr int kStgBytes = kEpiWarps * 2 * kStgBuf;  // 8 epilogue warps x 2 buff
 constexpr int kBeBytes = kEpiWarps * 128 * 4;       // per-warp (bias + embedding) row of the current tile
 constexpr int kStg16Buf = 32 * 32;                  // fp16 copy of a step: 32 pixel rows x 16 halves, no swizzle
 constexpr int kStg16Bytes = kEpiWarps * 2 * kStg16Buf;
-constexpr int kThreadsGN = 512;                     // + warps 12-15: operand transform (GroupNorm + SiLU on the landed A box)
+constexpr int kTransformWarps = 8;                  // two per scheduler: the transform is MUFU-bound (ex2 + rcp per element)
+constexpr int kThreadsGN = 384 + 32 * kTransformWarps;   // + warps 12..: operand transform (GroupNorm + SiLU on the landed A box)
 
 struct Tc3Args {
     void* out;
@@ -177,9 +178,21 @@ __device__ __forceinline__ uint4 lds128u(uint32_t a) {
 __device__ __forceinline__ void sts128u(uint32_t a, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// two fp32 -> one half2 word (a in the low half), round to nearest, saturating at +-65504: one F2FP.SATFINITE
 __device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
-    const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
-    return *reinterpret_cast<const uint32_t*>(&h);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 // plain (per-CTA) TMA load / store used by the epilogue
 __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
@@ -292,7 +305,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * 32 * kEpiWarps); }
         for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
         // GN: a_full collects one arrival per transform warp of both CTAs (4 + 4) instead of the two producers
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], GN ? 8 : 2); mbar_init(&a_empty[i], 1); mbar_init(&a_land[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], GN ? 2 * kTransformWarps : 2); mbar_init(&a_empty[i], 1); mbar_init(&a_land[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -543,6 +556,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // Pixels outside the image keep TMA's zero fill: the convolution pads AFTER normalisation + activation.
         const int tid = (warp - 12) * 32 + lane;
         const int j = tid & 7, rl = tid >> 3;
+        constexpr int kRowLanes = kTransformWarps * 4;
         const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
         int ac = 0;
         for (int tile = tile_first; tile < tile_end; tile += tile_step) {
@@ -563,11 +577,17 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 mbar_wait(&a_land[ab], (ac >> 1) & 1);
                 if (work) {
                     const uint32_t a_base = smem_u32(sA + ab * kBoxStride);
+                    // y = v * sc + sh;  SiLU(y) = y / (1 + 2^(v * nsc + nsh)) with (nsc, nsh) = -log2(e) * (sc, sh)
                     const float sc[8] = {t4[0].x, t4[0].z, t4[1].x, t4[1].z, t4[2].x, t4[2].z, t4[3].x, t4[3].z};
                     const float sh[8] = {t4[0].y, t4[0].w, t4[1].y, t4[1].w, t4[2].y, t4[2].w, t4[3].y, t4[3].w};
-#pragma unroll 3
-                    for (int r = rl; r < 18 * 18; r += 16) {
-                        const int py = r / 18, px = r - py * 18;
+                    float nsc[8], nsh[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { nsc[e] = sc[e] * -1.4426950408889634f; nsh[e] = sh[e] * -1.4426950408889634f; }
+                    // rows of this thread: r = rl + kRowLanes * i; (py, px) advance incrementally (no division in the loop)
+                    int py = rl / 18, px = rl - py * 18;
+                    constexpr int kDy = kRowLanes / 18, kDx = kRowLanes - 18 * kDy;
+#pragma unroll 2
+                    for (int r = rl; r < 18 * 18; r += kRowLanes) {
                         if ((unsigned)(y0 - 1 + py) < (unsigned)P.H && (unsigned)(x0 - 1 + px) < (unsigned)P.W) {
                             const uint32_t addr = a_base + (uint32_t)r * kRowBytes + (uint32_t)((j ^ (r & 7)) << 4);
                             uint4 v = lds128u(addr);
@@ -575,11 +595,15 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(&vw[e]));
-                                const float y0f = fmaf(fv.x, sc[2 * e], sh[2 * e]), y1f = fmaf(fv.y, sc[2 * e + 1], sh[2 * e + 1]);
-                                vw[e] = pack_half2_sat(__fdividef(y0f, 1.0f + __expf(-y0f)), __fdividef(y1f, 1.0f + __expf(-y1f)));
+                                const float ya = fmaf(fv.x, sc[2 * e], sh[2 * e]), yb = fmaf(fv.y, sc[2 * e + 1], sh[2 * e + 1]);
+                                const float da = 1.0f + ex2_approx(fmaf(fv.x, nsc[2 * e], nsh[2 * e]));
+                                const float db = 1.0f + ex2_approx(fmaf(fv.y, nsc[2 * e + 1], nsh[2 * e + 1]));
+                                vw[e] = pack_half2_sat(ya * rcp_approx(da), yb * rcp_approx(db));
                             }
                             sts128u(addr, v);
                         }
+                        px += kDx; py += kDy;
+                        if (px >= 18) { px -= 18; ++py; }
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

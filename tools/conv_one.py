@@ -15,17 +15,34 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from anoddpm_b200 import _lib          # noqa: E402
 
 
-def run(a, B, Ci, Co, HW, res, stats, emb, cr=0, n=10):
+def run(a, B, Ci, Co, HW, res, stats, emb, cr=0, n=10, gn=False, out16=False, out_f16=False, ci2=0):
     dev = torch.device("cuda:0")
-    x = torch.randn(B, HW, HW, Ci, device=dev).half()
+    x = torch.randn(B, HW, HW, Ci - ci2, device=dev).half()
     w = (torch.randn(Co, 9 * Ci + cr, device=dev) * 0.03).half()
     r1 = torch.randn(B, HW, HW, cr, device=dev).half() if cr else None
     bias = torch.randn(Co, device=dev)
     out = torch.empty(B, HW, HW, Co, device=dev)
     d = _lib.ConvDesc()
     d.out, d.a, d.w, d.bias = out.data_ptr(), x.data_ptr(), w.data_ptr(), bias.data_ptr()
-    d.B, d.H, d.W, d.Ca, d.Cout, d.ksize, d.impl = B, HW, HW, Ci, Co, 3, a.impl
+    d.B, d.H, d.W, d.Ca, d.Cout, d.ksize, d.impl = B, HW, HW, Ci - ci2, Co, 3, a.impl
     d.operand_f16 = 1
+    keep0 = []
+    if ci2:
+        x2 = torch.randn(B, HW, HW, ci2, device=dev).half()
+        keep0.append(x2)
+        d.a2, d.Ca2 = x2.data_ptr(), ci2
+    if gn:      # operand-side GroupNorm + SiLU: (scale, shift) table
+        tab = torch.stack([torch.rand(B, Ci, device=dev) + 0.5, torch.randn(B, Ci, device=dev) * 0.3], dim=-1).contiguous()
+        keep0.append(tab)
+        d.gn_table = tab.data_ptr()
+    if out16:
+        o16 = torch.empty(B, HW, HW, Co, device=dev, dtype=torch.float16)
+        keep0.append(o16)
+        d.out16 = o16.data_ptr()
+    if out_f16:
+        out = torch.empty(B, HW, HW, Co, device=dev, dtype=torch.float16)
+        d.out = out.data_ptr()
+        d.out_f16 = 1
     if cr:
         d.r1, d.Cr1 = r1.data_ptr(), cr
     keep = []
@@ -77,6 +94,15 @@ def main():
                                           ("+skip1x1(256)+stats", 0, True, False, 256)):
             ms, tf = run(a, a.batch, a.ci, a.co, a.hw, res, stats, emb, cr)
             print(f"| {name} | {ms:.3f} | {tf:.0f} |")
+        # production epilogues of a ResBlock, without / with the operand-side GroupNorm
+        for name, kw in (("conv1: +emb+stats, fp16 out", dict(res=0, stats=True, emb=True, out_f16=True)),
+                         ("conv1 GN: same, operand-side GroupNorm", dict(res=0, stats=True, emb=True, out_f16=True, gn=True)),
+                         ("conv2: +res1+stats", dict(res=1, stats=True, emb=False)),
+                         ("conv2 +fp16 copy", dict(res=1, stats=True, emb=False, out16=True)),
+                         ("conv2 GN: +res1+stats+fp16 copy, operand-side GroupNorm", dict(res=1, stats=True, emb=False, out16=True, gn=True)),
+                         ("conv2 GN, no fp16 copy", dict(res=1, stats=True, emb=False, gn=True))):
+            ms, tf = run(a, a.batch, a.ci, a.co, a.hw, **kw)
+            print(f"| {name} | {ms:.3f} | {tf:.0f} |", flush=True)
     else:
         ms, tf = run(a, a.batch, a.ci, a.co, a.hw, a.res, a.stats, a.emb, a.cr)
         print(f"{ms:.3f} ms  {tf:.0f} TFLOP/s")
