@@ -29,8 +29,8 @@ def test_conv_wgrad_vs_torch(shape, dx_boxes, monkeypatch):
     B, H, W, Cin, Cout, k = shape
     if k == 1 and dx_boxes:
         pytest.skip("1x1 has a single tap")
-    if B * H * W > 100000 and dx_boxes:
-        pytest.skip("large case once")
+    if dx_boxes and (W >= 16 or B * H * W > 100000):
+        pytest.skip("box-per-tap cross-check: 8-pixel-wide tiles only (three 16-pixel boxes per stage exceed shared memory)")
     monkeypatch.setenv("ANODDPM_WGRAD_DX_BOXES", str(dx_boxes))
     g = torch.Generator().manual_seed(sum(shape))
     a = torch.randn(B, H, W, Cin, generator=g).half().to(DEV)

@@ -75,10 +75,15 @@ def test_base256_batched_multistep_chain_vs_oracle():
     assert max(errs) < 1e-3, errs
 
 
-def test_base256_batch_invariance():
-    """sample b of a bs-8 forward equals its own bs-1 forward (tile runs that cross sample boundaries, register-held
-    statistics, 8 statistic replicas): only the order of fp64 atomics may differ."""
-    m = build_model(BASE256, "tc")
+@pytest.mark.parametrize("impl", ["exact", "tc"])
+def test_base256_batch_invariance(impl):
+    """sample b of a bs-8 forward against its own bs-1 forward (tile runs that cross sample boundaries, register-held
+    statistics flushed per sample, 8 statistic replicas).  The two runs add up the GroupNorm statistics in a different
+    order (1e-7 relative); the exact path carries that to ~1.5e-6 at the output.  On the tensor-core paths the same
+    perturbation moves a few operands across a 10-bit rounding boundary in every layer, so the two runs are two realisations
+    of the path's own rounding noise: measured 4-6e-4 on tc / tc_tf32 / tc2 alike (tools/bisect_batch_inv.py), the level
+    of the path's error against the fp32 reference -- a statistics or tiling bug would be orders of magnitude above it."""
+    m = build_model(BASE256, impl)
     g = torch.Generator().manual_seed(8)
     x = torch.randn(8, 1, 256, 256, generator=g).to(DEV)
     t = torch.tensor([999, 0, 431, 7, 250, 800, 1, 500], device=DEV)
@@ -88,8 +93,8 @@ def test_base256_batch_invariance():
         for b in (0, 3, 7):
             y1 = m(x[b:b + 1], t[b:b + 1])
             worst = max(worst, rel(yb[b:b + 1], y1))
-    print(f"[parity] base256 batch invariance (bs 8 vs bs 1): {worst:.3e}")
-    assert worst < 2e-5
+    print(f"[parity] base256 batch invariance impl={impl} (bs 8 vs bs 1): {worst:.3e}")
+    assert worst < (5e-6 if impl == "exact" else 1e-3)
 
 
 # ---------------------------------------------------------------------------------------------- (c) loss path goldens
@@ -188,7 +193,9 @@ def test_calc_total_vlb_vs_reference_golden(golden, impl, monkeypatch):
     bank = iter(torch.randn(T, 3, 1, 32, 32, generator=torch.Generator().manual_seed(31)).to(DEV))
     monkeypatch.setattr(torch, "randn_like", lambda x, *a, **k: next(bank))
     r = D.calc_total_vlb(x0, m, {"Batch_Size": 3})
-    worst = {k: rel(v.cpu(), torch.from_numpy(g[f"total_vlb/{k}"])) for k, v in r.items()}
+    worst = {k: rel(v.cpu(), torch.from_numpy(g[f"total_vlb/{k}"])) for k, v in r.items() if k != "prior_vlb"}
+    # prior_vlb = KL(q(x_T|x_0) || N(0,1)) ~ 1e-7 bits/dim here: a difference of nearly equal numbers, compared absolutely
+    assert float((r["prior_vlb"].cpu() - torch.from_numpy(g["total_vlb/prior_vlb"])).abs().max()) < 1e-6
     print(f"[parity] calc_total_vlb impl={impl}:", {k: f"{v:.2e}" for k, v in worst.items()})
     assert set(r) == {"total_vlb", "prior_vlb", "vb", "x_0_mse", "mse"}
     assert max(worst.values()) < (5e-5 if impl == "exact" else 3e-3)
