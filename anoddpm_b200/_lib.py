@@ -40,6 +40,18 @@ SIGNATURES = {
     "anoddpm_vlb_terms": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
     "anoddpm_conv_wgrad_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "anoddpm_conv_wgrad": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp]),
+    "anoddpm_gn_silu_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                    c_vp, c_int, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_int, c_int,
+                                    c_f32, c_vp]),
+    "anoddpm_cast_colsum": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_f32, c_vp]),
+    "anoddpm_colsum_f16": (c_int, [c_vp, c_vp, c_i64, c_int, c_f32, c_vp]),
+    "anoddpm_gemm_batched": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_i64, c_i64, c_i64, c_i64, c_i64, c_int, c_int,
+                                     c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_vp]),
+    "anoddpm_softmax_rows": (c_int, [c_vp, c_i64, c_int, c_vp]),
+    "anoddpm_softmax_bwd_rows": (c_int, [c_vp, c_vp, c_i64, c_int, c_vp]),
+    "anoddpm_silu_bwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "anoddpm_stem_wgrad": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_vp]),
+    "anoddpm_head_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_vp]),
     "anoddpm_sumsq": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "anoddpm_adamw_ema_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_int,
                                        c_f32, c_f32, c_vp]),

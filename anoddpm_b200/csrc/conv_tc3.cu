@@ -79,6 +79,8 @@ struct Tc3Args {
     int c_tab;                 // Ca1 + Ca2
     int chunks_a1;             // chunks of the first main source; chunks_a - chunks_a1 come from the second (torch.cat)
     int has_out16;             // the epilogue also stores an fp16 copy of the fp32 output
+    int dbg;                   // ANODDPM_TC3_DBG (attribution runs only): 1 = transform warps only forward the barrier,
+                               // 2 = read the box but do not write it back, 3 = scale + shift without the SiLU (no MUFU)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -567,7 +569,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const bool live = R < P.n_regions;
             for (int c = 0; c < nchunks; ++c, ++ac) {
                 const int ab = ac & 1;
-                const bool work = live && c < P.chunks_a;
+                const bool work = live && c < P.chunks_a && P.dbg != 1;
                 float4 t4[4];
                 if (work) {   // table row of this thread's 8 channels: issued before the wait, it does not depend on the box
                     const float4* tp = reinterpret_cast<const float4*>(P.gn_table + (size_t)b0 * P.c_tab + c * 64 + 8 * j);
@@ -598,9 +600,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                 const float ya = fmaf(fv.x, sc[2 * e], sh[2 * e]), yb = fmaf(fv.y, sc[2 * e + 1], sh[2 * e + 1]);
                                 const float da = 1.0f + ex2_approx(fmaf(fv.x, nsc[2 * e], nsh[2 * e]));
                                 const float db = 1.0f + ex2_approx(fmaf(fv.y, nsc[2 * e + 1], nsh[2 * e + 1]));
-                                vw[e] = pack_half2_sat(ya * rcp_approx(da), yb * rcp_approx(db));
+                                vw[e] = P.dbg == 3 ? pack_half2_sat(ya, yb) : pack_half2_sat(ya * rcp_approx(da), yb * rcp_approx(db));
                             }
-                            sts128u(addr, v);
+                            if (P.dbg != 2 || vw[0] == 0x7fff7fffu) sts128u(addr, v);
                         }
                         px += kDx; py += kDy;
                         if (px >= 18) { px -= 18; ++py; }
@@ -1060,6 +1062,7 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     P.gn_table = reinterpret_cast<const float2*>(d->gn_table);
     P.c_tab = P.Ca;
     P.has_out16 = d->out16 ? 1 : 0;
+    { const char* e = getenv("ANODDPM_TC3_DBG"); P.dbg = e ? atoi(e) : 0; }
     P.BN = d->Cout < 128 ? d->Cout : 128;
     const int acc_cols = kAccStages * 2 * P.BN;
     P.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;

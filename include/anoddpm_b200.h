@@ -238,6 +238,44 @@ int anoddpm_conv_wgrad_supported(int B, int H, int W, int Cin, int Cout, int ksi
 int anoddpm_conv_wgrad(float* dw, const void* dy_f16, const void* a_f16, int B, int H, int W, int Cin, int Cout, int ksize,
                        float alpha, void* stream);
 
+/* Backward of out = resample(act(GroupNorm(cat(x1, x2) [+ shift]))) (the forward of anoddpm_gn_apply /
+ * anoddpm_gn_apply_f16in; UNet.py:170-172, 190-193, 202-210), two passes over x and da:
+ *   pass 1: sums[b][c] = (sum_p g, sum_p g * xhat), g = gradient wrt the GroupNorm output (da through the resample and
+ *           SiLU'), pass 2: dx = rstd * (g * gamma - mean_group(g * gamma) - xhat * mean_group(g * gamma * xhat)) (+ addend).
+ * x1: fp32 NHWC, or fp16 (x1_f16: the conv sum stored by out_f16; shift_c / shift_bc as in anoddpm_gn_apply_f16in; dx1 is
+ * then fp16 and dsum[b][c] += sum_p dx -- the gradient of the per-(sample, channel) shift, i.e. of bias + embedding row).
+ * da: [B][Ho][Wo][C1+C2] fp16 or fp32 at the OUTPUT resolution of `mode`.  add: gradient reaching x on the skip path
+ * (add_mode 1 same resolution, 2 half resolution: x was avg-pooled there, 3 double resolution: x was upsampled there).
+ * dgamma / dbeta (+= alpha * ...) may be NULL.  sums_ws: caller-owned B * C * 2 floats.  All activation gradients carry
+ * the loss scale; alpha = 1 / scale un-scales the parameter gradients. */
+int anoddpm_gn_silu_bwd(void* dx1, float* dx2, float* dgamma, float* dbeta, float* dsum, float* sums_ws, const void* x1,
+                        int x1_f16, int C1, const float* x2, int C2, const double* stats1, const double* stats2,
+                        const float* gamma, const float* beta, const float* shift_c, const float* shift_bc, int shift_stride,
+                        const void* da, int da_f16, const void* add, int add_mode, int add_f16, int B, int H, int W,
+                        int groups, float eps, int silu, int mode, float alpha, void* stream);
+
+/* y = half(x * scale) (y may be NULL) and colsum[c] += alpha * sum_n x[n][c] (colsum may be NULL) for x fp32 [N][C]: the
+ * fp16 operand copy of an output gradient and the bias gradient of the convolution that produced the output, one pass. */
+int anoddpm_cast_colsum(void* y_f16, const float* x, float* colsum, int64_t N, int C, float scale, float alpha, void* stream);
+int anoddpm_colsum_f16(float* colsum, const void* x_f16, int64_t N, int C, float alpha, void* stream);
+
+/* Strided batched fp32 GEMM on CUDA cores: C[z](m, n) (+)= alpha * sum_k A[z](m, k) * B[z](k, n), element strides
+ * (a_ms, a_ks), (b_ks, b_ns), ldc; batch z = z1 * n2 + z2 with per-matrix strides.  The attention core backward
+ * (UNet.py:137-153: dV = P^T dO, dP = dO V^T, dQ = dL K, dK = dL^T Q) and the small timestep-MLP gradients. */
+int anoddpm_gemm_batched(float* c, const float* a, const float* b, int M, int N, int K, int64_t a_ms, int64_t a_ks,
+                         int64_t b_ks, int64_t b_ns, int64_t ldc, int n1, int n2, int64_t a_s1, int64_t a_s2, int64_t b_s1,
+                         int64_t b_s2, int64_t c_s1, int64_t c_s2, float alpha, int accumulate, void* stream);
+/* rows of length L: softmax in place; dl = p * (dp - <dp, p>) written over dp */
+int anoddpm_softmax_rows(float* s, int64_t rows, int L, void* stream);
+int anoddpm_softmax_bwd_rows(float* dp, const float* p, int64_t rows, int L, void* stream);
+/* dx = dy * SiLU'(x), elementwise */
+int anoddpm_silu_bwd(float* dx, const float* dy, const float* x, int64_t n, void* stream);
+/* Stem conv (Cin = 1, UNet.py:279-281): dw[co][tap] += alpha * sum dy[b,p,co] * x[b,p+tap]; dy NHWC fp16, x NCHW fp32. */
+int anoddpm_stem_wgrad(float* dw, const void* dy_f16, const float* x, int B, int H, int W, int Cout, float alpha, void* stream);
+/* Head conv (Cout = 1, UNet.py:384-388): da (NHWC fp16) = dy (*) w^T, dw[tap][ci] += alpha * sum dy * a, dbias += alpha * sum dy. */
+int anoddpm_head_bwd(void* da_f16, float* dw, float* dbias, const float* dy, const void* a_f16, const float* w, int B, int H,
+                     int W, int C, float alpha, void* stream);
+
 /* ------------------------------------------------------------------ training: fused optimiser step -------- */
 
 /* *out += sum(g[i]^2) in fp64 (caller zeroes).  First half of torch.nn.utils.clip_grad_norm_ (diffusion_training.py:104). */

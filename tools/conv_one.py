@@ -85,7 +85,19 @@ def main():
     ap.add_argument("--stats", action="store_true")
     ap.add_argument("--emb", action="store_true")
     ap.add_argument("--variants", action="store_true")
+    ap.add_argument("--gn-attrib", action="store_true", help="attribute the operand-transform overhead (ANODDPM_TC3_DBG)")
     a = ap.parse_args()
+    if a.gn_attrib:
+        print(f"| conv1 GN {a.ci}->{a.co} @{a.hw}^2 bs{a.batch}: transform variant | ms | TFLOP/s |\n|---|---:|---:|")
+        for name, dbg in (("full transform", "0"), ("barrier forwarding only", "1"), ("read box, no write-back", "2"),
+                          ("scale+shift only (no MUFU)", "3")):
+            os.environ["ANODDPM_TC3_DBG"] = dbg
+            ms, tf = run(a, a.batch, a.ci, a.co, a.hw, res=0, stats=True, emb=True, out_f16=True, gn=True)
+            print(f"| {name} | {ms:.3f} | {tf:.0f} |", flush=True)
+        os.environ["ANODDPM_TC3_DBG"] = "0"
+        ms, tf = run(a, a.batch, a.ci, a.co, a.hw, res=0, stats=True, emb=True, out_f16=True)
+        print(f"| no operand transform (plain conv1) | {ms:.3f} | {tf:.0f} |")
+        return
     if a.variants:
         print(f"| conv {a.ci}->{a.co} @{a.hw}^2 bs{a.batch} impl{a.impl} fp16 | ms | TFLOP/s |\n|---|---:|---:|")
         for name, res, stats, emb, cr in (("plain", 0, False, False, 0), ("+stats", 0, True, False, 0),
