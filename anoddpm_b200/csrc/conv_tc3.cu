@@ -44,7 +44,8 @@ constexpr int kABytes = 2 * kSubBytes;              // two subtiles per CTA
 constexpr int kBoxBytes = 18 * 18 * kRowBytes;      // single-box main loop: one (K-block, 18 px, 18 rows) box = both subtiles + halo
 constexpr int kBoxStride = 41 * 1024;               // 1024-byte aligned buffer stride (41,472 B used)
 constexpr int kAccStages = 2;
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 8;                       // weight-ring barriers (4 (chunk, dy) stages; GN variant: up to 8 single-tap stages)
+constexpr int kNA = 3;                              // GN variant: A boxes in flight (load + transform latency exceeds one chunk of MMAs)
 constexpr int kEpiWarps = 8;
 constexpr int kStgBuf = 32 * 64;                    // one epilogue buffer: 32 pixel rows x 16 fp32 channels, SWIZZLE_64B
 constexpr int kStgBytes = kEpiWarps * 2 * kStgBuf;  // 8 epilogue warps x 2 buffers
@@ -262,8 +263,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int S = P.stages;
     // multi-box: [S][2 subtiles][kSubBytes] then [S][3 taps][b_bytes]; single-box: [2][kBoxStride] then [S][3 taps][b_bytes]
     uint8_t* sA = smem;
-    uint8_t* sB = smem + (P.single_box ? 2 * kBoxStride : S * kABytes);
-    uint8_t* stg_all = sB + S * 3 * b_bytes;       // [8 warps][2][kStgBuf], 1024-byte aligned (ring sizes are multiples)
+    // GN variant: [3][kBoxStride] then [S single-tap weight stages][b_bytes]
+    uint8_t* sB = smem + (GN ? kNA * kBoxStride : (P.single_box ? 2 * kBoxStride : S * kABytes));
+    uint8_t* stg_all = sB + (GN ? S : S * 3) * b_bytes;   // [8 warps][2][kStgBuf], 1024-byte aligned (ring sizes are multiples)
     uint8_t* stg16_all = stg_all + kStgBytes;      // [8 warps][2][kStg16Buf] when the fp16 copy is requested
     float* be_all = reinterpret_cast<float*>(stg16_all + (P.has_out16 ? kStg16Bytes : 0));   // [8 warps][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(be_all) + kBeBytes);
@@ -272,10 +274,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]   both CTAs (multicast commit)
     uint64_t* tmem_empty = tmem_full + kAccStages; // [2]   leader only, 2 x 256 arrivals
     uint64_t* res_bar = tmem_empty + kAccStages;   // [8 warps][2] residual box landed
-    uint64_t* a_full = res_bar + 2 * kEpiWarps;    // [2]   single-box main loop: A box landed (leader only)
-    uint64_t* a_empty = a_full + 2;                // [2]   both CTAs (multicast commit)
-    uint64_t* a_land = a_empty + 2;                // [2]   GN: this CTA's raw A box landed (per CTA)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_land + 2);
+    uint64_t* a_full = res_bar + 2 * kEpiWarps;    // [3]   single-box main loop: A box landed / transformed (leader only)
+    uint64_t* a_empty = a_full + kNA;              // [3]   both CTAs (multicast commit)
+    uint64_t* a_land = a_empty + kNA;              // [3]   GN: this CTA's raw A box landed (per CTA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_land + kNA);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
@@ -307,7 +309,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * 32 * kEpiWarps); }
         for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
         // GN: a_full collects one arrival per transform warp of both CTAs (4 + 4) instead of the two producers
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], GN ? 2 * kTransformWarps : 2); mbar_init(&a_empty[i], 1); mbar_init(&a_land[i], 1); }
+        for (int i = 0; i < kNA; ++i) { mbar_init(&a_full[i], GN ? 2 * kTransformWarps : 2); mbar_init(&a_empty[i], 1); mbar_init(&a_land[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -337,38 +339,32 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const int n0 = nt * P.BN + (int)rank * (P.BN / 2);
                     const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
                     for (int c = 0; c < nchunks; ++c, ++ac) {
-                        const int ab = ac & 1;
+                        const int ab = ac % kNA;
                         uint8_t* a_dst = sA + ab * kBoxStride;
-                        mbar_wait(&a_empty[ab], ((ac >> 1) & 1) ^ 1);
-                        if (c < P.chunks_a) {
+                        mbar_wait(&a_empty[ab], ((ac / kNA) & 1) ^ 1);
+                        const bool main_src = c < P.chunks_a;
+                        const int cs = c - P.chunks_a;
+                        if (main_src) {
                             const bool first = c < P.chunks_a1;
                             mbar_expect_tx(&a_land[ab], (uint32_t)kBoxBytes);
                             tma_load_4d(a_dst, first ? &map_a : &map_a2, &a_land[ab], (first ? c : c - P.chunks_a1) * P.ke,
                                         x0 - 1, y0 - 1, b0);
-                            for (int dy = 0; dy < 3; ++dy, ++bc) {
-                                const int s = bc % S;
-                                mbar_wait(&empty[s], ((bc / S) & 1) ^ 1);
-                                uint8_t* b_dst = sB + s * 3 * b_bytes;
-                                if (leader) mbar_expect_tx(&full[s], 2u * 3u * (uint32_t)b_bytes);
-                                else mbar_arrive_remote(&full[s], 0);
-#pragma unroll
-                                for (int dx = 0; dx < 3; ++dx)
-                                    tma2_load_2d(b_dst + dx * b_bytes, &map_w, &full[s], (dy * 3 + dx) * P.Ca + c * P.ke, n0);
-                            }
                         } else {
-                            const int cs = c - P.chunks_a;
                             const bool first = cs < P.chunks_r1;
                             const CUtensorMap* am = first ? &map_r1 : &map_r2;
                             const int c0 = (first ? cs : cs - P.chunks_r1) * P.ke;
                             mbar_expect_tx(&a_land[ab], 2u * (16 * 8 * kRowBytes));
                             tma_load_4d(a_dst, am, &a_land[ab], c0, x0, y0, b0);
                             tma_load_4d(a_dst + 16 * 8 * kRowBytes, am, &a_land[ab], c0, x0 + 8, y0, b0);
+                        }
+                        // single-tap weight stages (8 KB each per CTA): finer ring, same bytes as two (chunk, dy) stages
+                        const int ntap = main_src ? 9 : 1;
+                        for (int tap = 0; tap < ntap; ++tap, ++bc) {
                             const int s = bc % S;
                             mbar_wait(&empty[s], ((bc / S) & 1) ^ 1);
                             if (leader) mbar_expect_tx(&full[s], 2u * (uint32_t)b_bytes);
                             else mbar_arrive_remote(&full[s], 0);
-                            tma2_load_2d(sB + s * 3 * b_bytes, &map_w, &full[s], 9 * P.Ca + cs * P.ke, n0);
-                            ++bc;
+                            tma2_load_2d(sB + s * b_bytes, &map_w, &full[s], main_src ? tap * P.Ca + c * P.ke : 9 * P.Ca + cs * P.ke, n0);
                         }
                     }
                 }
@@ -464,7 +460,53 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.BN >> 3) << 17) |
                                    ((uint32_t)(256 >> 4) << 24);
             int kbc = 0, it = 0;
-            if (P.single_box) {
+            if (GN) {
+                int bc = 0, ac = 0;
+                const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
+                for (int tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
+                    const int acc = it & 1;
+                    mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t tmem_d0 = tmem_base + (uint32_t)((acc * 2 + 0) * P.BN);
+                    const uint32_t tmem_d1 = tmem_base + (uint32_t)((acc * 2 + 1) * P.BN);
+                    for (int c = 0; c < nchunks; ++c, ++ac) {
+                        const int ab = ac % kNA;
+                        mbar_wait(&a_full[ab], (ac / kNA) & 1);
+                        const uint32_t a_base = smem_u32(sA + ab * kBoxStride);
+                        const bool main_src = c < P.chunks_a;
+                        const int ntap = main_src ? 9 : 1;
+                        for (int tap = 0; tap < ntap; ++tap, ++bc) {
+                            const int s = bc % S;
+                            mbar_wait(&full[s], (bc / S) & 1);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            if (elect_one()) {
+                                const uint64_t bd = make_sdesc(smem_u32(sB + s * b_bytes));
+                                uint64_t ad0, ad1;
+                                if (main_src) {
+                                    const int dy = tap / 3, dx = tap - 3 * dy;
+                                    ad0 = make_sdesc_sbo(a_base + (uint32_t)(18 * dy + dx) * kRowBytes, 18 * kRowBytes);
+                                    ad1 = make_sdesc_sbo(a_base + (uint32_t)(18 * dy + 8 + dx) * kRowBytes, 18 * kRowBytes);
+                                } else {
+                                    ad0 = make_sdesc(a_base);
+                                    ad1 = make_sdesc(a_base + 16 * 8 * kRowBytes);
+                                }
+#pragma unroll
+                                for (int k = 0; k < kKSteps; ++k) {
+                                    const uint32_t accum = (c | tap | k) ? 1u : 0u;
+                                    umma2<F16>(tmem_d0, ad0 + 2 * k, bd + 2 * k, idesc, accum);
+                                    umma2<F16>(tmem_d1, ad1 + 2 * k, bd + 2 * k, idesc, accum);
+                                }
+                                umma2_commit(&empty[s]);
+                                if (tap == ntap - 1) {
+                                    umma2_commit(&a_empty[ab]);
+                                    if (c == nchunks - 1) umma2_commit(&tmem_full[acc]);
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+            } else if (P.single_box) {
                 int bc = 0, ac = 0;
                 const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
                 for (int tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
@@ -568,7 +610,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int y0 = (rr / P.regions_x) * 16, x0 = (rr % P.regions_x) * 16;
             const bool live = R < P.n_regions;
             for (int c = 0; c < nchunks; ++c, ++ac) {
-                const int ab = ac & 1;
+                const int ab = ac % kNA;
                 const bool work = live && c < P.chunks_a && P.dbg != 1;
                 float4 t4[4];
                 if (work) {   // table row of this thread's 8 channels: issued before the wait, it does not depend on the box
@@ -576,7 +618,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                     for (int q = 0; q < 4; ++q) t4[q] = __ldg(tp + q);
                 }
-                mbar_wait(&a_land[ab], (ac >> 1) & 1);
+                mbar_wait(&a_land[ab], (ac / kNA) & 1);
                 if (work) {
                     const uint32_t a_base = smem_u32(sA + ab * kBoxStride);
                     // y = v * sc + sh;  SiLU(y) = y / (1 + 2^(v * nsc + nsh)) with (nsc, nsh) = -log2(e) * (sc, sh)
@@ -1076,7 +1118,12 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     const size_t fixed = (size_t)kStgBytes + (P.has_out16 ? kStg16Bytes : 0) + kBeBytes + 512 + 1024;
     const size_t budget = 227 * 1024 - fixed;
     int stages = P.single_box ? (int)((budget - 2 * kBoxStride) / (3 * b_bytes)) : (int)(budget / (kABytes + 3 * b_bytes));
-    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages > 4) stages = 4;
+    if (gn) {   // three A boxes + a ring of single-tap weight stages
+        stages = (int)((budget - kNA * kBoxStride) / b_bytes);
+        if (stages > kMaxStages) stages = kMaxStages;
+        ADP_REQUIRE(stages >= 4, "anoddpm_conv(impl=3, gn_table): shared memory budget leaves %d weight stages", stages);
+    }
     ADP_REQUIRE(stages >= 2, "anoddpm_conv(impl=3): shared memory budget leaves fewer than 2 stages");
     P.stages = stages;
     P.n_tiles_n = adp_ceil_div(d->Cout, P.BN);
@@ -1107,7 +1154,8 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
         if (rc) return rc;
     }
 
-    const size_t ring = P.single_box ? (size_t)2 * kBoxStride + (size_t)stages * 3 * b_bytes : (size_t)stages * (kABytes + 3 * b_bytes);
+    const size_t ring = gn ? (size_t)kNA * kBoxStride + (size_t)stages * b_bytes
+                           : (P.single_box ? (size_t)2 * kBoxStride + (size_t)stages * 3 * b_bytes : (size_t)stages * (kABytes + 3 * b_bytes));
     const size_t smem = ring + fixed;
     static bool attr_dev[64] = {};   // the attribute is per device
     int dev_ = 0;
