@@ -44,15 +44,15 @@ constexpr int kABytes = 2 * kSubBytes;              // two subtiles per CTA
 constexpr int kBoxBytes = 18 * 18 * kRowBytes;      // single-box main loop: one (K-block, 18 px, 18 rows) box = both subtiles + halo
 constexpr int kBoxStride = 41 * 1024;               // 1024-byte aligned buffer stride (41,472 B used)
 constexpr int kAccStages = 2;
-constexpr int kMaxStages = 8;                       // weight-ring barriers (4 (chunk, dy) stages; GN variant: up to 8 single-tap stages)
-constexpr int kNA = 3;                              // GN variant: A boxes in flight (load + transform latency exceeds one chunk of MMAs)
+constexpr int kMaxStages = 4;
 constexpr int kEpiWarps = 8;
 constexpr int kStgBuf = 32 * 64;                    // one epilogue buffer: 32 pixel rows x 16 fp32 channels, SWIZZLE_64B
 constexpr int kStgBytes = kEpiWarps * 2 * kStgBuf;  // 8 epilogue warps x 2 buffers
 constexpr int kBeBytes = kEpiWarps * 128 * 4;       // per-warp (bias + embedding) row of the current tile
 constexpr int kStg16Buf = 32 * 32;                  // fp16 copy of a step: 32 pixel rows x 16 halves, no swizzle
 constexpr int kStg16Bytes = kEpiWarps * 2 * kStg16Buf;
-constexpr int kTransformWarps = 8;                  // two per scheduler: the transform is MUFU-bound (ex2 + rcp per element)
+constexpr int kTransformWarps = 8;                  // warps 12..19, two per scheduler: the transform is MUFU-bound (ex2 + rcp per element)
+
 constexpr int kThreadsGN = 384 + 32 * kTransformWarps;   // + warps 12..: operand transform (GroupNorm + SiLU on the landed A box)
 
 struct Tc3Args {
@@ -81,7 +81,7 @@ struct Tc3Args {
     int chunks_a1;             // chunks of the first main source; chunks_a - chunks_a1 come from the second (torch.cat)
     int has_out16;             // the epilogue also stores an fp16 copy of the fp32 output
     int dbg;                   // ANODDPM_TC3_DBG (attribution runs only): 1 = transform warps only forward the barrier,
-                               // 2 = read the box but do not write it back, 3 = scale + shift without the SiLU (no MUFU)
+                               // 2 = read + compute but no write-back
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -263,9 +263,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int S = P.stages;
     // multi-box: [S][2 subtiles][kSubBytes] then [S][3 taps][b_bytes]; single-box: [2][kBoxStride] then [S][3 taps][b_bytes]
     uint8_t* sA = smem;
-    // GN variant: [3][kBoxStride] then [S single-tap weight stages][b_bytes]
-    uint8_t* sB = smem + (GN ? kNA * kBoxStride : (P.single_box ? 2 * kBoxStride : S * kABytes));
-    uint8_t* stg_all = sB + (GN ? S : S * 3) * b_bytes;   // [8 warps][2][kStgBuf], 1024-byte aligned (ring sizes are multiples)
+    uint8_t* sB = smem + (P.single_box ? 2 * kBoxStride : S * kABytes);
+    uint8_t* stg_all = sB + S * 3 * b_bytes;       // [8 warps][2][kStgBuf], 1024-byte aligned (ring sizes are multiples)
     uint8_t* stg16_all = stg_all + kStgBytes;      // [8 warps][2][kStg16Buf] when the fp16 copy is requested
     float* be_all = reinterpret_cast<float*>(stg16_all + (P.has_out16 ? kStg16Bytes : 0));   // [8 warps][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(be_all) + kBeBytes);
@@ -274,10 +273,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]   both CTAs (multicast commit)
     uint64_t* tmem_empty = tmem_full + kAccStages; // [2]   leader only, 2 x 256 arrivals
     uint64_t* res_bar = tmem_empty + kAccStages;   // [8 warps][2] residual box landed
-    uint64_t* a_full = res_bar + 2 * kEpiWarps;    // [3]   single-box main loop: A box landed / transformed (leader only)
-    uint64_t* a_empty = a_full + kNA;              // [3]   both CTAs (multicast commit)
-    uint64_t* a_land = a_empty + kNA;              // [3]   GN: this CTA's raw A box landed (per CTA)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_land + kNA);
+    uint64_t* a_full = res_bar + 2 * kEpiWarps;    // [2]   single-box main loop: A box landed (leader only)
+    uint64_t* a_empty = a_full + 2;                // [2]   both CTAs (multicast commit)
+    uint64_t* a_land = a_empty + 2;                // [2]   GN: this CTA's raw A box landed (per CTA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_land + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
@@ -309,7 +308,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * 32 * kEpiWarps); }
         for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
         // GN: a_full collects one arrival per transform warp of both CTAs (4 + 4) instead of the two producers
-        for (int i = 0; i < kNA; ++i) { mbar_init(&a_full[i], GN ? 2 * kTransformWarps : 2); mbar_init(&a_empty[i], 1); mbar_init(&a_land[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], GN ? 2 * kTransformWarps : 2); mbar_init(&a_empty[i], 1); mbar_init(&a_land[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -339,32 +338,38 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const int n0 = nt * P.BN + (int)rank * (P.BN / 2);
                     const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
                     for (int c = 0; c < nchunks; ++c, ++ac) {
-                        const int ab = ac % kNA;
+                        const int ab = ac & 1;
                         uint8_t* a_dst = sA + ab * kBoxStride;
-                        mbar_wait(&a_empty[ab], ((ac / kNA) & 1) ^ 1);
-                        const bool main_src = c < P.chunks_a;
-                        const int cs = c - P.chunks_a;
-                        if (main_src) {
+                        mbar_wait(&a_empty[ab], ((ac >> 1) & 1) ^ 1);
+                        if (c < P.chunks_a) {
                             const bool first = c < P.chunks_a1;
                             mbar_expect_tx(&a_land[ab], (uint32_t)kBoxBytes);
                             tma_load_4d(a_dst, first ? &map_a : &map_a2, &a_land[ab], (first ? c : c - P.chunks_a1) * P.ke,
                                         x0 - 1, y0 - 1, b0);
+                            for (int dy = 0; dy < 3; ++dy, ++bc) {
+                                const int s = bc % S;
+                                mbar_wait(&empty[s], ((bc / S) & 1) ^ 1);
+                                uint8_t* b_dst = sB + s * 3 * b_bytes;
+                                if (leader) mbar_expect_tx(&full[s], 2u * 3u * (uint32_t)b_bytes);
+                                else mbar_arrive_remote(&full[s], 0);
+#pragma unroll
+                                for (int dx = 0; dx < 3; ++dx)
+                                    tma2_load_2d(b_dst + dx * b_bytes, &map_w, &full[s], (dy * 3 + dx) * P.Ca + c * P.ke, n0);
+                            }
                         } else {
+                            const int cs = c - P.chunks_a;
                             const bool first = cs < P.chunks_r1;
                             const CUtensorMap* am = first ? &map_r1 : &map_r2;
                             const int c0 = (first ? cs : cs - P.chunks_r1) * P.ke;
                             mbar_expect_tx(&a_land[ab], 2u * (16 * 8 * kRowBytes));
                             tma_load_4d(a_dst, am, &a_land[ab], c0, x0, y0, b0);
                             tma_load_4d(a_dst + 16 * 8 * kRowBytes, am, &a_land[ab], c0, x0 + 8, y0, b0);
-                        }
-                        // single-tap weight stages (8 KB each per CTA): finer ring, same bytes as two (chunk, dy) stages
-                        const int ntap = main_src ? 9 : 1;
-                        for (int tap = 0; tap < ntap; ++tap, ++bc) {
                             const int s = bc % S;
                             mbar_wait(&empty[s], ((bc / S) & 1) ^ 1);
                             if (leader) mbar_expect_tx(&full[s], 2u * (uint32_t)b_bytes);
                             else mbar_arrive_remote(&full[s], 0);
-                            tma2_load_2d(sB + s * b_bytes, &map_w, &full[s], main_src ? tap * P.Ca + c * P.ke : 9 * P.Ca + cs * P.ke, n0);
+                            tma2_load_2d(sB + s * 3 * b_bytes, &map_w, &full[s], 9 * P.Ca + cs * P.ke, n0);
+                            ++bc;
                         }
                     }
                 }
@@ -460,53 +465,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.BN >> 3) << 17) |
                                    ((uint32_t)(256 >> 4) << 24);
             int kbc = 0, it = 0;
-            if (GN) {
-                int bc = 0, ac = 0;
-                const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
-                for (int tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
-                    const int acc = it & 1;
-                    mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t tmem_d0 = tmem_base + (uint32_t)((acc * 2 + 0) * P.BN);
-                    const uint32_t tmem_d1 = tmem_base + (uint32_t)((acc * 2 + 1) * P.BN);
-                    for (int c = 0; c < nchunks; ++c, ++ac) {
-                        const int ab = ac % kNA;
-                        mbar_wait(&a_full[ab], (ac / kNA) & 1);
-                        const uint32_t a_base = smem_u32(sA + ab * kBoxStride);
-                        const bool main_src = c < P.chunks_a;
-                        const int ntap = main_src ? 9 : 1;
-                        for (int tap = 0; tap < ntap; ++tap, ++bc) {
-                            const int s = bc % S;
-                            mbar_wait(&full[s], (bc / S) & 1);
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            if (elect_one()) {
-                                const uint64_t bd = make_sdesc(smem_u32(sB + s * b_bytes));
-                                uint64_t ad0, ad1;
-                                if (main_src) {
-                                    const int dy = tap / 3, dx = tap - 3 * dy;
-                                    ad0 = make_sdesc_sbo(a_base + (uint32_t)(18 * dy + dx) * kRowBytes, 18 * kRowBytes);
-                                    ad1 = make_sdesc_sbo(a_base + (uint32_t)(18 * dy + 8 + dx) * kRowBytes, 18 * kRowBytes);
-                                } else {
-                                    ad0 = make_sdesc(a_base);
-                                    ad1 = make_sdesc(a_base + 16 * 8 * kRowBytes);
-                                }
-#pragma unroll
-                                for (int k = 0; k < kKSteps; ++k) {
-                                    const uint32_t accum = (c | tap | k) ? 1u : 0u;
-                                    umma2<F16>(tmem_d0, ad0 + 2 * k, bd + 2 * k, idesc, accum);
-                                    umma2<F16>(tmem_d1, ad1 + 2 * k, bd + 2 * k, idesc, accum);
-                                }
-                                umma2_commit(&empty[s]);
-                                if (tap == ntap - 1) {
-                                    umma2_commit(&a_empty[ab]);
-                                    if (c == nchunks - 1) umma2_commit(&tmem_full[acc]);
-                                }
-                            }
-                            __syncwarp();
-                        }
-                    }
-                }
-            } else if (P.single_box) {
+            if (P.single_box) {
                 int bc = 0, ac = 0;
                 const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
                 for (int tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
@@ -600,7 +559,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // Pixels outside the image keep TMA's zero fill: the convolution pads AFTER normalisation + activation.
         const int tid = (warp - 12) * 32 + lane;
         const int j = tid & 7, rl = tid >> 3;
-        constexpr int kRowLanes = kTransformWarps * 4;
+        constexpr int kRowLanes = kTransformWarps * 4;                  // 32 box rows per sweep of the transform warps
+        constexpr int kSweeps = (18 * 18 + kRowLanes - 1) / kRowLanes;  // 11
+        constexpr int kU = 4;                                           // rows in flight per thread (the loop is latency-bound)
         const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
         int ac = 0;
         for (int tile = tile_first; tile < tile_end; tile += tile_step) {
@@ -610,7 +571,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int y0 = (rr / P.regions_x) * 16, x0 = (rr % P.regions_x) * 16;
             const bool live = R < P.n_regions;
             for (int c = 0; c < nchunks; ++c, ++ac) {
-                const int ab = ac % kNA;
+                const int ab = ac & 1;
                 const bool work = live && c < P.chunks_a && P.dbg != 1;
                 float4 t4[4];
                 if (work) {   // table row of this thread's 8 channels: issued before the wait, it does not depend on the box
@@ -618,7 +579,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                     for (int q = 0; q < 4; ++q) t4[q] = __ldg(tp + q);
                 }
-                mbar_wait(&a_land[ab], (ac / kNA) & 1);
+                mbar_wait(&a_land[ab], (ac >> 1) & 1);
                 if (work) {
                     const uint32_t a_base = smem_u32(sA + ab * kBoxStride);
                     // y = v * sc + sh;  SiLU(y) = y / (1 + 2^(v * nsc + nsh)) with (nsc, nsh) = -log2(e) * (sc, sh)
@@ -627,27 +588,36 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     float nsc[8], nsh[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) { nsc[e] = sc[e] * -1.4426950408889634f; nsh[e] = sh[e] * -1.4426950408889634f; }
-                    // rows of this thread: r = rl + kRowLanes * i; (py, px) advance incrementally (no division in the loop)
-                    int py = rl / 18, px = rl - py * 18;
-                    constexpr int kDy = kRowLanes / 18, kDx = kRowLanes - 18 * kDy;
-#pragma unroll 2
-                    for (int r = rl; r < 18 * 18; r += kRowLanes) {
-                        if ((unsigned)(y0 - 1 + py) < (unsigned)P.H && (unsigned)(x0 - 1 + px) < (unsigned)P.W) {
-                            const uint32_t addr = a_base + (uint32_t)r * kRowBytes + (uint32_t)((j ^ (r & 7)) << 4);
-                            uint4 v = lds128u(addr);
-                            uint32_t* vw = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll 1
+                    for (int i0 = 0; i0 < kSweeps; i0 += kU) {
+                        uint4 v[kU];
+                        uint32_t addr[kU];
+                        bool ok[kU];
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) {   // kU independent rows: all loads first, no divergent control flow
+                            const int r = rl + kRowLanes * (i0 + u);
+                            const int rc = min(r, 18 * 18 - 1);
+                            const int py = (rc * 3641) >> 16, px = rc - py * 18;      // rc / 18, rc % 18 for rc < 324
+                            ok[u] = r < 18 * 18 && (i0 + u) < kSweeps && (unsigned)(y0 - 1 + py) < (unsigned)P.H &&
+                                    (unsigned)(x0 - 1 + px) < (unsigned)P.W;
+                            addr[u] = a_base + (uint32_t)rc * kRowBytes + (uint32_t)((j ^ (rc & 7)) << 4);
+                            v[u] = lds128u(addr[u]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < kU; ++u) {
+                            uint32_t* vw = reinterpret_cast<uint32_t*>(&v[u]);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const float2 fv = __half22float2(*reinterpret_cast<const __half2*>(&vw[e]));
                                 const float ya = fmaf(fv.x, sc[2 * e], sh[2 * e]), yb = fmaf(fv.y, sc[2 * e + 1], sh[2 * e + 1]);
                                 const float da = 1.0f + ex2_approx(fmaf(fv.x, nsc[2 * e], nsh[2 * e]));
                                 const float db = 1.0f + ex2_approx(fmaf(fv.y, nsc[2 * e + 1], nsh[2 * e + 1]));
-                                vw[e] = P.dbg == 3 ? pack_half2_sat(ya, yb) : pack_half2_sat(ya * rcp_approx(da), yb * rcp_approx(db));
+                                vw[e] = pack_half2_sat(ya * rcp_approx(da), yb * rcp_approx(db));
                             }
-                            if (P.dbg != 2 || vw[0] == 0x7fff7fffu) sts128u(addr, v);
                         }
-                        px += kDx; py += kDy;
-                        if (px >= 18) { px -= 18; ++py; }
+#pragma unroll
+                        for (int u = 0; u < kU; ++u)
+                            if (ok[u] && P.dbg != 2) sts128u(addr[u], v[u]);      // rows outside the image keep TMA's zero fill
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1118,12 +1088,7 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     const size_t fixed = (size_t)kStgBytes + (P.has_out16 ? kStg16Bytes : 0) + kBeBytes + 512 + 1024;
     const size_t budget = 227 * 1024 - fixed;
     int stages = P.single_box ? (int)((budget - 2 * kBoxStride) / (3 * b_bytes)) : (int)(budget / (kABytes + 3 * b_bytes));
-    if (stages > 4) stages = 4;
-    if (gn) {   // three A boxes + a ring of single-tap weight stages
-        stages = (int)((budget - kNA * kBoxStride) / b_bytes);
-        if (stages > kMaxStages) stages = kMaxStages;
-        ADP_REQUIRE(stages >= 4, "anoddpm_conv(impl=3, gn_table): shared memory budget leaves %d weight stages", stages);
-    }
+    if (stages > kMaxStages) stages = kMaxStages;
     ADP_REQUIRE(stages >= 2, "anoddpm_conv(impl=3): shared memory budget leaves fewer than 2 stages");
     P.stages = stages;
     P.n_tiles_n = adp_ceil_div(d->Cout, P.BN);
@@ -1154,8 +1119,7 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
         if (rc) return rc;
     }
 
-    const size_t ring = gn ? (size_t)kNA * kBoxStride + (size_t)stages * b_bytes
-                           : (P.single_box ? (size_t)2 * kBoxStride + (size_t)stages * 3 * b_bytes : (size_t)stages * (kABytes + 3 * b_bytes));
+    const size_t ring = P.single_box ? (size_t)2 * kBoxStride + (size_t)stages * 3 * b_bytes : (size_t)stages * (kABytes + 3 * b_bytes);
     const size_t smem = ring + fixed;
     static bool attr_dev[64] = {};   // the attribute is per device
     int dev_ = 0;

@@ -85,12 +85,14 @@ def main():
     ap.add_argument("--stats", action="store_true")
     ap.add_argument("--emb", action="store_true")
     ap.add_argument("--variants", action="store_true")
+    ap.add_argument("--gn", action="store_true", help="operand-side GroupNorm + SiLU (gn_table)")
+    ap.add_argument("--out16", action="store_true")
+    ap.add_argument("--outf16", action="store_true")
     ap.add_argument("--gn-attrib", action="store_true", help="attribute the operand-transform overhead (ANODDPM_TC3_DBG)")
     a = ap.parse_args()
     if a.gn_attrib:
         print(f"| conv1 GN {a.ci}->{a.co} @{a.hw}^2 bs{a.batch}: transform variant | ms | TFLOP/s |\n|---|---:|---:|")
-        for name, dbg in (("full transform", "0"), ("barrier forwarding only", "1"), ("read box, no write-back", "2"),
-                          ("scale+shift only (no MUFU)", "3")):
+        for name, dbg in (("full transform", "0"), ("barrier forwarding only", "1"), ("read + compute, no write-back", "2")):
             os.environ["ANODDPM_TC3_DBG"] = dbg
             ms, tf = run(a, a.batch, a.ci, a.co, a.hw, res=0, stats=True, emb=True, out_f16=True, gn=True)
             print(f"| {name} | {ms:.3f} | {tf:.0f} |", flush=True)
@@ -116,7 +118,7 @@ def main():
             ms, tf = run(a, a.batch, a.ci, a.co, a.hw, **kw)
             print(f"| {name} | {ms:.3f} | {tf:.0f} |", flush=True)
     else:
-        ms, tf = run(a, a.batch, a.ci, a.co, a.hw, a.res, a.stats, a.emb, a.cr)
+        ms, tf = run(a, a.batch, a.ci, a.co, a.hw, a.res, a.stats, a.emb, a.cr, gn=a.gn, out16=a.out16, out_f16=a.outf16)
         print(f"{ms:.3f} ms  {tf:.0f} TFLOP/s")
 
 
