@@ -45,6 +45,7 @@ constexpr int kBoxBytes = 18 * 18 * kRowBytes;      // single-box main loop: one
 constexpr int kBoxStride = 41 * 1024;               // 1024-byte aligned buffer stride (41,472 B used)
 constexpr int kAccStages = 2;
 constexpr int kMaxStages = 4;
+constexpr int kNAMax = 3;                           // GN variant: up to three A boxes in flight (ANODDPM_TC3_NA)
 constexpr int kEpiWarps = 8;
 constexpr int kStgBuf = 32 * 64;                    // one epilogue buffer: 32 pixel rows x 16 fp32 channels, SWIZZLE_64B
 constexpr int kStgBytes = kEpiWarps * 2 * kStgBuf;  // 8 epilogue warps x 2 buffers
@@ -80,6 +81,7 @@ struct Tc3Args {
     int c_tab;                 // Ca1 + Ca2
     int chunks_a1;             // chunks of the first main source; chunks_a - chunks_a1 come from the second (torch.cat)
     int has_out16;             // the epilogue also stores an fp16 copy of the fp32 output
+    int na;                    // A boxes in flight: 2, or 3 in the GN variant when shared memory allows
     int dbg;                   // ANODDPM_TC3_DBG (attribution runs only): 1 = transform warps only forward the barrier,
                                // 2 = read + compute but no write-back
 };
@@ -205,6 +207,12 @@ __device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, 
         ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// L2 prefetch of a box (no shared memory, no barrier): the later load then pays L2 latency instead of HBM latency
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2),
+                 "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
                  "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -263,7 +271,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int S = P.stages;
     // multi-box: [S][2 subtiles][kSubBytes] then [S][3 taps][b_bytes]; single-box: [2][kBoxStride] then [S][3 taps][b_bytes]
     uint8_t* sA = smem;
-    uint8_t* sB = smem + (P.single_box ? 2 * kBoxStride : S * kABytes);
+    uint8_t* sB = smem + (P.single_box ? P.na * kBoxStride : S * kABytes);
     uint8_t* stg_all = sB + S * 3 * b_bytes;       // [8 warps][2][kStgBuf], 1024-byte aligned (ring sizes are multiples)
     uint8_t* stg16_all = stg_all + kStgBytes;      // [8 warps][2][kStg16Buf] when the fp16 copy is requested
     float* be_all = reinterpret_cast<float*>(stg16_all + (P.has_out16 ? kStg16Bytes : 0));   // [8 warps][128]
@@ -274,9 +282,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint64_t* tmem_empty = tmem_full + kAccStages; // [2]   leader only, 2 x 256 arrivals
     uint64_t* res_bar = tmem_empty + kAccStages;   // [8 warps][2] residual box landed
     uint64_t* a_full = res_bar + 2 * kEpiWarps;    // [2]   single-box main loop: A box landed (leader only)
-    uint64_t* a_empty = a_full + 2;                // [2]   both CTAs (multicast commit)
-    uint64_t* a_land = a_empty + 2;                // [2]   GN: this CTA's raw A box landed (per CTA)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_land + 2);
+    uint64_t* a_empty = a_full + kNAMax;           // [3]   both CTAs (multicast commit)
+    uint64_t* a_land = a_empty + kNAMax;           // [3]   GN: this CTA's raw A box landed (per CTA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_land + kNAMax);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
@@ -308,7 +316,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * 32 * kEpiWarps); }
         for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
         // GN: a_full collects one arrival per transform warp of both CTAs (4 + 4) instead of the two producers
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], GN ? 2 * kTransformWarps : 2); mbar_init(&a_empty[i], 1); mbar_init(&a_land[i], 1); }
+        for (int i = 0; i < kNAMax; ++i) { mbar_init(&a_full[i], GN ? 2 * kTransformWarps : 2); mbar_init(&a_empty[i], 1); mbar_init(&a_land[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -330,17 +338,36 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             // leader's a_full); weight stages as in the single-box loop
             if (elected) {
                 int bc = 0, ac = 0;
+                const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
+                // L2 prefetch cursor: the raw box of the chunk `kPF` positions ahead of the one being loaded (the load of a box
+                // straight from HBM takes longer than one chunk of MMAs; from L2 it does not)
+                constexpr int kPF = 3;
+                const int n_my_tiles = tile_end > tile_first ? (tile_end - tile_first + tile_step - 1) / tile_step : 0;
+                const long long q_end = (long long)n_my_tiles * nchunks;
+                auto prefetch_chunk = [&](long long q) {
+                    if (q >= q_end) return;
+                    const int ti = (int)(q / nchunks), c = (int)(q - (long long)ti * nchunks);
+                    if (c >= P.chunks_a) return;                 // skip sources: small centre boxes, not prefetched
+                    const int tile = tile_first + ti * tile_step;
+                    const int R = (tile / P.n_tiles_n) * 2 + (int)rank;
+                    if (R >= P.n_regions) return;
+                    const int b0 = R / P.regions_per_img, rr = R - b0 * P.regions_per_img;
+                    const int y0 = (rr / P.regions_x) * 16, x0 = (rr % P.regions_x) * 16;
+                    const bool first = c < P.chunks_a1;
+                    tma_prefetch_4d(first ? &map_a : &map_a2, (first ? c : c - P.chunks_a1) * P.ke, x0 - 1, y0 - 1, b0);
+                };
+                for (int q = 0; q < kPF; ++q) prefetch_chunk(q);
                 for (int tile = tile_first; tile < tile_end; tile += tile_step) {
                     const int pair = tile / P.n_tiles_n, nt = tile - pair * P.n_tiles_n;
                     const int R = pair * 2 + (int)rank;
                     const int b0 = R / P.regions_per_img, rr = R - b0 * P.regions_per_img;
                     const int y0 = (rr / P.regions_x) * 16, x0 = (rr % P.regions_x) * 16;
                     const int n0 = nt * P.BN + (int)rank * (P.BN / 2);
-                    const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
                     for (int c = 0; c < nchunks; ++c, ++ac) {
-                        const int ab = ac & 1;
+                        const int ab = ac % P.na;
                         uint8_t* a_dst = sA + ab * kBoxStride;
-                        mbar_wait(&a_empty[ab], ((ac >> 1) & 1) ^ 1);
+                        prefetch_chunk((long long)ac + kPF);
+                        mbar_wait(&a_empty[ab], ((ac / P.na) & 1) ^ 1);
                         if (c < P.chunks_a) {
                             const bool first = c < P.chunks_a1;
                             mbar_expect_tx(&a_land[ab], (uint32_t)kBoxBytes);
@@ -385,9 +412,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const int n0 = nt * P.BN + (int)rank * (P.BN / 2);
                 const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
                 for (int c = 0; c < nchunks; ++c, ++ac) {
-                    const int ab = ac & 1;
+                    const int ab = ac % P.na;
                     uint8_t* a_dst = sA + ab * kBoxStride;
-                    mbar_wait(&a_empty[ab], ((ac >> 1) & 1) ^ 1);
+                    mbar_wait(&a_empty[ab], ((ac / P.na) & 1) ^ 1);
                     if (c < P.chunks_a) {
                         if (leader) mbar_expect_tx(&a_full[ab], 2u * (uint32_t)kBoxBytes);
                         else mbar_arrive_remote(&a_full[ab], 0);
@@ -475,8 +502,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const uint32_t tmem_d0 = tmem_base + (uint32_t)((acc * 2 + 0) * P.BN);
                     const uint32_t tmem_d1 = tmem_base + (uint32_t)((acc * 2 + 1) * P.BN);
                     for (int c = 0; c < nchunks; ++c, ++ac) {
-                        const int ab = ac & 1;
-                        mbar_wait(&a_full[ab], (ac >> 1) & 1);
+                        const int ab = ac % P.na;
+                        mbar_wait(&a_full[ab], (ac / P.na) & 1);
                         const uint32_t a_base = smem_u32(sA + ab * kBoxStride);
                         const bool main_src = c < P.chunks_a;
                         const int ndy = main_src ? 3 : 1;
@@ -571,7 +598,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int y0 = (rr / P.regions_x) * 16, x0 = (rr % P.regions_x) * 16;
             const bool live = R < P.n_regions;
             for (int c = 0; c < nchunks; ++c, ++ac) {
-                const int ab = ac & 1;
+                const int ab = ac % P.na;
                 const bool work = live && c < P.chunks_a && P.dbg != 1;
                 float4 t4[4];
                 if (work) {   // table row of this thread's 8 channels: issued before the wait, it does not depend on the box
@@ -579,7 +606,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                     for (int q = 0; q < 4; ++q) t4[q] = __ldg(tp + q);
                 }
-                mbar_wait(&a_land[ab], (ac >> 1) & 1);
+                mbar_wait(&a_land[ab], (ac / P.na) & 1);
                 if (work) {
                     const uint32_t a_base = smem_u32(sA + ab * kBoxStride);
                     // y = v * sc + sh;  SiLU(y) = y / (1 + 2^(v * nsc + nsh)) with (nsc, nsh) = -log2(e) * (sc, sh)
@@ -1087,7 +1114,9 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     if (gn) P.single_box = 1;
     const size_t fixed = (size_t)kStgBytes + (P.has_out16 ? kStg16Bytes : 0) + kBeBytes + 512 + 1024;
     const size_t budget = 227 * 1024 - fixed;
-    int stages = P.single_box ? (int)((budget - 2 * kBoxStride) / (3 * b_bytes)) : (int)(budget / (kABytes + 3 * b_bytes));
+    P.na = 2;
+    if (gn) { const char* e = getenv("ANODDPM_TC3_NA"); P.na = e ? atoi(e) : 2; if (P.na < 2 || P.na > kNAMax) P.na = 2; }
+    int stages = P.single_box ? (int)((budget - (size_t)P.na * kBoxStride) / (3 * b_bytes)) : (int)(budget / (kABytes + 3 * b_bytes));
     if (stages > kMaxStages) stages = kMaxStages;
     ADP_REQUIRE(stages >= 2, "anoddpm_conv(impl=3): shared memory budget leaves fewer than 2 stages");
     P.stages = stages;
@@ -1119,7 +1148,7 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
         if (rc) return rc;
     }
 
-    const size_t ring = P.single_box ? (size_t)2 * kBoxStride + (size_t)stages * 3 * b_bytes : (size_t)stages * (kABytes + 3 * b_bytes);
+    const size_t ring = P.single_box ? (size_t)P.na * kBoxStride + (size_t)stages * 3 * b_bytes : (size_t)stages * (kABytes + 3 * b_bytes);
     const size_t smem = ring + fixed;
     static bool attr_dev[64] = {};   // the attribute is per device
     int dev_ = 0;

@@ -97,6 +97,14 @@ def main():
             ms, tf = run(a, a.batch, a.ci, a.co, a.hw, res=0, stats=True, emb=True, out_f16=True, gn=True)
             print(f"| {name} | {ms:.3f} | {tf:.0f} |", flush=True)
         os.environ["ANODDPM_TC3_DBG"] = "0"
+        os.environ["ANODDPM_TC3_NA"] = "3"
+        for name, kw in (("conv1 GN, 3 A boxes + 2 weight stages", dict(res=0, stats=True, emb=True, out_f16=True, gn=True)),
+                         ("conv2 GN + fp16 copy, 3 A boxes + 2 weight stages", dict(res=1, stats=True, emb=False, out16=True, gn=True))):
+            ms, tf = run(a, a.batch, a.ci, a.co, a.hw, **kw)
+            print(f"| {name} | {ms:.3f} | {tf:.0f} |", flush=True)
+        os.environ["ANODDPM_TC3_NA"] = "2"
+        ms, tf = run(a, a.batch, a.ci, a.co, a.hw, res=1, stats=True, emb=False, out16=True, gn=True)
+        print(f"| conv2 GN + fp16 copy, 2 A boxes | {ms:.3f} | {tf:.0f} |", flush=True)
         ms, tf = run(a, a.batch, a.ci, a.co, a.hw, res=0, stats=True, emb=True, out_f16=True)
         print(f"| no operand transform (plain conv1) | {ms:.3f} | {tf:.0f} |")
         return
