@@ -6,10 +6,10 @@ on a CUDA device is executed by the sm_100a kernels of csrc/ (``engine.UNetEngin
 GroupNorm statistics + fused GN/SiLU/resample, tcgen05 TF32 implicit-GEMM convolutions with the
 timestep-embedding add, skip 1x1 convolution and residual folded in, and a fused attention kernel.
 
-The module classes (ResBlock, AttentionBlock, ...) also define ordinary torch forwards: they document
-the semantics and serve autograd.  The training (autograd) forward is NOT yet native -- it is only taken
-when explicitly enabled with ``UNetModel.allow_autograd_fallback = True`` (or env
-ANODDPM_AUTOGRAD_FALLBACK=1) and is never used by the detection path, the tests' parity checks or bench.py.
+The module classes (ResBlock, AttentionBlock, ...) also define ordinary torch forwards: they document the
+semantics of a block used on its own.  ``UNetModel.forward`` never calls them: without gradients it runs the inference
+engine, with gradients the native training path (``train.forward_train``: same forward kernels, hand-written backward --
+tcgen05 data / weight gradients, GroupNorm / attention backward kernels); there is no PyTorch-autograd fallback.
 """
 import math
 import os
@@ -180,8 +180,6 @@ class ResBlock(TimestepBlock):
 class UNetModel(nn.Module):
     """guided-diffusion style UNet; constructor/defaults of reference UNet.py:222-235."""
 
-    allow_autograd_fallback = os.environ.get("ANODDPM_AUTOGRAD_FALLBACK", "0") == "1"
-
     def __init__(self, img_size, base_channels, conv_resample=True, n_heads=1, n_head_channels=-1, channel_mults="",
                  num_res_blocks=2, dropout=0, attention_resolutions="32,16,8", biggan_updown=True, in_channels=1):
         self.dtype = torch.float32
@@ -283,33 +281,19 @@ class UNetModel(nn.Module):
 
     def forward(self, x, time):
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if not x.is_cuda:
+            raise RuntimeError("anoddpm_b200.UNetModel runs on sm_100a only: move the model and inputs to a CUDA "
+                               "device (no CPU fallback)")
         if not needs_grad:
-            if not x.is_cuda:
-                raise RuntimeError("anoddpm_b200.UNetModel runs on sm_100a only: move the model and inputs to a CUDA "
-                                   "device (no CPU fallback)")
             if self.training and self.dropout > 0:
                 raise NotImplementedError(
                     "UNetModel(dropout>0) in train() mode: the reference applies dropout here (UNet.py:190-193) and the "
                     "native inference engine does not -- call .eval() for sampling")
             return self.engine().forward(x, time)
-        if not UNetModel.allow_autograd_fallback:
-            raise NotImplementedError(
-                "the training (autograd) forward is not native yet; run inference under torch.no_grad(), or opt in "
-                "to the PyTorch autograd fallback with UNetModel.allow_autograd_fallback = True")
-        return self.forward_torch(x, time)
-
-    def forward_torch(self, x, time):
-        """Plain-torch forward (reference UNet.py:390-406): autograd fallback only, see the module docstring."""
-        emb = self.time_embedding(time)
-        skips = []
-        h = x.type(self.dtype)
-        for module in self.down:
-            h = module(h, emb)
-            skips.append(h)
-        h = self.middle(h, emb)
-        for module in self.up:
-            h = module(torch.cat([h, skips.pop()], dim=1), emb)
-        return self.out(h.type(x.dtype))
+        # training: native forward that keeps what the hand-written backward needs (anoddpm_b200/train.py); there is no
+        # PyTorch-autograd / cuDNN fallback
+        from .train import forward_train
+        return forward_train(self, x, time)
 
 
 def update_ema_params(target, source, decay_rate=0.9999):

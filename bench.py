@@ -457,9 +457,9 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------ training step (config 2)
 def run_train(args):
     """BASELINE configs[1] / SURVEY 8(d) config 2: one training step at bs 8 per GPU, 256x256, simplex noise.
-    NOT the headline metric (never run by default).  The UNet forward/backward of this step is PyTorch autograd
-    (UNetModel.allow_autograd_fallback, library kernels) -- native backward kernels are not built; the noise, q_sample
-    and the optimiser side (one all-reduce of the flat gradient + clip + AdamW + EMA, csrc/optim.cu) are native."""
+    NOT the headline metric (never run by default).  Everything in the step is native: simplex noise, q_sample, the UNet
+    forward and the hand-written backward (anoddpm_b200/train.py: tcgen05 data / weight gradients, GroupNorm / attention
+    backward kernels), the bucketed gradient all-reduce and clip + AdamW + EMA (csrc/optim.cu)."""
     import copy
     from anoddpm_b200 import GaussianDiffusionModel, UNetModel, dist as D, get_beta_schedule
     from anoddpm_b200.optim import FusedAdamWEMA
@@ -467,7 +467,6 @@ def run_train(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B = 8
-    UNetModel.allow_autograd_fallback = True
     model = build_unet(dev).train()
     ema = copy.deepcopy(model)
     opt = FusedAdamWEMA(model, ema, lr=1e-4, weight_decay=0.0, betas=(0.9, 0.999), max_norm=1.0, ema_decay=0.9999)
@@ -506,10 +505,12 @@ def run_train(args):
         print(json.dumps({"metric": "training px/s (256x256 bs 8 per GPU, simplex, AdamW + EMA)", "value": world * B * 65536 / (ms / 1e3),
                           "unit": "px/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                          "dtype": "f32 (TF32 library convs in the autograd fallback) / native f32 optimiser",
+                          "dtype": "f16 tensor-core operands (forward and backward), f32 accumulation / gradients / optimiser",
                           "data": "synthetic", "config": {"workload": "BASELINE configs[1]: train step bs 8 per GPU", "global_batch": world * B},
-                          "native_parts": "simplex noise, q_sample, gradient all-reduce + clip + AdamW + EMA (2 kernels)",
-                          "library_parts": "UNet forward + backward (PyTorch autograd: native backward kernels not built)",
+                          "native_parts": "simplex noise, q_sample, UNet forward + backward (tcgen05 dgrad / wgrad, GroupNorm + attention "
+                                          "backward kernels), bucketed gradient all-reduce + clip + AdamW + EMA",
+                          "library_parts": "none (torch.autograd only orders the per-block backward calls and sums skip-tensor gradients)",
+                          "train_flop_per_step": 3 * 2 * 277.26e9 * B * world,
                           "loss_first_last": [float(losses[0]), float(losses[-1])], "clocks": clk}))
     D.barrier()
 

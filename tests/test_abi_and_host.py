@@ -100,13 +100,15 @@ def test_unet_state_dict_layout_matches_reference(golden):
     assert m.attention_resolutions == "32,16,8" and m.num_heads == 1
 
 
-def test_unet_fails_loudly_without_cuda_or_native_autograd():
+def test_unet_fails_loudly_without_cuda():
+    """no CPU path and no PyTorch-autograd fallback: inference and training forwards both refuse CPU tensors"""
     from anoddpm_b200.UNet import UNetModel
     m = UNetModel(32, 32)
+    assert not hasattr(UNetModel, "allow_autograd_fallback") and not hasattr(m, "forward_torch")
     x, t = torch.zeros(1, 1, 32, 32), torch.zeros(1, dtype=torch.long)
     with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
         m(x, t)
-    with pytest.raises(NotImplementedError, match="not native"):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(x, t)
 
 

@@ -5,9 +5,10 @@ Tolerances (rel = max|a-b| / max|b|, the L-inf ratio of SURVEY 8(d) config 1):
   * exact-fp32 path (conv_impl="exact"): 2e-5 (summation order only) -- the strict-parity mode, always <= 1e-3;
   * tensor-core paths (tcgen05 with 10-bit-mantissa operands rounded to nearest -- kind::tf32, = the reference's OWN
     GPU numerics under PyTorch defaults (SURVEY F15), or kind::f16 where channel counts are multiples of 64 -- and
-    fp32 accumulation): 1e-3 on the BASELINE model (256^2, base 128; measured ~4e-4) and 3e-3 on the small base-32
-    test models, whose short K (288..1152) averages the 2^-11 operand rounding less (measured 1.0e-3..1.3e-3;
-    SURVEY F13 predicted 7.9e-4 L2 for them).
+    fp32 accumulation): 1e-3 on the BASELINE model (256^2, base 128; measured ~4e-4).  The DEFAULT path ("tc") keeps
+    convolutions with fewer than 128 input channels on the exact kernel (their short K does not average the 2^-11 operand
+    rounding), which brings the small base-32 / base-64 test models to 2e-4..7e-4 and the 100-step config-1 round trip to
+    3e-4; the all-tensor-core variants (tc1 / tc2 / tc_tf32) measure 0.8e-3..1.2e-3 there.
 """
 import ctypes
 
@@ -19,8 +20,10 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 REPL = 8        # ANODDPM_STAT_REPLICAS
-TOL = {"exact": 2e-5, "tc": 1e-3, "tc_tf32": 1e-3, "tc1": 1e-3, "tc2": 1e-3}
-TOL_SMALL = {"exact": 2e-5, "tc": 3e-3, "tc_tf32": 3e-3, "tc1": 3e-3, "tc2": 3e-3}
+TOL = {"exact": 5e-6, "tc": 1e-3, "tc_tf32": 1e-3, "tc1": 1e-3, "tc2": 1e-3}     # BASELINE model: measured 1.3e-6 / 4.2e-4 .. 5.1e-4
+# measured on the B200 (round 2, GPUTEST log): exact 1.9e-6; tc (the default: short-K convs exact, the rest tensor cores)
+# 2.0e-4 .. 6.9e-4; the all-tensor-core variants tc1 / tc2 8.1e-4 .. 1.22e-3.  Tolerance = measured x 1.5.
+TOL_SMALL = {"exact": 5e-6, "tc": 1e-3, "tc_tf32": 1.8e-3, "tc1": 1.8e-3, "tc2": 1.8e-3}
 
 
 def rel(a, b):
@@ -489,7 +492,8 @@ def test_config1_sampling_loop_vs_reference_golden(golden, impl):
         assert np.array_equal(seq[1].numpy(), g[f"{tag}/x_T"])           # q_sample is bit-exact
         ref = torch.from_numpy(g[f"{tag}/final"])
         print(f"[parity] config-1 loop {tag} impl={impl}: rel={rel(seq[-1], ref):.3e}")
-        assert rel(seq[-1], ref) < (1e-4 if impl == "exact" else 3e-3) * (1 if td == 12 else 3), (tag, rel(seq[-1], ref))
+        # measured: exact 7e-7 / 1.3e-6, tc 1.7e-4 (12 steps) / 3.0e-4 (100 steps); the north star's bar is 1e-3
+        assert rel(seq[-1], ref) < (5e-6 if impl == "exact" else (3e-4 if td == 12 else 6e-4)), (tag, rel(seq[-1], ref))
     bank = iter(torch.randn(12, 1, 1, 64, 64, generator=torch.Generator().manual_seed(7)).to(DEV))
     D.noise_fn = lambda x, t: next(bank)
     seq = D.forward_backward(m, x0, see_whole_sequence="whole", t_distance=6, denoise_fn="noise_fn")
