@@ -19,6 +19,7 @@ are un-scaled where they are produced (fp32).
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -109,8 +110,16 @@ def _pack_dgrad(w):
     return wf.clamp(-65504.0, 65504.0).half().contiguous()
 
 
-def _dgrad(w, dy16, B, H, W, want_f16=True):
-    """gradient wrt the conv input: [B][H][W][Cin] (fp16 on the halo-reuse kernel, else fp32); returns (tensor, is_f16)"""
+# Data gradients that feed an ELEMENTWISE consumer (the GroupNorm backward) stay fp32 by default: an fp16 store there is
+# a 2^-11 rounding per element per layer that nothing averages (measured: per-tensor gradient error 2.2e-3 with fp16
+# stores vs the fp32 reference); operands of the next tensor-core GEMM are fp16 either way.
+DA_F16 = os.environ.get("ANODDPM_TRAIN_DA_F16", "0") == "1"
+
+
+def _dgrad(w, dy16, B, H, W, want_f16=None):
+    """gradient wrt the conv input: [B][H][W][Cin] fp32 (fp16 on request, halo-reuse kernel only); returns (tensor, is_f16)"""
+    if want_f16 is None:
+        want_f16 = DA_F16
     ksize = 1 if (w.dim() == 3 or w.shape[-1] == 1) else 3
     cin = w.shape[1]
     out, _, f16 = _conv(dy16, _pack_dgrad(w), None, B, H, W, cin, ksize, out_f16=want_f16)
