@@ -52,6 +52,7 @@ SIGNATURES = {
     "anoddpm_silu_bwd": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "anoddpm_stem_wgrad": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_vp]),
     "anoddpm_head_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_vp]),
+    "anoddpm_pack_conv_w": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_i64, c_int, c_int, c_vp]),
     "anoddpm_sumsq": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "anoddpm_adamw_ema_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_int,
                                        c_f32, c_f32, c_vp]),

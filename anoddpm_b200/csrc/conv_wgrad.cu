@@ -217,8 +217,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (P.splits == 1) {     // this CTA holds the whole sum: plain 16-byte read-modify-writes (dw is a running gradient)
 #pragma unroll
-                for (int e = 0; e < 16; ++e) atomicAdd(dst + cb + e, __uint_as_float(r[e]) * P.alpha);
+                    for (int e = 0; e < 16; e += 4) {
+                        float4 v = *reinterpret_cast<float4*>(dst + cb + e);
+                        v.x += __uint_as_float(r[e]) * P.alpha; v.y += __uint_as_float(r[e + 1]) * P.alpha;
+                        v.z += __uint_as_float(r[e + 2]) * P.alpha; v.w += __uint_as_float(r[e + 3]) * P.alpha;
+                        *reinterpret_cast<float4*>(dst + cb + e) = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4)     // split-K partial sums: 16-byte vector reductions in L2
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + cb + e),
+                                     "f"(__uint_as_float(r[e]) * P.alpha), "f"(__uint_as_float(r[e + 1]) * P.alpha),
+                                     "f"(__uint_as_float(r[e + 2]) * P.alpha), "f"(__uint_as_float(r[e + 3]) * P.alpha)
+                                     : "memory");
+                }
             }
         }
     }
@@ -301,7 +315,9 @@ extern "C" int anoddpm_conv_wgrad(float* dw, const void* dy16, const void* a16, 
     ADP_REQUIRE(stages >= 2, "anoddpm_conv_wgrad: stage of %d bytes leaves fewer than 2 stages", P.stage_bytes);
     P.stages = stages;
     const int units = P.n_co * P.n_ci * (ksize == 3 ? 3 : 1);
-    int splits = (148 * 2 + units - 1) / units;       // about two waves of CTAs
+    // one CTA per SM (204 KB of shared memory): ONE wave -- units * splits <= 148 -- so no partial second wave; each CTA
+    // then runs a long K loop and pays its epilogue (147 K reductions) once
+    int splits = 148 / units;
     if (splits > P.n_tiles) splits = P.n_tiles;
     if (splits < 1) splits = 1;
     P.splits = splits;

@@ -169,58 +169,69 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(const GnBwdArgs P) {
             }
             if (APPLY) { ag[j] = s_a[g]; bg[j] = s_b[g]; }
         }
-        for (int p = p0 + r; p < p1; p += rows) {
-            const int y = p / P.W, x = p - y * P.W;
-            const size_t pix = (size_t)b * HW + p;
-            float xv[4], d[4];
-            load_x(P, IN16, b, pix, c, sh, xv);
-            load_dpre(P, b, y, x, C, c, d);
-            float dx[4];
+        constexpr int U = APPLY ? 2 : 4;            // pixels in flight per thread (the passes are HBM-latency bound otherwise)
+        for (int pb = p0 + r; pb < p1; pb += rows * U) {
+            float xv[U][4], d[U][4], ad[U][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float xh = (xv[j] - mu[j]) * rs[j];
-                float g = d[j];
-                if (P.silu) {
-                    const float yy = xh * ga[j] + be[j];
-                    const float sg = sigmoid_f(yy);
-                    g *= sg * (1.0f + yy * (1.0f - sg));
-                }
-                if (APPLY) dx[j] = rs[j] * (g * ga[j] - ag[j] - xh * bg[j]);
-                else { acc[j] += g; acc[4 + j] += g * xh; }
-            }
-            if (APPLY) {
-                if (P.add_mode) {
-                    float t[4];
+            for (int u = 0; u < U; ++u) {
+                const int p = pb + u * rows;
+                if (p >= p1) continue;
+                const int y = p / P.W, x = p - y * P.W;
+                const size_t pix = (size_t)b * HW + p;
+                load_x(P, IN16, b, pix, c, sh, xv[u]);
+                load_dpre(P, b, y, x, C, c, d[u]);
+                if (APPLY && P.add_mode) {
                     if (P.add_mode == 1) {
-                        load4(P.add, P.add16, pix * C + c, t);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) dx[j] += t[j];
+                        load4(P.add, P.add16, pix * C + c, ad[u]);
                     } else if (P.add_mode == 2) {
-                        load4(P.add, P.add16, (((size_t)b * (P.H >> 1) + (y >> 1)) * (P.W >> 1) + (x >> 1)) * C + c, t);
+                        load4(P.add, P.add16, (((size_t)b * (P.H >> 1) + (y >> 1)) * (P.W >> 1) + (x >> 1)) * C + c, ad[u]);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) dx[j] += 0.25f * t[j];
+                        for (int j = 0; j < 4; ++j) ad[u][j] *= 0.25f;
                     } else {
+                        float t[4];
+                        ad[u][0] = ad[u][1] = ad[u][2] = ad[u][3] = 0.f;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             load4(P.add, P.add16, (((size_t)b * (2 * P.H) + 2 * y + (i >> 1)) * (2 * P.W) + 2 * x + (i & 1)) * C + c, t);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) dx[j] += t[j];
+                            for (int j = 0; j < 4; ++j) ad[u][j] += t[j];
                         }
                     }
                 }
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[j] += dx[j];
-                if (IN16) {
-                    const __half2 h0 = __floats2half2_rn(dx[0], dx[1]), h1 = __floats2half2_rn(dx[2], dx[3]);
-                    uint2 u;
-                    u.x = *reinterpret_cast<const uint32_t*>(&h0);
-                    u.y = *reinterpret_cast<const uint32_t*>(&h1);
-                    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(P.dx1) + pix * P.C1 + c) = u;
-                } else {
-                    F4 o;
-                    o.x = dx[0]; o.y = dx[1]; o.z = dx[2]; o.w = dx[3];
-                    if (c < P.C1) st4(reinterpret_cast<float*>(P.dx1) + pix * P.C1 + c, o);
-                    else st4(P.dx2 + pix * P.C2 + (c - P.C1), o);
+            for (int u = 0; u < U; ++u) {
+                const int p = pb + u * rows;
+                if (p >= p1) continue;
+                const size_t pix = (size_t)b * HW + p;
+                float dx[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float xh = (xv[u][j] - mu[j]) * rs[j];
+                    float g = d[u][j];
+                    if (P.silu) {
+                        const float yy = xh * ga[j] + be[j];
+                        const float sg = __fdividef(1.0f, 1.0f + __expf(-yy));
+                        g *= sg * (1.0f + yy * (1.0f - sg));
+                    }
+                    if (APPLY) dx[j] = rs[j] * (g * ga[j] - ag[j] - xh * bg[j]) + (P.add_mode ? ad[u][j] : 0.f);
+                    else { acc[j] += g; acc[4 + j] += g * xh; }
+                }
+                if (APPLY) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[j] += dx[j];
+                    if (IN16) {
+                        const __half2 h0 = __floats2half2_rn(dx[0], dx[1]), h1 = __floats2half2_rn(dx[2], dx[3]);
+                        uint2 uu;
+                        uu.x = *reinterpret_cast<const uint32_t*>(&h0);
+                        uu.y = *reinterpret_cast<const uint32_t*>(&h1);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(P.dx1) + pix * P.C1 + c) = uu;
+                    } else {
+                        F4 o;
+                        o.x = dx[0]; o.y = dx[1]; o.z = dx[2]; o.w = dx[3];
+                        if (c < P.C1) st4(reinterpret_cast<float*>(P.dx1) + pix * P.C1 + c, o);
+                        else st4(P.dx2 + pix * P.C2 + (c - P.C1), o);
+                    }
                 }
             }
         }
@@ -531,6 +542,27 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(float* __restrict__ dw,
     }
 }
 
+// ---------------------------------------------------------------- weight packs for the tensor-core convolutions
+// OIHW (or OI1) fp32 parameter -> fp16 pack, saturating round to nearest.  One thread per (row, column) pair moves the
+// ksize^2 taps of that pair.   normal:     dst[co][col_offset + tap * Cin + ci]              (forward operand, K-major)
+//                              transposed: dst[ci][col_offset + (T - 1 - tap) * Cout + co]   (data-gradient operand: the
+// spatially flipped, in/out-transposed filter).  The fast thread index follows the destination's contiguous dimension.
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(256) pack_w_kernel(__half* __restrict__ dst, const float* __restrict__ w, int Cout, int Cin,
+                                                     int T, long long row_stride, int col_offset) {
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (long long)Cout * Cin) return;
+    int co, ci;
+    if (TRANSPOSED) { co = (int)(idx % Cout); ci = (int)(idx / Cout); }
+    else { ci = (int)(idx % Cin); co = (int)(idx / Cin); }
+    const float* src = w + ((size_t)co * Cin + ci) * T;
+    for (int t = 0; t < T; ++t) {
+        const float v = fminf(fmaxf(src[t], -65504.f), 65504.f);
+        if (TRANSPOSED) dst[(size_t)ci * row_stride + col_offset + (size_t)(T - 1 - t) * Cout + co] = __float2half_rn(v);
+        else dst[(size_t)co * row_stride + col_offset + (size_t)t * Cin + ci] = __float2half_rn(v);
+    }
+}
+
 bool al16b(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -660,6 +692,19 @@ extern "C" int anoddpm_head_bwd(void* da_f16, float* dw, float* dbias, const flo
     int rpc = 64;
     while (rpc > 1 && adp_ceil_div(rows, rpc) < 148 * 4) rpc >>= 1;
     head_wgrad_kernel<<<adp_ceil_div(rows, rpc), 256, 0, st>>>(dw, dbias, dy, static_cast<const __half*>(a_f16), B, H, W, C, alpha, rpc);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}
+
+extern "C" int anoddpm_pack_conv_w(void* dst_f16, const float* w, int Cout, int Cin, int ksize, int64_t row_stride,
+                                   int col_offset, int transposed, void* stream) {
+    ADP_REQUIRE(dst_f16 && w && Cout > 0 && Cin > 0 && (ksize == 1 || ksize == 3) && row_stride > 0 && col_offset >= 0,
+                "anoddpm_pack_conv_w: bad arguments");
+    const long long n = (long long)Cout * Cin;
+    const int T = ksize * ksize;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (transposed) pack_w_kernel<true><<<adp_ceil_div(n, 256), 256, 0, st>>>(static_cast<__half*>(dst_f16), w, Cout, Cin, T, row_stride, col_offset);
+    else pack_w_kernel<false><<<adp_ceil_div(n, 256), 256, 0, st>>>(static_cast<__half*>(dst_f16), w, Cout, Cin, T, row_stride, col_offset);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }

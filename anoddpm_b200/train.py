@@ -94,20 +94,33 @@ def _conv(a16, w_packed16, bias, B, H, W, cout, ksize, r=None, emb=None, emb_str
     return out, st, out_f16
 
 
+def _ksize(w):
+    return 1 if (w.dim() == 3 or w.shape[-1] == 1) else 3
+
+
 def _pack_fwd(weights):
-    """forward pack [Cout][taps*Cin (+ Cskip)] fp16 of one or two OIHW / OI1 parameters"""
-    parts = [pack_conv_weight(w.detach()) for w in weights]
-    return torch.cat(parts, dim=1).clamp(-65504.0, 65504.0).half().contiguous()
+    """forward pack [Cout][taps*Cin (+ Cskip)] fp16 of one or two OIHW / OI1 parameters (one native pass each)"""
+    cout = weights[0].shape[0]
+    widths = [w.shape[1] * _ksize(w) ** 2 for w in weights]
+    ktot = sum(widths)
+    out = torch.empty((cout, ktot), device=weights[0].device, dtype=torch.float16)
+    off = 0
+    for w, n in zip(weights, widths):
+        wd = w.detach()
+        assert wd.is_contiguous() and wd.dtype == torch.float32
+        call("anoddpm_pack_conv_w", ptr(out), ptr(wd), cout, w.shape[1], _ksize(w), ktot, off, 0, stream())
+        off += n
+    return out
 
 
 def _pack_dgrad(w):
     """data-gradient pack: d_a = conv(dy, w') with w'[ci][tap'][co] = w[co][ci][2-ky][2-kx] (flipped, transposed)"""
-    w = w.detach()
-    if w.dim() == 3:
-        w = w.unsqueeze(-1)
-    co, ci, kh, kw = w.shape
-    wf = w.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, kh * kw * co)
-    return wf.clamp(-65504.0, 65504.0).half().contiguous()
+    wd = w.detach()
+    assert wd.is_contiguous() and wd.dtype == torch.float32
+    co, ci, k = w.shape[0], w.shape[1], _ksize(w)
+    out = torch.empty((ci, k * k * co), device=w.device, dtype=torch.float16)
+    call("anoddpm_pack_conv_w", ptr(out), ptr(wd), co, ci, k, k * k * co, 0, 1, stream())
+    return out
 
 
 # Data gradients that feed an ELEMENTWISE consumer (the GroupNorm backward) stay fp32 by default: an fp16 store there is
@@ -120,7 +133,7 @@ def _dgrad(w, dy16, B, H, W, want_f16=None):
     """gradient wrt the conv input: [B][H][W][Cin] fp32 (fp16 on request, halo-reuse kernel only); returns (tensor, is_f16)"""
     if want_f16 is None:
         want_f16 = DA_F16
-    ksize = 1 if (w.dim() == 3 or w.shape[-1] == 1) else 3
+    ksize = _ksize(w)
     cin = w.shape[1]
     out, _, f16 = _conv(dy16, _pack_dgrad(w), None, B, H, W, cin, ksize, out_f16=want_f16)
     return out, f16
@@ -242,9 +255,10 @@ class _HeadFn(torch.autograd.Function):
     """GroupNorm -> SiLU -> conv3x3(C -> 1) (UNet.py:384-388), output NCHW"""
 
     @staticmethod
-    def forward(ctx, cx, h, gn_w, gn_b, w, b, gn):
+    def forward(ctx, cx, h, st, gn_w, gn_b, w, b, gn):
         B, H, W, C = h.shape
-        st = _stats(h, B, H * W)
+        if st is None:
+            st = _stats(h, B, H * W)
         out = torch.empty((B, w.shape[0], H, W), device=h.device, dtype=torch.float32)
         wp = pack_conv_weight(w.detach()).contiguous().float()
         call("anoddpm_conv_head_gn", ptr(out), ptr(h), ptr(st), ptr(gn_w), ptr(gn_b), ptr(wp), ptr(b), B, C, H, W, w.shape[0],
@@ -269,7 +283,7 @@ class _HeadFn(torch.autograd.Function):
         call("anoddpm_head_bwd", ptr(da16), ptr(dwp), ptr(dbias), ptr(dyc), ptr(a16), ptr(wp), B, H, W, C, float(alpha), stream())
         dh, _, dg, db, _ = _gn_bwd(h, False, st, None, None, gn, None, None, 0, da16, True, None, 0, 0, B, H, W, True, 0, alpha)
         dw = dwp.view(3, 3, C).permute(2, 0, 1).reshape(1, C, 3, 3).contiguous()
-        return None, dh, dg, db, dw, dbias, None
+        return None, dh, None, dg, db, dw, dbias, None
 
 
 class _TimeMLPFn(torch.autograd.Function):
@@ -342,8 +356,16 @@ class _EmbProjFn(torch.autograd.Function):
         ones = torch.ones(B, device=dev, dtype=torch.float32)
         dbias = torch.empty(S, device=dev, dtype=torch.float32)
         _gemm(dbias, ones, d_rows, 1, S, B, 0, 1, S, 1, S, alpha)
-        d_se = torch.empty((B, E), device=dev, dtype=torch.float32)
-        _gemm(d_se, d_rows, wcat, B, E, S, S, 1, E, 1, E)
+        # d_se[b][k] = sum_n d_rows[b][n] wcat[n][k]: the reduction (S ~ 12 K) is split over the batch dimension of the GEMM
+        KS = 256
+        nz = (S + KS - 1) // KS
+        if S % KS == 0:
+            part = torch.empty((nz, B, E), device=dev, dtype=torch.float32)
+            _gemm(part, d_rows, wcat, B, E, KS, S, 1, E, 1, E, n1=nz, n2=1, sa=(KS, 0), sb=(KS * E, 0), sc=(B * E, 0))
+            d_se = part.sum(dim=0)
+        else:
+            d_se = torch.empty((B, E), device=dev, dtype=torch.float32)
+            _gemm(d_se, d_rows, wcat, B, E, S, S, 1, E, 1, E)
         d_emb = torch.empty((B, E), device=dev, dtype=torch.float32)
         call("anoddpm_silu_bwd", ptr(d_emb), ptr(d_se), ptr(emb), B * E, stream())
         grads = []
@@ -359,7 +381,7 @@ class _ResFn(torch.autograd.Function):
     then gn1.w, gn1.b, conv1.w, conv1.b, gn2.w, gn2.b, conv2.w, conv2.b [, skip.w, skip.b]"""
 
     @staticmethod
-    def forward(ctx, cx, rb, emb_off, x1, x2, rows, *p):
+    def forward(ctx, cx, rb, emb_off, x1, st1, x2, st2, rows, *p):
         gn1, gn2 = rb.in_layers[0], rb.out_layers[0]
         conv1_w, conv1_b, conv2_w, conv2_b = p[2], p[3], p[6], p[7]
         skip_conv = len(p) > 8
@@ -372,8 +394,10 @@ class _ResFn(torch.autograd.Function):
         if rb.out_layers[2].p > 0:
             raise NotImplementedError("native training: dropout > 0 is not implemented")
         Ho, Wo = (H // 2, W // 2) if mode == 1 else ((H * 2, W * 2) if mode == 2 else (H, W))
-        st1 = _stats(x1, B, H * W)
-        st2 = _stats(x2, B, H * W) if x2 is not None else None
+        if st1 is None:        # statistics come out of the producing conv's epilogue where there is one
+            st1 = _stats(x1, B, H * W)
+        if x2 is not None and st2 is None:
+            st2 = _stats(x2, B, H * W)
         a1, raw = _gn_apply(x1, st1, x2, st2, gn1, B, H, W, True, mode, want_raw=skip_conv or mode == 1)
         S = rows.shape[1]
         emb = _View(rows, emb_off)
@@ -389,20 +413,24 @@ class _ResFn(torch.autograd.Function):
             a2, _ = _gn_apply(h, st_h, None, None, gn2, B, Ho, Wo, True, 0)
         if skip_conv:
             assert mode == 0
-            out, _, _ = _conv(a2, _pack_fwd([conv2_w, p[8]]), (conv2_b + p[9]).detach().float().contiguous(), B, Ho, Wo, cout, 3, r=raw)
+            out, st_out, _ = _conv(a2, _pack_fwd([conv2_w, p[8]]), (conv2_b + p[9]).detach().float().contiguous(), B, Ho, Wo, cout, 3,
+                                   r=raw, want_stats=True)
         elif mode == 1:
-            out, _, _ = _conv(a2, _pack_fwd([conv2_w]), conv2_b, B, Ho, Wo, cout, 3, res=raw, res_mode=1)     # raw = pooled x (fp32)
+            out, st_out, _ = _conv(a2, _pack_fwd([conv2_w]), conv2_b, B, Ho, Wo, cout, 3, res=raw, res_mode=1, want_stats=True)   # raw = pooled x
         else:
-            impl3 = _lib.lib().anoddpm_conv_tc3_supported
-            out, _, _ = _conv(a2, _pack_fwd([conv2_w]), conv2_b, B, Ho, Wo, cout, 3, res=x1, res_mode=1 if mode == 0 else 3)
+            out, st_out, _ = _conv(a2, _pack_fwd([conv2_w]), conv2_b, B, Ho, Wo, cout, 3, res=x1, res_mode=1 if mode == 0 else 3,
+                                   want_stats=True)
+        if st_out is None:
+            st_out = _stats(out, B, Ho * Wo)
         ctx.cx, ctx.rb, ctx.emb_off, ctx.meta = cx, rb, emb_off, (mode, skip_conv, B, H, W, Ho, Wo, C1, C2, cout, h16, S)
         ctx.x2_none = x2 is None
         ctx.save_for_backward(x1, x2 if x2 is not None else x1, st1, st2 if st2 is not None else st1, a1,
                               raw if (skip_conv and raw is not None) else a1, h, st_h, a2, rows, *p)
-        return out
+        ctx.mark_non_differentiable(st_out)
+        return out, st_out
 
     @staticmethod
-    def backward(ctx, d_out):
+    def backward(ctx, d_out, _d_st=None):
         x1, x2, st1, st2, a1, raw, h, st_h, a2, rows = ctx.saved_tensors[:10]
         p = ctx.saved_tensors[10:]
         mode, skip_conv, B, H, W, Ho, Wo, C1, C2, cout, h16, S = ctx.meta
@@ -444,7 +472,7 @@ class _ResFn(torch.autograd.Function):
             add, add_mode, add_f16 = d_out, {0: 1, 1: 2, 2: 3}[mode], False
         dx1, dx2, dg1, dbt1, _ = _gn_bwd(x1, False, st1, x2, st2, gn1, None, None, 0, d_a1, d_a1_f16, add, add_mode, add_f16, B, H, W,
                                          True, mode, alpha)
-        return (None, None, None, dx1, dx2, d_rows, dg1, dbt1, dw1, db1, dg2, dbt2, dw2, db2) + grads_skip
+        return (None, None, None, dx1, None, dx2, None, d_rows, dg1, dbt1, dw1, db1, dg2, dbt2, dw2, db2) + grads_skip
 
 
 class _AttnFn(torch.autograd.Function):
@@ -452,11 +480,12 @@ class _AttnFn(torch.autograd.Function):
     params: norm.w, norm.b, to_qkv.w, to_qkv.b, proj_out.w, proj_out.b"""
 
     @staticmethod
-    def forward(ctx, cx, ab, x, *p):
+    def forward(ctx, cx, ab, x, st, *p):
         B, H, W, C = x.shape
         T, heads = H * W, ab.num_heads
         gn = ab.norm
-        st = _stats(x, B, T)
+        if st is None:
+            st = _stats(x, B, T)
         xn, _ = _gn_apply(x, st, None, None, gn, B, H, W, False, 0)
         qkv, _, _ = _conv(xn, _pack_fwd([p[2]]), p[3], B, H, W, 3 * C, 1)
         a = torch.empty((B, H, W, C), device=x.device, dtype=torch.float16)
@@ -466,13 +495,16 @@ class _AttnFn(torch.autograd.Function):
             call("anoddpm_attention_tc", ptr(a), ptr(qkv), ptr(ws), B, T, C, heads, 2, stream())
         else:
             call("anoddpm_attention", ptr(a), ptr(qkv), B, T, C, heads, 2, stream())
-        out, _, _ = _conv(a, _pack_fwd([p[4]]), p[5], B, H, W, C, 1, res=x, res_mode=1)
+        out, st_out, _ = _conv(a, _pack_fwd([p[4]]), p[5], B, H, W, C, 1, res=x, res_mode=1, want_stats=True)
+        if st_out is None:
+            st_out = _stats(out, B, T)
         ctx.cx, ctx.ab = cx, ab
         ctx.save_for_backward(x, st, xn, qkv, a, *p)
-        return out
+        ctx.mark_non_differentiable(st_out)
+        return out, st_out
 
     @staticmethod
-    def backward(ctx, d_out):
+    def backward(ctx, d_out, _d_st=None):
         x, st, xn, qkv, a = ctx.saved_tensors[:5]
         p = ctx.saved_tensors[5:]
         ab = ctx.ab
@@ -516,7 +548,7 @@ class _AttnFn(torch.autograd.Function):
         d_xn, d_xn_f16 = _dgrad(p[2], dq16.view(B, H, W, C3), B, H, W, want_f16=False)
         dx, _, dg, db, _ = _gn_bwd(x, False, st, None, None, ab.norm, None, None, 0, d_xn, d_xn_f16, d_out, 1, False, B, H, W, False, 0,
                                    alpha)
-        return None, None, dx, dg, db, dwq, dbq, dwp, dbp
+        return None, None, dx, None, dg, db, dwq, dbq, dwp, dbp
 
 
 # ---------------------------------------------------------------------------------------------------------- driver
@@ -547,6 +579,7 @@ def forward_train(model, x, time):
         rows = _EmbProjFn.apply(cx, emb, *wb)
 
         def run_seq(seq, h, skip=None):
+            """h, skip: (tensor, statistics-or-None) pairs"""
             for layer in seq:
                 if isinstance(layer, ResBlock):
                     ps = [layer.in_layers[0].weight, layer.in_layers[0].bias, layer.in_layers[2].weight, layer.in_layers[2].bias,
@@ -555,18 +588,19 @@ def forward_train(model, x, time):
                         if layer.skip_connection.kernel_size != (1, 1):
                             raise NotImplementedError("ResBlock(use_conv=True) skip has no native kernel")
                         ps += [layer.skip_connection.weight, layer.skip_connection.bias]
-                    h = _ResFn.apply(cx, layer, offs[id(layer)], h, skip, rows, *ps)
+                    x2, st2 = skip if skip is not None else (None, None)
+                    h = _ResFn.apply(cx, layer, offs[id(layer)], h[0], h[1], x2, st2, rows, *ps)
                     skip = None
                 elif isinstance(layer, AttentionBlock):
                     assert skip is None
-                    h = _AttnFn.apply(cx, layer, h, layer.norm.weight, layer.norm.bias, layer.to_qkv.weight, layer.to_qkv.bias,
-                                      layer.proj_out.weight, layer.proj_out.bias)
+                    h = _AttnFn.apply(cx, layer, h[0], h[1], layer.norm.weight, layer.norm.bias, layer.to_qkv.weight,
+                                      layer.to_qkv.bias, layer.proj_out.weight, layer.proj_out.bias)
                 else:
                     raise NotImplementedError(f"{type(layer).__name__} has no native training kernels")
             return h
 
         stem = model.down[0][0]
-        h = _StemFn.apply(cx, x, stem.weight, stem.bias)
+        h = (_StemFn.apply(cx, x, stem.weight, stem.bias), None)
         skips = [h]
         for seq in list(model.down)[1:]:
             h = run_seq(seq, h)
@@ -575,5 +609,5 @@ def forward_train(model, x, time):
         for seq in model.up:
             h = run_seq(seq, h, skip=skips.pop())
         gn, conv = model.out[0], model.out[2]
-        out = _HeadFn.apply(cx, h, gn.weight, gn.bias, conv.weight, conv.bias, gn)
+        out = _HeadFn.apply(cx, h[0], h[1], gn.weight, gn.bias, conv.weight, conv.bias, gn)
         return _OutputGate.apply(cx, out)

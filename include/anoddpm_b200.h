@@ -276,6 +276,13 @@ int anoddpm_stem_wgrad(float* dw, const void* dy_f16, const float* x, int B, int
 int anoddpm_head_bwd(void* da_f16, float* dw, float* dbias, const float* dy, const void* a_f16, const float* w, int B, int H,
                      int W, int C, float alpha, void* stream);
 
+/* fp16 operand pack of a convolution weight (OIHW / OI1 fp32, the nn.Parameter): transposed = 0 the forward pack
+ * dst[co][col_offset + tap * Cin + ci] (rows of row_stride halves; a fused 1x1 skip weight goes behind the 9 taps with
+ * col_offset = 9 * Cin); transposed = 1 the data-gradient pack dst[ci][col_offset + (T-1-tap) * Cout + co] (flipped,
+ * in/out swapped), so that d_input = anoddpm_conv(d_output, pack).  Parameters change every optimiser step; one pass each. */
+int anoddpm_pack_conv_w(void* dst_f16, const float* w, int Cout, int Cin, int ksize, int64_t row_stride, int col_offset,
+                        int transposed, void* stream);
+
 /* ------------------------------------------------------------------ training: fused optimiser step -------- */
 
 /* *out += sum(g[i]^2) in fp64 (caller zeroes).  First half of torch.nn.utils.clip_grad_norm_ (diffusion_training.py:104). */
