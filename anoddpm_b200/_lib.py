@@ -27,6 +27,7 @@ SIGNATURES = {
     "anoddpm_abi_version": (c_int, []),
     "anoddpm_last_error": (ctypes.c_char_p, []),
     "anoddpm_build_info": (ctypes.c_char_p, []),
+    "anoddpm_fp64_fma_probe": (c_int, [c_vp, c_int, c_int, c_vp]),
     "anoddpm_simplex_init": (c_int, [c_i64, c_vp]),
     "anoddpm_simplex_init_batch": (c_int, [c_vp, c_int, c_vp]),
     "anoddpm_simplex_noise": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp, c_int, c_f64, c_f64, c_vp]),

@@ -50,6 +50,39 @@ def FPR(real_mask, recon_mask):
     return torch.sum(FP).float() / ((torch.sum(FP) + torch.sum(TN)).float() + 1e-6)
 
 
+def ROC_AUC(real_mask, square_error):
+    """(fpr, tpr, thresholds) of the pixel-wise squared error as an anomaly score (evaluation.py:79-83: sklearn's
+    roc_curve on the flattened arrays, on the host -- the reference's definition; ``auc_histogram`` is the device path)"""
+    from sklearn.metrics import roc_curve
+    if isinstance(real_mask, torch.Tensor):
+        return roc_curve(real_mask.detach().cpu().numpy().flatten(), square_error.detach().cpu().numpy().flatten())
+    return roc_curve(real_mask.flatten(), square_error.flatten())
+
+
+def AUC_score(fpr, tpr):
+    from sklearn.metrics import auc
+    return auc(fpr, tpr)
+
+
+def auc_histogram(real_mask, square_error, bins=65536):
+    """Area under the ROC curve on the DEVICE, no host copy of the images: the scores are binned (uniform bins over
+    [0, max]), positives / negatives counted per bin, and the trapezoid rule over the bin edges gives
+    AUC = sum_b neg_b * (pos_above_b + pos_b / 2) / (P * N) -- exactly sklearn's roc_curve + auc for scores quantised to
+    the bins (ties inside a bin get half credit).  Per image when the inputs are batched (dim 0)."""
+    m = real_mask.reshape(real_mask.shape[0], -1) > 0
+    s = square_error.reshape(square_error.shape[0], -1).float()
+    out = []
+    for b in range(s.shape[0]):
+        hi = s[b].max().clamp_min(1e-30)
+        idx = (s[b] / hi * (bins - 1)).round().long().clamp_(0, bins - 1)
+        pos = torch.bincount(idx[m[b]], minlength=bins).double()
+        neg = torch.bincount(idx[~m[b]], minlength=bins).double()
+        P, N = pos.sum(), neg.sum()
+        above = P - torch.cumsum(pos, 0)                       # positives in strictly higher bins
+        out.append((neg * (above + 0.5 * pos)).sum() / (P * N).clamp_min(1.0))
+    return torch.stack(out)
+
+
 def detection_counts(image, recon, mask, threshold=0.5):
     """(B, 6) float64 on the device: n11, n10, n01, n00, sum of squared error, max(image) per image."""
     _lib.require_cuda(image, "image")

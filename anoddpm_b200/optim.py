@@ -41,6 +41,27 @@ class GradReducer:
     def reset(self):
         self.next_bucket = 0
         self.handles = []
+        self._done = None
+
+    def track(self, offsets, sizes):
+        """per-tensor completion tracking for ``tensor_done``: tensors sorted by offset"""
+        order = sorted(range(len(offsets)), key=lambda i: offsets[i])
+        self._offsets = [offsets[i] for i in order]
+        self._rank = {i: r for r, i in enumerate(order)}
+        self._n = len(order)
+
+    def tensor_done(self, i):
+        """the gradient of tensor i is final (autograd's post-accumulate hook): buckets whose whole range is final are
+        reduced at once, even when the tensors of a layer complete in arbitrary order"""
+        if not self.active():
+            return
+        if self._done is None:
+            self._done = [False] * self._n
+            self._tail = self._n               # tensors [tail, n) are final
+        self._done[self._rank[i]] = True
+        while self._tail > 0 and self._done[self._tail - 1]:
+            self._tail -= 1
+        self.mark_ready(self._offsets[self._tail] if self._tail < self._n else self.flat_g.numel())
 
     def active(self):
         return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
@@ -108,6 +129,11 @@ class FusedAdamWEMA:
         self.steps = 0
         self._sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
         self.reducer = GradReducer(self.flat_g, self.offsets, [p.numel() for p in self.params])
+        self.reducer.track(self.offsets, [p.numel() for p in self.params])
+        # overlap: as soon as autograd has accumulated a parameter's gradient it reports in; complete tail buckets go out on
+        # NCCL while the backward of the earlier layers is still running
+        for i, p in enumerate(self.params):
+            p.register_post_accumulate_grad_hook(lambda _p, i=i: self.reducer.tensor_done(i))
 
     def _bind_grads(self):
         """p.grad = view into the flat gradient buffer (gradients accumulate straight into it)"""

@@ -104,7 +104,7 @@ class ClockSampler:
 
 def build_unet(device):
     from anoddpm_b200 import UNetModel
-    from oracle.unet_oracle import fill_state_dict   # deterministic synthetic weights only (no oracle compute)
+    from anoddpm_b200.synth import fill_state_dict   # deterministic key-addressed synthetic weights
     m = UNetModel(**UNET_KW).eval()
     m.load_state_dict(fill_state_dict(m.state_dict(), seed=1))
     return m.to(device)
@@ -173,44 +173,70 @@ def run_native(args):
         ms = ev0.elapsed_time(ev1)
         steps_per_image = 1.0
     else:
+        # device-timed steps and the end-to-end chain are measured ALTERNATELY (two rounds each, same power / thermal state);
+        # `value` and `e2e` are the means of their rounds
         t_start = torch.full((B,), T_DISTANCE - 1, device=dev, dtype=torch.int64)
         x = diff.sample_q(x_host.to(dev), t_start, noise_fn(x_host.to(dev), t_start))
         launches["n"] += 1
         x = reverse_steps(x, T_DISTANCE - 1, args.warmup)
+        chain(x_host, 3)
         torch.cuda.synchronize(); D.barrier()
-        clocks.mark(); l0, e0 = launches["n"], eng.launches
-        ev0.record()
-        h0 = time.perf_counter()
-        x = reverse_steps(x, T_DISTANCE - 1 - args.warmup, args.steps)
-        host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / args.steps   # host time to ENQUEUE one step (no sync)
-        ev1.record(); torch.cuda.synchronize(); D.barrier()
-        ms = ev0.elapsed_time(ev1)
+        clocks.mark()
+        k_e2e = max(3, min(args.steps, 25))
+        ms_rounds, e2e_rounds, t_hi = [], [], T_DISTANCE - 1 - args.warmup
+        l0 = e0 = None
+        for rnd in range(2):
+            torch.cuda.synchronize(); D.barrier()
+            if rnd == 0:
+                l0, e0 = launches["n"], eng.launches
+            ev0.record()
+            h0 = time.perf_counter()
+            x = reverse_steps(x, t_hi, args.steps)
+            if rnd == 0:
+                host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / args.steps   # host time to ENQUEUE one step (no sync)
+            ev1.record(); torch.cuda.synchronize(); D.barrier()
+            if rnd == 0:
+                l1, e1n = launches["n"], eng.launches
+            ms_rounds.append(ev0.elapsed_time(ev1))
+            t_hi -= args.steps
+            t0 = time.perf_counter()
+            ev0.record()
+            y = chain(x_host, k_e2e)
+            ev1.record(); torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) * 1e3
+            e2e_rounds.append(max(ev0.elapsed_time(ev1), wall) / k_e2e)   # .cpu() completes after the last event: slower clock
+        ms = float(np.mean(ms_rounds))
         steps_per_image = float(T_DISTANCE)
     clk = clocks.stop()
     per_fwd = getattr(eng, "launches_per_forward", 0)
     fwd_timed = args.steps * (T_DISTANCE if args.full_chain else 1)
     # eager: the engine counted every launch; graph replay: launches per captured step x replays
-    n_launch = (launches["n"] - l0) + ((eng.launches - e0) if args.no_graphs else per_fwd * fwd_timed)
+    if args.full_chain:
+        n_launch = (launches["n"] - l0) + ((eng.launches - e0) if args.no_graphs else per_fwd * fwd_timed)
+    else:
+        n_launch = (l1 - l0) + ((e1n - e0) if args.no_graphs else per_fwd * fwd_timed)
     ms = D.max_over_ranks(ms, dev)
     ms_per_step = ms / args.steps
     value = world * B / (steps_per_image * ms_per_step / 1e3)
 
     # ---- end-to-end through the public API with host buffers (H2D of the batch + D2H of the result inside the timed region)
-    k_e2e = max(2, min(args.steps, 25))
-    chain(x_host, 2)
-    torch.cuda.synchronize(); D.barrier()
-    t0 = time.perf_counter()
-    ev0.record()
-    y = chain(x_host, k_e2e)
-    ev1.record(); torch.cuda.synchronize()
-    e2e_ms = D.max_over_ranks(ev0.elapsed_time(ev1), dev) / k_e2e
-    wall_ms = (time.perf_counter() - t0) * 1e3 / k_e2e
-    e2e_ms = max(e2e_ms, D.max_over_ranks(wall_ms, dev))     # .cpu() completes after the last event; take the slower clock
+    if args.full_chain:
+        k_e2e = 3
+        chain(x_host, 2)
+        torch.cuda.synchronize(); D.barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        y = chain(x_host, k_e2e)
+        ev1.record(); torch.cuda.synchronize()
+        e2e_rounds = [max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3) / k_e2e]
+    e2e_ms = D.max_over_ranks(float(np.mean(e2e_rounds)), dev)
     img_bytes = B * 256 * 256 * 4
     e2e = {"value": world * B / (T_DISTANCE * e2e_ms / 1e3), "unit": "images/s",
            "h2d_bytes_per_step": int(img_bytes / k_e2e + B * 1024), "d2h_bytes_per_step": int(img_bytes / k_e2e),
            "api": f"x_pinned.to(cuda) -> GaussianDiffusionModel.sample_q + reverse_steps (= forward_backward(unet, x, None, "
-                  f"t_distance={k_e2e}, 'simplex')) -> .cpu(); per-step time x 800 steps/image",
+                  f"t_distance={k_e2e}, 'simplex')) -> .cpu(); per-step time x 800 steps/image; measured alternately with the "
+                  f"device-timed steps (rounds: {[round(v, 3) for v in e2e_rounds]} ms/step e2e, "
+                  f"{[round(v / args.steps, 3) for v in (ms_rounds if not args.full_chain else [ms])]} ms/step device)",
            "finite": bool(torch.isfinite(y).all())}
 
     out = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
@@ -225,7 +251,9 @@ def run_native(args):
                       "parallelism": f"dp{world} (images sharded by index, no collective in the loop)",
                       "l2": "working set per step >> 126 MB L2 (no explicit flush)", "conv_impl": model.conv_impl,
                       "cuda_graph": bool(diff.use_cuda_graphs)},
-           "e2e": e2e, "gpu_launches": int(n_launch), "clocks": clk, "tc_convs_per_forward": eng.tc_convs,
+           "e2e": e2e, "secondary": {"t_distance": 250, "value": value * T_DISTANCE / 250.0, "unit": "images/s",
+                                     "note": "the reference's own ROC sweep uses t_distance=250 (detection.py:503): same per-step time, 250 steps/image"},
+           "gpu_launches": int(n_launch), "clocks": clk, "tc_convs_per_forward": eng.tc_convs,
            "host_enqueue_ms_per_step": host_enqueue_ms, "fused_gn_stats_per_forward": getattr(eng, "fused_stats", 0),
            "gn_stats_passes_per_forward": getattr(eng, "stats_passes", 0)}
 
@@ -234,7 +262,7 @@ def run_native(args):
         torch.cuda.empty_cache()
         out["roofline"] = roofline(model, dev, B)
         out["aux_rooflines"] = aux_rooflines(dev)
-        out["cpu_baseline"] = cpu_baseline(sample_steps=2) if world == 1 and not args.no_cpu_baseline else None
+        out["cpu_baseline"] = cpu_baseline() if world == 1 and not args.no_cpu_baseline else None
         print(json.dumps(out))
     D.barrier()
 
@@ -251,55 +279,96 @@ def _time_ms(fn, n=10, warm=3):
     return e0.elapsed_time(e1) / n
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel/shape (conv 128->128 @256^2 bs 32,
-# fp16 operands, fp32 output) from the committed `ncu --set full` capture profiles/r01g_ncu_conv_tc3_singlebox.md
-NCU_TRAFFIC_DOMINANT = {"bytes": 0.600577e9 + 1.022959e9, "source": "profiles/r01g_ncu_conv_tc3_singlebox.md"}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel/shape in its PRODUCTION form (conv1 of a
+# ResBlock, 128->128 @256^2 bs 32: operand-side GroupNorm + SiLU, +bias/embedding statistics, fp16 output) from the committed
+# `ncu --set full` capture profiles/r02_ncu_conv_tc3_gn.md (algorithmic: 0.537 GB read + 0.537 GB written)
+NCU_TRAFFIC_DOMINANT = {"bytes": 0.600738e9 + 0.498947e9, "source": "profiles/r02_ncu_conv_tc3_gn.md"}
 
 
 def roofline(model, dev, B):
     """Dominant kernel = the tensor-core conv (conv_tc3_kernel).  Live CUDA-event timing, through the same C-ABI entry
-    point the engine uses, of the three conv shapes that carry 61% of the UNet MACs; the
-    headline entry is the single most frequent shape (128->128 @256^2: 9 launches per forward, 31% of the MACs)."""
+    point the engine uses, of the three conv shapes that carry 61% of the UNet MACs, each in the
+    THREE forms it takes: `plain` (no epilogue extras -- the favourable variant round 1 quoted), `conv1` = the production
+    first conv of a ResBlock (operand-side GroupNorm + SiLU on raw fp16 boxes, + embedding row, statistics, fp16 output) and
+    `conv2` = the production second conv (operand-side GroupNorm, + fp32 residual, statistics, fp32 output + fp16 copy).
+    The headline `achieved` is the PRODUCTION conv1 form of the most frequent shape (128->128 @256^2)."""
     import ctypes
     from anoddpm_b200 import _lib
-    from anoddpm_b200.engine import round_tf32_
     pk = peaks()
-    res = []
-    tot_flop, tot_ms = 0.0, 0.0
     impl = {"tc": 3, "tc_tf32": 3, "tc2": 2, "tc1": 1}.get(model.conv_impl, 0)
     f16 = model.conv_impl == "tc"
-    for (Ci, Co, HW, count) in ((128, 128, 256, 9), (256, 128, 256, 3), (128, 128, 128, 9)):
-        a = round_tf32_(torch.randn(B, HW, HW, Ci, device=dev))
-        w = round_tf32_(torch.randn(Co, 9 * Ci, device=dev) * 0.03)
+    fused = f16 and impl == 3 and getattr(model, "fuse_gn", True)
+
+    def run(Ci, Co, HW, form):
+        a = torch.randn(B, HW, HW, Ci, device=dev)
+        w = torch.randn(Co, 9 * Ci, device=dev) * 0.03
         if f16:
             a, w = a.half(), w.half()
         bias = torch.zeros(Co, device=dev)
-        out = torch.empty(B, HW, HW, Co, device=dev)
+        keep = [a, w, bias]
         d = _lib.ConvDesc()
-        d.out, d.a, d.w, d.bias = out.data_ptr(), a.data_ptr(), w.data_ptr(), bias.data_ptr()
         d.B, d.H, d.W, d.Ca, d.Cout, d.ksize, d.impl = B, HW, HW, Ci, Co, 3, impl
-        d.gn_stats = None
         d.operand_f16 = 1 if f16 else 0
+        out_f16 = form == "conv1" and f16 and impl == 3
+        out = torch.empty(B, HW, HW, Co, device=dev, dtype=torch.float16 if out_f16 else torch.float32)
+        d.out, d.a, d.w, d.bias, d.out_f16 = out.data_ptr(), a.data_ptr(), w.data_ptr(), bias.data_ptr(), 1 if out_f16 else 0
+        abytes = a.numel() * a.element_size() + out.numel() * out.element_size() + w.numel() * w.element_size()
+        if form != "plain":
+            st = torch.zeros(8 * B * Co * 2, device=dev, dtype=torch.float64)
+            keep.append(st)
+            d.gn_stats = st.data_ptr()
+            if fused:
+                tab = torch.stack([torch.rand(B, Ci, device=dev) + 0.5, torch.randn(B, Ci, device=dev) * 0.3], dim=-1).contiguous()
+                keep.append(tab)
+                d.gn_table = tab.data_ptr()
+            if form == "conv1":
+                emb = torch.randn(B, Co, device=dev)
+                keep.append(emb)
+                d.emb, d.emb_stride = emb.data_ptr(), Co
+            else:
+                res = torch.randn(B, HW, HW, Co, device=dev)
+                keep.append(res)
+                d.res, d.res_mode = res.data_ptr(), 1
+                abytes += res.numel() * 4
+                if fused:
+                    o16 = torch.empty(B, HW, HW, Co, device=dev, dtype=torch.float16)
+                    keep.append(o16)
+                    d.out16 = o16.data_ptr()
+                    abytes += o16.numel() * 2
         ms = _time_ms(lambda: _lib.call("anoddpm_conv", ctypes.byref(d), _lib.stream()))
         flop = 2.0 * B * HW * HW * Co * 9 * Ci
-        abytes = a.numel() * a.element_size() + out.numel() * 4 + w.numel() * w.element_size()
-        res.append({"shape": f"conv3x3 {Ci}->{Co} @{HW}^2 bs{B}", "ms": ms, "tflops": flop / ms / 1e9,
-                    "count_per_forward": count, "flop": flop, "algorithmic_bytes": abytes})
-        tot_flop += flop * count
-        tot_ms += ms * count
-        del a, w, out
-    dom = res[0]
-    kname = {3: "conv_tc3_kernel (tcgen05.mma.cta_group::2 kind::%s, single-box halo-reuse main loop, persistent CTA pairs, TMA-fed implicit GEMM, TMA-store epilogue)" % ("f16" if f16 else "tf32"),
+        return {"shape": f"conv3x3 {Ci}->{Co} @{HW}^2 bs{B}", "form": form, "ms": ms, "tflops": flop / ms / 1e9, "flop": flop,
+                "algorithmic_bytes": abytes}
+
+    res = []
+    tot_flop, tot_ms = 0.0, 0.0
+    for (Ci, Co, HW, count) in ((128, 128, 256, 9), (256, 128, 256, 3), (128, 128, 128, 9)):
+        forms = ("plain", "conv1", "conv2") if impl == 3 else ("plain",)
+        for form in forms:
+            r = run(Ci, Co, HW, form)
+            r["count_per_forward"] = count
+            res.append(r)
+            if form == forms[-2 if len(forms) > 1 else 0]:       # weight the production conv1 form
+                tot_flop += r["flop"] * count
+                tot_ms += r["ms"] * count
+    dom = next(r for r in res if r["form"] == ("conv1" if impl == 3 else "plain"))
+    kname = {3: "conv_tc3_kernel (tcgen05.mma.cta_group::2 kind::%s, single-box halo-reuse main loop, persistent CTA pairs, TMA-fed "
+                "implicit GEMM%s, TMA-store epilogue)" % ("f16" if f16 else "tf32", ", transform warps apply GroupNorm + SiLU to the landed "
+                                                          "operand boxes" if fused else ""),
              2: "conv_tc2_kernel (tcgen05.mma.cta_group::2, persistent CTA pairs)", 1: "conv_tc_kernel (tcgen05.mma kind::tf32)",
              0: "conv_simt_kernel"}[impl]
     peak = pk["bf16_burst"]      # the kernel is timed alone here -> burst figure (B200_PROFILING.md)
-    return {"bound": "tensor", "kernel": kname, "shape": dom["shape"], "achieved": dom["tflops"], "peak": peak,
+    plain = res[0]
+    return {"bound": "tensor", "kernel": kname, "shape": dom["shape"], "form": dom["form"] + " (production epilogue"
+            + (", operand-side GroupNorm)" if fused else ")"), "achieved": dom["tflops"], "peak": peak,
             "unit": "TFLOP/s", "frac": dom["tflops"] / peak,
             "peak_note": f"dense bf16 cuBLAS burst, {pk['src']} (MEASURED_PEAKS.json); sustained figure {pk['bf16_sustained']}: frac "
                          f"{dom['tflops'] / pk['bf16_sustained']:.3f}" + ("" if f16 else "; kind::tf32 issues at half the bf16 rate"),
+            "plain_variant": {"achieved": plain["tflops"], "frac": plain["tflops"] / peak,
+                              "note": "same shape with no epilogue extras and no operand transform (the variant BENCH_r01 quoted)"},
             "algorithmic": "2*M*N*K flop per launch, M=B*H*W, N=Cout, K=9*Cin", "flop_per_launch": dom["flop"],
             "algorithmic_bytes": dom["algorithmic_bytes"],
-            "traffic": NCU_TRAFFIC_DOMINANT["bytes"] if (f16 and impl == 3 and B == 32) else None,
+            "traffic": NCU_TRAFFIC_DOMINANT["bytes"] if (fused and B == 32) else None,
             "traffic_source": NCU_TRAFFIC_DOMINANT["source"],
             "weighted_3_shapes_tflops": tot_flop / tot_ms / 1e9, "per_shape": res}
 
@@ -382,18 +451,41 @@ def aux_rooflines(dev):
     vol = torch.empty(32, 256, 256, device=dev)
     ms = _time_ms(lambda: _lib.call("anoddpm_simplex_octaves", _lib.ptr(vol), 0, 32, 256, 256, _lib.ptr(tabs), None, 8, 0.8, 64.0,
                                     _lib.stream()))
+    # FP64 roofline denominator, measured like MEASURED_PEAKS.json measures bf16: dependent-FMA probe, best of 10 (burst) and
+    # a back-to-back loop of ~1 s (sustained)
+    probe_out = torch.zeros(8, device=dev, dtype=torch.float64)
+    blocks, iters = 148 * 8, 20000
+    probe = lambda: _lib.call("anoddpm_fp64_fma_probe", _lib.ptr(probe_out), blocks, iters, _lib.stream())   # noqa: E731
+    flop_probe = 2.0 * 8 * iters * 256 * blocks
+    best = min(_time_ms(probe, n=1, warm=1) for _ in range(10))
+    n_sus = max(3, int(1000.0 / max(best, 1e-3)))
+    sus = _time_ms(probe, n=n_sus, warm=0)
+    fp64_burst, fp64_sus = flop_probe / best / 1e9, flop_probe / sus / 1e9
+    gflops = 146.0 * 8 * 32 * 65536 / ms / 1e6
     out["simplex_config5"] = {"bound": "fp64 alu", "shape": "(32,256,256) x 8 octaves, fp32 out", "ms": ms,
-                              "mvox_per_s": 32 * 65536 / ms / 1e3, "gflops_fp64": 146.0 * 8 * 32 * 65536 / ms / 1e6,
+                              "mvox_per_s": 32 * 65536 / ms / 1e3, "gflops_fp64": gflops, "achieved": gflops / 1e3,
+                              "peak": fp64_burst, "unit": "TFLOP/s", "frac": gflops / 1e3 / fp64_burst,
+                              "peak_note": f"measured FP64 FMA probe (anoddpm_fp64_fma_probe): burst {fp64_burst:.1f}, sustained {fp64_sus:.1f} "
+                                           "TFLOP/s counting an fma as 2 flop; the generator is compiled -fmad=false (bit-exact vs the CPU: "
+                                           "separate mul and add, 1 flop per issue slot), so its ceiling is HALF this figure",
+                              "frac_of_unfused_ceiling": gflops / 1e3 / (fp64_burst / 2),
                               "algorithmic": "~146 fp64 flop per voxel-octave (SURVEY App. C.4)"}
     return out
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
-def cpu_reverse_step_seconds(steps, threads):
-    """The oracle port of ONE reverse step at bs 1 (UNet fwd fp32 on torch CPU + C simplex + posterior), timed."""
+CPU_STEPS = 10          # timed reverse steps of the CPU arm (median), after CPU_WARM warm-up steps
+CPU_WARM = 2
+
+
+def cpu_reverse_step_seconds(steps=CPU_STEPS, threads=None, warm=CPU_WARM):
+    """The oracle port of ONE reverse step at bs 1 (UNet fwd fp32 on torch CPU + C simplex + posterior): `steps` timed
+    iterations after `warm` warm-up ones, fixed thread count; returns (median, all samples).  The SAME function feeds
+    `cpu_baseline` of the native arm and `--impl reference`."""
     from oracle import diffusion_oracle as DO, unet_oracle as UO
     from oracle.simplex_oracle import OracleSimplex
     from tests.util_unet import empty_state_dict
+    threads = threads or cpu_threads()
     torch.set_num_threads(threads)
     kw = dict(UNET_KW)
     sd = UO.fill_state_dict(empty_state_dict(img_size=256, base_channels=128, attention_resolutions="16,8"), seed=1)
@@ -401,16 +493,16 @@ def cpu_reverse_step_seconds(steps, threads):
     x = torch.rand(1, 1, 256, 256, generator=torch.Generator().manual_seed(0)) * 2 - 1
     times = []
     with torch.no_grad():
-        for i in range(steps + 1):
+        for i in range(steps + warm):
             t = torch.tensor([T_DISTANCE - 1 - i])
             t0 = time.perf_counter()
             eps = UO.forward(sd, x, t, **kw)
             z = torch.from_numpy(OracleSimplex(1000 + i, threads=threads).rand_3d_fixed_T_octaves(
                 (256, 256), np.array([int(t)]), 6, 0.8, 64).astype(np.float32))[None]
             x = DO.sample_p(tab, x, t, eps, z)["sample"]
-            if i > 0:                      # first iteration = warm-up
+            if i >= warm:
                 times.append(time.perf_counter() - t0)
-    return float(np.mean(times))
+    return float(np.median(times)), times
 
 
 def cpu_threads():
@@ -418,9 +510,9 @@ def cpu_threads():
     return min(os.cpu_count() or 1, 32)
 
 
-def cpu_baseline(sample_steps=2):
+def cpu_baseline():
     threads = cpu_threads()
-    s = cpu_reverse_step_seconds(sample_steps, threads)
+    s, samples = cpu_reverse_step_seconds()
     # simplex microbench (config 5) on the host cores with the C oracle
     from oracle.simplex_oracle import OracleSimplex
     O = OracleSimplex(12345, threads=threads)
@@ -429,25 +521,27 @@ def cpu_baseline(sample_steps=2):
     O.rand_3d_octaves((32, 256, 256), 8, 0.8, 64)
     sx = time.perf_counter() - t0
     return {"value": 1.0 / (T_DISTANCE * s), "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": f"{sample_steps} reverse steps at bs 1 (256x256, same UNet) after 1 warm-up step, "
-                      f"{s:.3f} s/step, extrapolated x800 steps/image", "s_per_step": s,
+            "sample": f"median of {len(samples)} reverse steps at bs 1 (256x256, same UNet) after {CPU_WARM} warm-up steps, "
+                      f"{s:.3f} s/step (min {min(samples):.3f}, max {max(samples):.3f}), extrapolated x800 steps/image",
+            "s_per_step": s,
             "simplex_config5_mvox_per_s": 32 * 65536 / sx / 1e6}
 
 
 def run_reference(args):
     """Reference arm: the reference's own CPU implementation of the path.  The reference is Python and cannot
-    travel to the GPU box, so this times the oracle port (pinned bit-identical to it on CPU) on the host cores."""
+    travel to the GPU box, so this times the oracle port (pinned bit-identical to it on CPU) on the host cores -- the same
+    function, thread count and sample as the native arm's `cpu_baseline`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = cpu_threads()
-    steps = max(1, min(args.steps, 3))
-    s = cpu_reverse_step_seconds(steps, threads)
+    s, samples = cpu_reverse_step_seconds()
     v = 1.0 / (T_DISTANCE * s)
     cb = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
-          "sample": f"{steps} reverse steps at bs 1 after 1 warm-up, {s:.3f} s/step, x800 steps/image"}
+          "sample": f"median of {len(samples)} reverse steps at bs 1 after {CPU_WARM} warm-up steps, {s:.3f} s/step "
+                    f"(min {min(samples):.3f}, max {max(samples):.3f}), x800 steps/image"}
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
-                      "steps": steps, "warmup": 1, "ms_per_step": s * 1e3, "higher_is_better": True, "scaling": "weak",
+                      "steps": len(samples), "warmup": CPU_WARM, "ms_per_step": s * 1e3, "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": "same chain as the native arm, oracle port on host CPU, bs 1 sample", "t_distance": T_DISTANCE},
                       "cpu_baseline": cb,

@@ -225,6 +225,10 @@ long long anoddpm_attention_tc_workspace_bytes(int B, int T, int C);
 int anoddpm_attention_tc(void* out, const float* qkv, void* workspace, int B, int T, int C, int heads, int out_mode,
                          void* stream);
 
+/* FP64 FMA throughput probe: `blocks` CTAs of 256 threads run iters x 8 dependent fma per thread (2 * 8 * iters * 256 *
+ * blocks flop).  bench.py times it to obtain the FP64 roofline denominator of the simplex generator. */
+int anoddpm_fp64_fma_probe(double* out, int blocks, int iters, void* stream);
+
 /* ------------------------------------------------------------------ training: backward kernels ------------- */
 
 /* Weight gradient of a 3x3 (padding 1) or 1x1 convolution on tcgen05 tensor cores (what autograd computes for

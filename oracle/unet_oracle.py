@@ -142,21 +142,7 @@ def forward(sd, x, t, img_size, base_channels, channel_mults="", num_res_blocks=
 
 
 def fill_state_dict(sd, seed=0):
-    """Deterministic, key-addressed weights (so zero-initialised reference tensors, SURVEY F8, carry signal,
-    and so the same values can be regenerated on any machine without shipping a checkpoint).
-    weight ~ U(-1,1)*fan_in^-1/2 ; norm weight ~ 1+0.2*U ; bias ~ 0.2*U."""
-    import zlib
-    out = {}
-    for k in sd.keys():
-        v = sd[k]
-        g = torch.Generator().manual_seed((zlib.crc32(k.encode()) + 7919 * seed) & 0x7FFFFFFF)
-        u = torch.rand(v.shape, generator=g, dtype=torch.float32) * 2 - 1
-        if v.dim() >= 2:
-            fan_in = v[0].numel()
-            u = u * fan_in ** -0.5
-        elif k.endswith("weight"):
-            u = 1 + 0.2 * u
-        else:
-            u = 0.2 * u
-        out[k] = u
-    return out
+    """Deterministic, key-addressed synthetic weights: the filler lives in anoddpm_b200/synth.py (it is input generation,
+    not oracle arithmetic, and bench.py's native arm must not import oracle/); kept here under its old name for the tests."""
+    from anoddpm_b200.synth import fill_state_dict as _fill
+    return _fill(sd, seed)

@@ -60,8 +60,17 @@ REDUCE_WORKER = textwrap.dedent("""
     red.mark_ready(600); launched.append(red.next_bucket)         # bucket 0 goes out while "backward" continues
     red.mark_ready(300); launched.append(red.next_bucket)
     red.finish()                                                  # the rest + wait + divide by the world size
+    # per-tensor completion in arbitrary order (autograd's post-accumulate hooks): a bucket goes out when ALL its tensors are final
+    g2 = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    red2 = GradReducer(g2, offsets, sizes, bucket_elems=350)
+    red2.track(offsets, sizes)
+    seq = []
+    for i in (3, 4, 1, 2, 0):                                     # tensor 4 = [900, 1000), 3 = [600, 900), ...
+        red2.tensor_done(i)
+        seq.append(red2.next_bucket)
+    red2.finish()
     with open(os.path.join(os.environ["ADP_OUT"], f"red{rank}.json"), "w") as f:
-        json.dump({"launched": launched, "g": g.tolist()}, f)
+        json.dump({"launched": launched, "g": g.tolist(), "seq": seq, "g2": g2.tolist()}, f)
     D.shutdown()
 """) % ROOT
 
@@ -80,3 +89,5 @@ def test_two_rank_bucketed_gradient_average(tmp_path):
     rows = [json.load(open(tmp_path / f"red{r}.json")) for r in range(2)]
     assert rows[0]["launched"] == rows[1]["launched"] == [0, 1, 1]
     assert rows[0]["g"] == rows[1]["g"] == [1.5 * i for i in range(1000)]
+    assert rows[0]["seq"] == rows[1]["seq"] == [0, 1, 1, 2, 3]    # bucket (600,1000) after tensors 3+4, (100,600) after 1+2, (0,100) last
+    assert rows[0]["g2"] == rows[1]["g2"] == [1.5 * i for i in range(1000)]
