@@ -262,6 +262,7 @@ class UNetModel(nn.Module):
         # "tc" only: GroupNorm + SiLU are applied to the raw fp16 operand boxes inside the 3x3 convolutions (conv_tc3's
         # transform warps) wherever the producer left an fp16 copy -- no stand-alone normalisation pass, no normalised copy
         self.fuse_gn = os.environ.get("ANODDPM_FUSE_GN", "1") != "0"
+        self.fuse_gn2 = os.environ.get("ANODDPM_FUSE_GN2", "1") == "1"     # also the second GroupNorm of a ResBlock
 
     # -- native inference path ---------------------------------------------------------------------
     def engine(self):

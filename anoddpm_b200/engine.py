@@ -360,7 +360,10 @@ class UNetEngine:
             del a1
         if e["skip_conv"] and raw is None and plan2[1]:
             plan2 = (plan2[0], False)      # no fp16 raw copy available: run conv2 with TF32 operands
-        fuse2 = self.fuse_gn and plan2 == (3, True) and h.shift is not None
+        # GroupNorm 2 inside conv2: in kernel-microseconds about equal to the stand-alone fp16 -> fp16 pass + plain conv2 (conv2's
+        # residual / statistics epilogue already loads the SM next to the MMAs), and the step time under the board's power cap
+        # is the same within noise (26.4-26.5 ms both ways, A/B on one box); kept on: 4 B/element less HBM traffic
+        fuse2 = self.fuse_gn and self.fuse_gn2 and plan2 == (3, True) and h.shift is not None
         if fuse2:
             # GroupNorm 2 + SiLU inside conv2 (the table carries the bias + embedding offset the fp16 h leaves out)
             tab2 = self._gn_table([h], e["gn2"], B, Ho * Wo)
@@ -465,6 +468,7 @@ class UNetEngine:
         self.h1_f16 = self.allow_f16 and getattr(m, "h1_fp16", True)
         # GroupNorm + SiLU applied to the operand boxes inside the 3x3 convs (no normalised copies in HBM)
         self.fuse_gn = self.h1_f16 and getattr(m, "fuse_gn", True)
+        self.fuse_gn2 = getattr(m, "fuse_gn2", True)
         self.gn_tables = 0
         self.f16_outputs = 0
         self.f16_convs = 0

@@ -230,7 +230,7 @@ def test_resblock_with_fused_skip_conv_residual_stream_scale(scale):
     eng = UNetEngine.__new__(UNetEngine)
     eng.launches = eng.fused_stats = eng.stats_passes = eng.tc_convs = eng.f16_convs = eng.f16_outputs = 0
     eng.use_tc, eng.tc_impl, eng.allow_f16, eng.h1_f16, eng.tc_min_channels = True, 3, True, True, 0
-    eng.fuse_gn, eng.gn_tables = True, 0
+    eng.fuse_gn, eng.fuse_gn2, eng.gn_tables = True, True, 0
     eng.emb_w, eng.emb_b, eng.emb_off = [], [], 0
     y = eng.run_resblocks([net.b1, net.b2], x, emb)
     r = rel(y, ref)
