@@ -69,6 +69,8 @@ SIGNATURES = {
     "anoddpm_conv_tc_supported": (c_int, [ctypes.POINTER(ConvDesc)]),
     "anoddpm_conv_tc3_supported": (c_int, [ctypes.POINTER(ConvDesc)]),
     "anoddpm_conv_stem": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "anoddpm_conv_head_gn_supported": (c_int, [c_int, c_int, c_int, c_int]),
+    "anoddpm_conv_stem_fused": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "anoddpm_conv_head": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "anoddpm_conv_head_gn": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32,
                              c_vp]),

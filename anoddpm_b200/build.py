@@ -17,7 +17,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path
 # exact-arithmetic translation units: no fma contraction so fp64/fp32 results match the CPU reference bit for bit
 EXACT = {"simplex.cu", "diffusion.cu", "optim.cu"}
 SOURCES = ["abi.cu", "simplex.cu", "diffusion.cu", "unet_ops.cu", "conv_tc.cu", "conv_tc2.cu", "conv_tc3.cu", "attention_tc.cu",
-           "optim.cu", "conv_wgrad.cu", "unet_bwd.cu"]
+           "optim.cu", "conv_wgrad.cu", "unet_bwd.cu", "edge_convs.cu"]
 
 
 def _stale(target, deps):

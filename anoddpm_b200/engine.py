@@ -507,9 +507,18 @@ class UNetEngine:
         stem = self.down[0][0]["conv"]
         C0 = stem.out_channels
         h = torch.empty((B, H, W, C0), device=dev, dtype=torch.float32)
-        call("anoddpm_conv_stem", ptr(h), ptr(x), ptr(stem.weight), ptr(stem.bias), B, Cin, H, W, C0, stream())
+        if Cin == 1 and W % 8 == 0 and 256 % max(C0 // 4, 1) == 0 and C0 % 4 == 0 and self.use_tc:
+            # one pass: features + their GroupNorm statistics (+ the fp16 copy the first conv's operand transform reads)
+            st0 = self._stats_slot(B, C0)
+            h16 = torch.empty((B, H, W, C0), device=dev, dtype=torch.float16) if self.fuse_gn else None
+            call("anoddpm_conv_stem_fused", ptr(h), ptr(h16), ptr(st0), ptr(x), ptr(stem.weight), ptr(stem.bias), B, Cin, H, W, C0,
+                 stream())
+            h = _T(h, st0, t16=h16)
+            self.fused_stats += 1
+        else:
+            call("anoddpm_conv_stem", ptr(h), ptr(x), ptr(stem.weight), ptr(stem.bias), B, Cin, H, W, C0, stream())
+            h = _T(h)
         self.launches += 1
-        h = _T(h)
         skips = [(h, H, W)]
         for entry in self.down[1:]:
             h, H, W = self._entry(entry, [h], B, H, W, need16=True)      # every down output is a skip tensor of the up path

@@ -211,6 +211,14 @@ int anoddpm_conv_head_gn(float* out_nchw, const float* x_nhwc, const double* sta
                          const float* w_packed, const float* bias, int B, int Cin, int H, int W, int Cout, int groups,
                          float eps, void* stream);
 
+/* 1 if anoddpm_conv_head_gn runs its separable single-output form (Cout == 1, C/32 a power of two <= 16, H, W % 16 == 0). */
+int anoddpm_conv_head_gn_supported(int C, int H, int W, int Cout);
+/* Stem for single-channel images in one pass that also emits what the first ResBlock needs: the per-channel GroupNorm
+ * statistics of the output (stats, [REPLICAS][B][Cout][2] fp64, accumulated; may be NULL) and an fp16 copy of the output
+ * (out16, may be NULL) -- the raw operand of a convolution with gn_table.  Cin == 1, W % 8 == 0.  UNet.py:279-281. */
+int anoddpm_conv_stem_fused(float* out_nhwc, void* out16_nhwc, double* stats, const float* x_nchw, const float* w_oihw,
+                            const float* bias, int B, int Cin, int H, int W, int Cout, void* stream);
+
 /* QKV attention on qkv[B][T][3*C] (channel layout [head][q|k|v][ch], UNet.py:146-147):
  * out[b][t][h*ch + c] = sum_s softmax_s( (q_t . k_s) / sqrt(ch) ) v_s[c].   UNet.py:137-153. */
 int anoddpm_attention(void* out /* B x T x C; fp32, or fp16 when out_mode == 2 */, const float* qkv, int B, int T, int C,

@@ -421,3 +421,26 @@ def test_out_of_range_timesteps():
     out = D.sample_p(lambda a, b: torch.zeros_like(a), x, torch.tensor([3, 100], device=DEV), denoise_fn=lambda a, b: torch.zeros_like(a))
     s = out["sample"]
     assert bool(torch.isfinite(s[0]).all()) and bool(torch.isnan(s[1]).all())     # poisoned, not an out-of-bounds read
+
+
+def test_fused_stem_features_statistics_and_fp16_copy():
+    """anoddpm_conv_stem_fused: Conv2d(1 -> C, 3x3) + the per-channel GroupNorm statistics of its output + the fp16 copy,
+    one pass (UNet.py:279-281 followed by the first ResBlock's GroupNorm)."""
+    import torch.nn.functional as F
+    from anoddpm_b200 import _lib
+    g = torch.Generator().manual_seed(12)
+    for (B, H, W, C) in [(3, 32, 48, 128), (1, 256, 256, 128), (2, 16, 8, 64)]:
+        x = torch.randn(B, 1, H, W, generator=g).to(DEV)
+        w = (torch.randn(C, 1, 3, 3, generator=g) * 0.3).to(DEV)
+        b = torch.randn(C, generator=g).to(DEV)
+        out = torch.empty(B, H, W, C, device=DEV)
+        out16 = torch.empty(B, H, W, C, device=DEV, dtype=torch.float16)
+        st = torch.zeros(8, B, C, 2, device=DEV, dtype=torch.float64)
+        _lib.call("anoddpm_conv_stem_fused", _lib.ptr(out), _lib.ptr(out16), _lib.ptr(st), _lib.ptr(x), _lib.ptr(w), _lib.ptr(b), B, 1, H, W,
+                  C, _lib.stream())
+        ref = F.conv2d(x.double(), w.double(), b.double(), padding=1).permute(0, 2, 3, 1)
+        assert rel(out, ref.float()) < 1e-6
+        assert torch.equal(out16, out.half())
+        s = st.sum(0)
+        assert torch.allclose(s[..., 0], ref.sum(dim=(1, 2)), rtol=1e-6, atol=1e-4)
+        assert torch.allclose(s[..., 1], (ref ** 2).sum(dim=(1, 2)), rtol=1e-6, atol=1e-4)

@@ -385,7 +385,8 @@ def test_head_conv_with_fused_groupnorm_silu():
     from anoddpm_b200 import _lib
     from anoddpm_b200.engine import pack_conv_weight
     g = torch.Generator().manual_seed(31)
-    for (B, C, H, W, Co) in [(2, 128, 32, 64, 1), (1, 64, 16, 16, 3), (3, 32, 40, 24, 1)]:
+    for (B, C, H, W, Co) in [(2, 128, 32, 64, 1), (1, 64, 16, 16, 3), (3, 32, 40, 24, 1), (1, 256, 48, 32, 1), (2, 32, 16, 16, 1),
+                             (1, 512, 16, 32, 1)]:
         x = (torch.randn(B, C, H, W, generator=g) * 2 + 0.7).to(DEV)
         w = (torch.randn(Co, C, 3, 3, generator=g) * 0.1).to(DEV)
         bias = torch.randn(Co, generator=g).to(DEV)
