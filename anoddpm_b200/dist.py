@@ -1,8 +1,8 @@
 """Data-parallel plumbing for the detection path: one process per GPU, images sharded by global index,
 no collective inside the sampling loop (each image's chain depends only on its own x, t, seed and the
 replicated weights -- reference detection.py:209-227 iterates images independently).  Only scalar
-results (timings, counts) are reduced at the end.  Training would add one gradient all-reduce per step
-(SURVEY section 8(e)); that path is not native yet.
+results (timings, counts) are reduced at the end.  Training adds the one gradient exchange per step of SURVEY
+section 8(e): optim.GradReducer averages the flat gradient in buckets, tail first, overlapped with the native backward.
 """
 import os
 

@@ -1,18 +1,19 @@
 """UNet inference engine: walks a ``UNetModel`` module tree once, packs its weights for the kernels and
 executes the forward pass as a sequence of C-ABI calls on the current CUDA stream.
 
-Data layout in HBM: activations NHWC fp32 (pixel-major, channels contiguous = the K axis of the implicit
-GEMM, so a 32-channel K-block is one 128-byte TMA row); conv weights packed [Cout][Ktot] K-major with
-Ktot ordered tap-major / channel-minor followed by the 1x1 skip-connection channels; GroupNorm
-statistics fp64 (sum, sum of squares) per (sample, group).
+Data layout in HBM: activations NHWC (pixel-major, channels contiguous = the K axis of the implicit GEMM, so a K-block of one
+pixel is one 128-byte TMA row): the residual stream fp32 (+ a raw fp16 copy where a later conv reads it as an operand),
+conv1 outputs fp16 (convolution sum without bias / embedding); conv weights packed [Cout][Ktot] K-major with Ktot ordered
+tap-major / channel-minor followed by the 1x1 skip-connection channels; GroupNorm statistics fp64 (sum, sum of squares) per
+(sample, CHANNEL) in 8 replicas, emitted by the epilogue of the kernel that produced the tensor.
 
-Fusion map of one ResBlock (reference UNet.py:202-217), 4 launches instead of ~20 library calls:
-    gn_apply(cat(x, skip): +SiLU, +avgpool/upsample, +fp16/TF32 rounding, +rounded raw copy for the skip conv)
-    -> conv3x3(+bias, +timestep-embedding row, +per-channel statistics of h)
-    -> gn_apply(+SiLU) -> conv3x3(+bias, +1x1 skip conv as extra K-blocks | +identity residual with the x_upd
-       resample folded into the epilogue read, +per-channel statistics of the block output)
-Every activation carries its per-channel (sum, sum of squares) out of the conv epilogue that produced it, so GroupNorm
-needs a separate statistics pass only for the few tensors produced by other kernels (stem, 1x1 / 8x8 convs).
+Fusion map of one same-resolution ResBlock (reference UNet.py:202-217), 4 launches instead of ~20 library calls:
+    gn_table(GN1 of x [, skip])  -> conv3x3 whose loader applies GroupNorm + SiLU to the raw fp16 boxes of x [and of the
+       skip tensor: torch.cat folded into the K loop] (+bias, +timestep-embedding row, +statistics of h, fp16 output)
+    gn_table(GN2 of h)           -> conv3x3 with the same operand transform (+bias, +1x1 skip conv on the raw fp16 copies as
+       extra K-blocks | +identity residual, +statistics of the output, fp32 output + fp16 copy for the next block)
+Resampling blocks, attention inputs and tensors without an fp16 copy still take a stand-alone GroupNorm pass
+(gn_apply: +SiLU, +avg-pool / nearest-upsample, +fp16 rounding, +raw copy / pooled residual).
 """
 import ctypes
 
