@@ -596,6 +596,22 @@ class GaussianDiffusionModel:
         x = self.sample_q(x_0, t_tensor, noise_fn(x_0, t_tensor).float())
         return self.reverse_steps(model, x, int(t_distance) - 1, int(t_distance), denoise_fn)
 
+    batch_repeats = True      # detection_A / detection_B: run the total_avg repeats of one t_distance as ONE batched chain set
+
+    def _repeat_chains(self, model, x_0, t_distance, total_avg):
+        """the `total_avg` independent noise -> denoise chains of one image (reference :500-510, 555-565 loops them one by
+        one).  Batched: the image is repeated along the batch axis and every repeat draws its own noise (per-sample simplex
+        seeds / independent Gaussian draws), so the repeats share every kernel launch of the UNet instead of running
+        total_avg x t_distance single-image forwards.  The host RNG is consumed step-major instead of chain-major: the
+        repeats are equally independent draws, but not the same numbers as the sequential order (batch_repeats = False)."""
+        if self.batch_repeats and x_0.shape[0] == 1 and total_avg > 1:
+            x_rep = x_0.expand(total_avg, *x_0.shape[1:]).contiguous()
+            return self._noise_then_denoise(model, x_rep, t_distance, self.noise_fn)
+        output = torch.empty((total_avg, *x_0.shape[1:]), device=x_0.device)
+        for avg in range(total_avg):
+            output[avg, ...] = self._noise_then_denoise(model, x_0, t_distance, self.noise_fn)
+        return output
+
     def detection_A(self, model, x_0, args, file, mask, total_avg=2):
         """Frequency / t_distance sweep with fixed-frequency simplex noise (GaussianDiffusion.py:480-527): every
         sampling chain runs on the native kernels; the PNG output is written when matplotlib is available."""
@@ -606,9 +622,7 @@ class GaussianDiffusionModel:
             self.noise_fn = lambda x, t: generate_simplex_noise(self.simplex, x, t, False, frequency=freq,
                                                                 in_channels=self.img_channels)
             for t_distance in range(50, int(args["T"] * 0.6), 50):
-                output = torch.empty((total_avg, 1, *args["img_size"]), device=x_0.device)
-                for avg in range(total_avg):
-                    output[avg, ...] = self._noise_then_denoise(model, x_0, t_distance, self.noise_fn)
+                output = self._repeat_chains(model, x_0, t_distance, total_avg)
                 output_mean = torch.mean(output, dim=0).reshape(1, 1, *args["img_size"])
                 mse = ((output_mean - x_0).square() * 2) - 1
                 mse_threshold = ((mse > 0).float() * 2) - 1
@@ -631,9 +645,7 @@ class GaussianDiffusionModel:
             self.noise_fn = lambda x, t: torch.randn_like(x)
         dice_coeff = []
         for t_distance in range(50, end, 50):
-            output = torch.empty((total_avg, 1, *args["img_size"]), device=x_0.device)
-            for avg in range(total_avg):
-                output[avg, ...] = self._noise_then_denoise(model, x_0, t_distance, self.noise_fn)
+            output = self._repeat_chains(model, x_0, t_distance, total_avg)
             output_mean = torch.mean(output, dim=[0]).reshape(1, 1, *args["img_size"])
             n_prev = len(os.listdir(out_dir))
             dice = None   # reference: evaluation.heatmap(...) draws a figure and returns None

@@ -306,7 +306,36 @@ def gen_loss():
     print("loss.npz", len(out), "arrays")
 
 
+def gen_eval():
+    """Detection metrics of the reference's evaluation.py:26-87 on synthetic (image, reconstruction, mask) triples: the
+    values detection.py:229-250 computes per image."""
+    import importlib
+    ev = importlib.import_module("evaluation")
+    assert ev.__file__.startswith("/root/reference")
+    out = {}
+    g = torch.Generator().manual_seed(77)
+    for i, (H, W) in enumerate([(64, 64), (32, 48), (256, 256)]):
+        image = torch.rand(1, 1, H, W, generator=g) * 2 - 1
+        recon = (image + torch.randn(1, 1, H, W, generator=g) * 0.6).clamp(-1, 1)
+        mask = (torch.rand(1, 1, H, W, generator=g) > 0.7).float()
+        k = f"case{i}"
+        out[f"{k}/image"], out[f"{k}/recon"], out[f"{k}/mask"] = image.numpy(), recon.numpy(), mask.numpy()
+        mse = (image - recon).square()
+        fpr, tpr, _ = ev.ROC_AUC(mask.to(torch.uint8), mse)
+        out[f"{k}/auc"] = np.array(ev.AUC_score(fpr, tpr))
+        thr = (mse > 0.5).float()
+        out[f"{k}/dice"] = ev.dice_coeff(image, recon, mask, mse=thr).numpy()
+        out[f"{k}/dice_default"] = ev.dice_coeff(image, recon, mask).numpy()
+        out[f"{k}/precision"] = ev.precision(mask, thr).numpy()
+        out[f"{k}/recall"] = ev.recall(mask, thr).numpy()
+        out[f"{k}/fpr"] = ev.FPR(mask, thr).numpy()
+        out[f"{k}/iou"] = np.array(ev.IoU(mask, thr))
+        out[f"{k}/psnr"] = np.array(ev.PSNR(recon, image))
+    np.savez_compressed(os.path.join(HERE, "eval.npz"), **out)
+    print("eval.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["simplex", "diffusion", "unet", "loop", "vlb", "loss"]
+    which = sys.argv[1:] or ["simplex", "diffusion", "unet", "loop", "vlb", "loss", "eval"]
     for w in which:
         globals()["gen_" + w]()
