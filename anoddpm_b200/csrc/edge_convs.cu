@@ -229,6 +229,71 @@ __global__ void __launch_bounds__(256) conv_stem_fused_kernel(float* __restrict_
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ input pipeline (N4)
+// The deterministic part of the reference's MRI transform (dataset.py:585-593: ToPILImage -> CenterCrop(crop) -> Resize(bilinear)
+// -> ToTensor -> Normalize(0.5, 0.5)) for a batch of slices read straight out of cached volumes, BIT-EXACT:
+//   * ToPILImage turns a float32 array into an 8-bit 'L' image: q = uint8(trunc(v * 255));
+//   * CenterCrop pads with 0 to at least crop x crop (left / top = floor(d / 2)) and crops at round-half-even((size - crop) / 2);
+//   * Resize = PIL's 8-bit resampler: triangle filter, half-pixel centres, support scaled by the downscale factor
+//     (antialiasing), coefficients normalised, quantised to 22-bit fixed point, horizontal pass to uint8, then vertical pass:
+//     out = clip8((2^21 + sum pix * kk) >> 22);
+//   * ToTensor (/ 255) and Normalize: (v - 0.5) / 0.5 in fp32.
+// thread = output pixel; slice b = rows of `row_stride` elements starting at vols + vol_offset[b].
+constexpr int RS_MAXT = 32;
+__device__ __forceinline__ int resample_coeffs(int out_i, int in_size, int out_size, int* kk, int& xmin_out) {
+    const double scale = (double)in_size / out_size;
+    const double fs = scale > 1.0 ? scale : 1.0, support = fs, ss = 1.0 / fs;
+    const double center = (out_i + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5), xmax = (int)(center + support + 0.5);
+    if (xmin < 0) xmin = 0;
+    if (xmax > in_size) xmax = in_size;
+    const int n = xmax - xmin;
+    double k[RS_MAXT], ww = 0.0;
+    for (int x = 0; x < n; ++x) {
+        double w = 1.0 - fabs((x + xmin - center + 0.5) * ss);
+        if (w < 0.0) w = 0.0;
+        k[x] = w;
+        ww += w;
+    }
+    for (int x = 0; x < n; ++x) kk[x] = (int)(0.5 + (k[x] / ww) * 4194304.0);      // 1 << 22
+    xmin_out = xmin;
+    return n;
+}
+__global__ void __launch_bounds__(128) slice_resize_kernel(float* __restrict__ out, const float* __restrict__ vols,
+                                                           const long long* __restrict__ vol_offset, int B, int Hs, int Ws,
+                                                           long long row_stride, int crop, int Ho, int Wo) {
+    const long long idx = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (idx >= (long long)B * Ho * Wo) return;
+    const int ox = (int)(idx % Wo), oy = (int)((idx / Wo) % Ho), b = (int)(idx / ((long long)Wo * Ho));
+    const float* src = vols + vol_offset[b];
+    const int pad_l = Ws < crop ? (crop - Ws) / 2 : 0, pad_t = Hs < crop ? (crop - Hs) / 2 : 0;
+    const int Wp = Ws < crop ? crop : Ws, Hp = Hs < crop ? crop : Hs;
+    const int crop_l = (int)rint((Wp - crop) / 2.0), crop_t = (int)rint((Hp - crop) / 2.0);
+    int kx[RS_MAXT], ky[RS_MAXT], x0, y0;
+    const int nx = resample_coeffs(ox, crop, Wo, kx, x0), ny = resample_coeffs(oy, crop, Ho, ky, y0);
+    long long acc = 1LL << 21;
+    for (int j = 0; j < ny; ++j) {
+        const int yy = y0 + j + crop_t - pad_t;                   // row of the original slice (outside: CenterCrop's zero padding)
+        long long h = 1LL << 21;
+        if (yy >= 0 && yy < Hs) {
+            for (int i = 0; i < nx; ++i) {
+                const int xx = x0 + i + crop_l - pad_l;
+                if (xx >= 0 && xx < Ws) {
+                    const float v = src[(long long)yy * row_stride + xx] * 255.0f;
+                    h += (long long)(unsigned char)(int)v * kx[i];          // uint8(trunc(v * 255))
+                }
+            }
+        }
+        long long hq = h >> 22;                                    // horizontal pass result, clipped to 8 bits
+        hq = hq < 0 ? 0 : (hq > 255 ? 255 : hq);
+        acc += hq * ky[j];
+    }
+    long long q = acc >> 22;
+    q = q < 0 ? 0 : (q > 255 ? 255 : q);
+    out[idx] = ((float)q / 255.0f - 0.5f) / 0.5f;
+}
+
 }  // namespace
 
 extern "C" int anoddpm_conv_head_gn_supported(int C, int H, int W, int Cout) {
@@ -266,6 +331,19 @@ extern "C" int anoddpm_conv_stem_fused(float* out_nhwc, void* out16_nhwc, double
     const size_t smem = ((size_t)10 * Cout + 256 * 8) * sizeof(float);
     conv_stem_fused_kernel<<<(unsigned)ctas, 256, smem, (cudaStream_t)stream>>>(out_nhwc, static_cast<__half*>(out16_nhwc), stats,
                                                                                  x_nchw, w_oihw, bias, B, H, W, Cout, spc);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}
+
+extern "C" int anoddpm_slice_resize_norm(float* out, const float* vols, const int64_t* vol_offset, int B, int Hs, int Ws,
+                                         int64_t row_stride, int crop, int Ho, int Wo, void* stream) {
+    ADP_REQUIRE(out && vols && vol_offset && B > 0 && Hs > 0 && Ws > 0 && crop > 0 && Ho > 0 && Wo > 0 && row_stride >= Ws,
+                "anoddpm_slice_resize_norm: bad arguments");
+    const double sc = (double)crop / (Ho < Wo ? Ho : Wo);
+    ADP_REQUIRE(2.0 * (sc > 1.0 ? sc : 1.0) + 2.0 <= RS_MAXT, "anoddpm_slice_resize_norm: downscale factor %.1f needs more than %d taps", sc, RS_MAXT);
+    const long long n = (long long)B * Ho * Wo;
+    slice_resize_kernel<<<adp_ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(out, vols, (const long long*)vol_offset, B, Hs, Ws,
+                                                                                row_stride, crop, Ho, Wo);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }

@@ -219,6 +219,14 @@ int anoddpm_conv_head_gn_supported(int C, int H, int W, int Cout);
 int anoddpm_conv_stem_fused(float* out_nhwc, void* out16_nhwc, double* stats, const float* x_nchw, const float* w_oihw,
                             const float* bias, int B, int Cin, int H, int W, int Cout, void* stream);
 
+/* Input pipeline: the deterministic part of the reference's MRI slice transform on the device
+ * (dataset.py:585-593, 631-640: image[:, s, :] -> ToPILImage -> CenterCrop(crop) -> Resize(bilinear) -> ToTensor ->
+ * Normalize(0.5, 0.5)).  Sample b reads its slice at vols + vol_offset[b] with rows row_stride elements apart (so a slice
+ * of a cached [Hs][D][Ws] volume needs no host-side gather); out is (B, 1, Ho, Wo) fp32.  The random affine jitter of the
+ * training transform is NOT applied here. */
+int anoddpm_slice_resize_norm(float* out, const float* vols, const int64_t* vol_offset /* [device] */, int B, int Hs, int Ws,
+                              int64_t row_stride, int crop, int Ho, int Wo, void* stream);
+
 /* QKV attention on qkv[B][T][3*C] (channel layout [head][q|k|v][ch], UNet.py:146-147):
  * out[b][t][h*ch + c] = sum_s softmax_s( (q_t . k_s) / sqrt(ch) ) v_s[c].   UNet.py:137-153. */
 int anoddpm_attention(void* out /* B x T x C; fp32, or fp16 when out_mode == 2 */, const float* qkv, int B, int T, int C,

@@ -335,7 +335,26 @@ def gen_eval():
     print("eval.npz", len(out), "arrays")
 
 
+def gen_pipeline():
+    """Input pipeline: the deterministic part of MRIDataset's transform (dataset.py:585-593 -- the
+    torchvision calls the reference makes, without the RandomAffine jitter) on slices of a synthetic cached volume."""
+    from torchvision import transforms
+    g = np.random.default_rng(5)
+    out = {}
+    vol = g.random((256, 6, 192), dtype=np.float32)
+    out["vol"] = vol
+    for name, size in (("s256", (256, 256)), ("s64", (64, 64)), ("s128x96", (128, 96))):
+        tf = transforms.Compose([transforms.ToPILImage(), transforms.CenterCrop(235),
+                                 transforms.Resize(size, transforms.InterpolationMode.BILINEAR), transforms.ToTensor(),
+                                 transforms.Normalize((0.5), (0.5))])
+        for s in (0, 3):
+            image = vol[:, s:s + 1, :].reshape(256, 192).astype(np.float32)          # dataset.py:631
+            out[f"{name}/slice{s}"] = tf(image).numpy()
+    np.savez_compressed(os.path.join(HERE, "pipeline.npz"), **out)
+    print("pipeline.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["simplex", "diffusion", "unet", "loop", "vlb", "loss", "eval"]
+    which = sys.argv[1:] or ["simplex", "diffusion", "unet", "loop", "vlb", "loss", "eval", "pipeline"]
     for w in which:
         globals()["gen_" + w]()

@@ -55,3 +55,19 @@ def test_fused_metrics_kernel_vs_reference_golden(golden):
         m1 = EV.detection_metrics(im3[i:i + 1], re3[i:i + 1], ma3[i:i + 1])
         assert all(np.isclose(float(m3[key][i]), float(m1[key][0]), rtol=1e-9, equal_nan=True) for key in m3)
     assert np.isclose(float(m3["dice"][0]), float(g["case0/dice"]), rtol=1e-6)
+
+
+@pytest.mark.gpu
+def test_gpu_input_pipeline_vs_reference_transform(golden):
+    """anoddpm_slice_resize_norm: slice extraction + CenterCrop + PIL 8-bit bilinear Resize + ToTensor +
+    Normalize on the device, bit-exact against the torchvision calls of the reference's MRIDataset (tests/golden/pipeline.npz)."""
+    from anoddpm_b200.pipeline import MRISlicePipeline
+    g = golden("pipeline")
+    vol = g["vol"]
+    for name, size in (("s256", (256, 256)), ("s64", (64, 64)), ("s128x96", (128, 96))):
+        P = MRISlicePipeline(img_size=size, crop=235).add_volume("a", vol).add_volume("b", vol[::-1].copy())
+        x = P.batch(["a", "a", "b"], [0, 3, 3])
+        assert x.shape == (3, 1, *size) and x.is_cuda
+        assert np.array_equal(x[0].cpu().numpy(), g[f"{name}/slice0"])
+        assert np.array_equal(x[1].cpu().numpy(), g[f"{name}/slice3"])
+        assert not np.array_equal(x[2].cpu().numpy(), g[f"{name}/slice3"])           # the flipped volume is a different image
