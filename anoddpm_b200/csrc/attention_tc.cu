@@ -14,7 +14,8 @@
 //        GEMM2  O[128][ch] = P Vt^T       same pipeline, K-blocks of 64 keys (Vt tiles loaded while the softmax runs);
 //        epilogue           tcgen05.ld, x 1/sum, store fp32 / TF32-rounded fp32 / fp16 into out[B][T][C].
 //   Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..5 softmax + epilogue.
-// Contract (anoddpm_attention_tc_supported): T in {64,128,192,256}, ch = C/heads in {64,128,192,256}.
+// Contract (anoddpm_attention_tc_supported): T, ch = C/heads multiples of 64; T <= 256 and ch <= 256 run this kernel,
+// longer sequences (T a multiple of 256) and wider heads the tiled kernel below.
 #include "common.cuh"
 #include "anoddpm_b200.h"
 #include <cuda.h>
@@ -324,6 +325,244 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------------- attention, tiled
+// The same attention for long sequences and wide heads (T > 256 keys or ch > 256 channels: what the reference's constructor
+// defaults instantiate -- attention at 32x32 maps = 1024 tokens, a single head of 256 / 512 channels; UNet.py:232, 106-112).
+// S no longer fits the 512 TMEM columns next to O, so the keys are processed in tiles of TK = 256:
+//   pass 1  for every key tile: S_j = Q K_j^T into TMEM columns [0, TK); thread-per-row running MAXIMUM only;
+//   pass 2  for every key tile: S_j again, P_j = exp2((S_j - max) log2 e) rounded to fp16 into shared memory (row sums of
+//           the rounded values), O += P_j V_j into TMEM columns [256, 256 + chs).
+// (max-first instead of an online rescale of O: no TMEM read-modify-write of the accumulator; the price is QK^T twice.)
+// Heads wider than 256 channels split their OUTPUT channels over gridDim.z CTAs (each recomputes S over the full head).
+// T <= 256 (one tile) skips pass 1 and takes the maximum inside the tile like attention_tc_kernel.
+__global__ void __launch_bounds__(kThreads, 1)
+attention_tc_tiled_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                          const __grid_constant__ CUtensorMap map_v, const AttnArgs P, int TK, int chs) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;                                   // [kStages][kStageBytes]
+    uint8_t* sP = smem + kStages * kStageBytes;             // [TK/64][128 rows][128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * kQBytes);
+    uint64_t* full = bars;                 // [kStages]
+    uint64_t* empty = bars + kStages;      // [kStages]
+    uint64_t* s_full = bars + 2 * kStages; // S_j accumulated
+    uint64_t* s_empty = s_full + 1;        // S_j read by all 128 rows (pass 1)
+    uint64_t* p_full = s_full + 2;         // P_j staged in shared memory (128 arrivals)
+    uint64_t* p_empty = s_full + 3;        // P_j consumed by GEMM 2
+    uint64_t* o_full = s_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * 128, bh = blockIdx.y, split = blockIdx.z;
+    const int T = P.T, ch = P.ch;
+    const int ntiles = (T + TK - 1) / TK;
+    const int npass1 = ntiles > 1 ? ntiles : 0;
+    const int nkb1 = ch / 64, nkb2 = TK / 64;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(s_full, 1);
+        mbar_init(s_empty, 128);
+        mbar_init(p_full, 128);
+        mbar_init(p_empty, 1);
+        mbar_init(o_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (elect_one()) {
+            int it = 0;
+            for (int g = 0; g < npass1 + ntiles; ++g) {
+                const bool pass2 = g >= npass1;
+                const int j = pass2 ? g - npass1 : g;
+                for (int kb = 0; kb < nkb1; ++kb, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], (uint32_t)(kQBytes + TK * 128));
+                    tma_load_3d(ring + s * kStageBytes, &map_q, &full[s], kb * 64, m0, bh);            // rows >= T: zeros
+                    tma_load_3d(ring + s * kStageBytes + kQBytes, &map_k, &full[s], kb * 64, j * TK, bh);
+                }
+                if (pass2) {
+                    for (int kb = 0; kb < nkb2; ++kb, ++it) {
+                        const int s = it % kStages;
+                        mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+                        mbar_expect_tx(&full[s], (uint32_t)(chs * 128));
+                        tma_load_3d(ring + s * kStageBytes + kQBytes, &map_v, &full[s], j * TK + kb * 64, split * chs, bh);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TK >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc2 = (1u << 4) | ((uint32_t)(chs >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        int it = 0, n_se = 0, n_pf = 0;
+        for (int g = 0; g < npass1 + ntiles; ++g) {
+            const bool pass2 = g >= npass1;
+            const int j = pass2 ? g - npass1 : g;
+            // S may be overwritten once every row has read the previous pass-1 tile (pass-2 tiles hand S over through p_full)
+            if (g > 0 && g <= npass1) {
+                mbar_wait(s_empty, n_se & 1);
+                ++n_se;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            for (int kb = 0; kb < nkb1; ++kb, ++it) {
+                const int s = it % kStages;
+                mbar_wait(&full[s], (it / kStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint64_t ad = make_sdesc(smem_u32(ring + s * kStageBytes));
+                    const uint64_t bd = make_sdesc(smem_u32(ring + s * kStageBytes + kQBytes));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(tmem_base, ad + 2 * k, bd + 2 * k, idesc1, (kb | k) ? 1u : 0u);
+                    umma_commit(&empty[s]);
+                    if (kb == nkb1 - 1) umma_commit(s_full);
+                }
+                __syncwarp();
+            }
+            if (pass2) {
+                mbar_wait(p_full, n_pf & 1);
+                ++n_pf;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < nkb2; ++kb, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(&full[s], (it / kStages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const uint64_t ad = make_sdesc(smem_u32(sP + kb * kQBytes));
+                        const uint64_t bd = make_sdesc(smem_u32(ring + s * kStageBytes + kQBytes));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16(tmem_base + kOCol, ad + 2 * k, bd + 2 * k, idesc2, (j | kb | k) ? 1u : 0u);
+                        umma_commit(&empty[s]);
+                        if (kb == nkb2 - 1) {
+                            umma_commit(p_empty);
+                            if (j == ntiles - 1) umma_commit(o_full);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ---------------- softmax + epilogue: thread = query row ----------------
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const float kLog2e = 1.4426950408889634f;
+        float mx = -INFINITY, sum = 0.f;
+        int n_sf = 0, n_pe = 0;
+        for (int g = 0; g < npass1; ++g, ++n_sf) {            // pass 1: row maximum over all key tiles
+            mbar_wait(s_full, n_sf & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int c = 0; c < TK; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(trow + (uint32_t)c, v);
+#pragma unroll
+                for (int q = 0; q < 32; ++q) mx = fmaxf(mx, __uint_as_float(v[q]));
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(s_empty);
+        }
+        for (int j = 0; j < ntiles; ++j, ++n_sf) {            // pass 2: probabilities and P V
+            mbar_wait(s_full, n_sf & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (npass1 == 0) {
+                for (int c = 0; c < TK; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(trow + (uint32_t)c, v);
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) mx = fmaxf(mx, __uint_as_float(v[q]));
+                }
+            }
+            const float mxs = mx * kLog2e;
+            if (j > 0) {                                        // GEMM 2 of the previous tile must have read sP
+                mbar_wait(p_empty, n_pe & 1);
+                ++n_pe;
+            }
+            for (int c = 0; c < TK; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(trow + (uint32_t)c, v);
+                uint32_t h2[16];
+#pragma unroll
+                for (int q = 0; q < 32; q += 2) {
+                    const float p0 = exp2f(fmaf(__uint_as_float(v[q]), kLog2e, -mxs));
+                    const float p1 = exp2f(fmaf(__uint_as_float(v[q + 1]), kLog2e, -mxs));
+                    const __half2 hp = __floats2half2_rn(p0, p1);
+                    const float2 back = __half22float2(hp);
+                    sum += back.x + back.y;
+                    h2[q >> 1] = *reinterpret_cast<const uint32_t*>(&hp);
+                }
+                uint8_t* prow = sP + (c >> 6) * kQBytes + r * 128;
+                const int j0 = (c & 63) >> 3;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    *reinterpret_cast<uint4*>(prow + (((j0 + q) ^ (r & 7)) << 4)) =
+                        make_uint4(h2[4 * q], h2[4 * q + 1], h2[4 * q + 2], h2[4 * q + 3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(p_full);
+        }
+        const float inv = 1.0f / sum;
+        mbar_wait(o_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int t = m0 + r;
+        const int b = bh / P.heads, h = bh - b * P.heads;
+        const size_t o = ((size_t)b * T + t) * P.C + (size_t)h * ch + (size_t)split * chs;
+        for (int c = 0; c < chs; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(trow + (uint32_t)(kOCol + c), v);
+            if (t >= T) continue;
+            if (P.out_mode == 2) {
+                __half* op = reinterpret_cast<__half*>(P.out) + o + c;
+#pragma unroll
+                for (int q = 0; q < 32; q += 8) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float a0 = fminf(fmaxf(__uint_as_float(v[q + 2 * e]) * inv, -65504.f), 65504.f);
+                        const float a1 = fminf(fmaxf(__uint_as_float(v[q + 2 * e + 1]) * inv, -65504.f), 65504.f);
+                        const __half2 hh = __floats2half2_rn(a0, a1);
+                        w[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
+                    *reinterpret_cast<uint4*>(op + q) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            } else {
+                float* op = reinterpret_cast<float*>(P.out) + o + c;
+#pragma unroll
+                for (int q = 0; q < 32; q += 4) {
+                    float a[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        a[e] = __uint_as_float(v[q + e]) * inv;
+                        if (P.out_mode == 1) a[e] = round_tf32(a[e]);
+                    }
+                    *reinterpret_cast<float4*>(op + q) = make_float4(a[0], a[1], a[2], a[3]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -364,7 +603,14 @@ int make_map3(CUtensorMap* m, const void* p, int n0, int n1, int n2, int rows) {
 extern "C" int anoddpm_attention_tc_supported(int T, int C, int heads) {
     if (T <= 0 || C <= 0 || heads <= 0 || C % heads) return 0;
     const int ch = C / heads;
-    return (T % 64 == 0 && T <= 256 && ch % 64 == 0 && ch <= 256) ? 1 : 0;
+    if (T % 64 || ch % 64) return 0;
+    if (T <= 256 && ch <= 256) return 1;                       // one CTA holds S and O in TMEM (attention_tc_kernel)
+    // tiled kernel: key tiles of 256, output channels of wide heads split over CTAs
+    if (T > 256 && T % 256) return 0;
+    if (ch > 1024) return 0;
+    const int nsplit = (ch + 255) / 256;
+    if (ch % nsplit || (ch / nsplit) % 64) return 0;
+    return 1;
 }
 
 extern "C" long long anoddpm_attention_tc_workspace_bytes(int B, int T, int C) {
@@ -375,7 +621,7 @@ extern "C" int anoddpm_attention_tc(void* out, const float* qkv, void* workspace
                                     int out_mode, void* stream) {
     ADP_REQUIRE(out && qkv && workspace && B > 0, "anoddpm_attention_tc: bad arguments");
     ADP_REQUIRE(anoddpm_attention_tc_supported(T, C, heads), "anoddpm_attention_tc: T=%d C=%d heads=%d not supported "
-                "(T and C/heads must be multiples of 64, at most 256)", T, C, heads);
+                "(T and C/heads multiples of 64; T <= 256 or a multiple of 256)", T, C, heads);
     ADP_REQUIRE(out_mode >= 0 && out_mode <= 2, "anoddpm_attention_tc: out_mode must be 0, 1 or 2");
     ADP_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 127) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(qkv) & 15) == 0, "anoddpm_attention_tc: misaligned pointers");
@@ -388,11 +634,14 @@ extern "C" int anoddpm_attention_tc(void* out, const float* qkv, void* workspace
     const float scale = 1.0f / sqrtf(sqrtf((float)ch));
     attn_pack_kernel<<<dim3(ch / 64, T / 64, BH), 256, 0, st>>>(Q, K, Vt, qkv, T, C, heads, scale);
     ADP_LAUNCH_CHECK();
+    const bool tiled = T > 256 || ch > 256;
+    const int TK = T < 256 ? T : 256;
+    const int nsplit = (ch + 255) / 256, chs = ch / nsplit;
     CUtensorMap mq, mk, mv;
     int rc;
     if ((rc = make_map3(&mq, Q, ch, T, BH, 128))) return rc;
-    if ((rc = make_map3(&mk, K, ch, T, BH, T))) return rc;
-    if ((rc = make_map3(&mv, Vt, T, ch, BH, ch))) return rc;
+    if ((rc = make_map3(&mk, K, ch, T, BH, tiled ? TK : T))) return rc;
+    if ((rc = make_map3(&mv, Vt, T, ch, BH, tiled ? chs : ch))) return rc;
     AttnArgs P;
     P.out = out; P.T = T; P.C = C; P.ch = ch; P.heads = heads; P.out_mode = out_mode;
     const size_t smem = (size_t)kStages * kStageBytes + 4 * kQBytes + 256 + 1024;
@@ -401,9 +650,11 @@ extern "C" int anoddpm_attention_tc(void* out, const float* qkv, void* workspace
     ADP_CUDA(cudaGetDevice(&dev_));
     if (!attr_dev[dev_ & 63]) {
         ADP_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(attention_tc_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_dev[dev_ & 63] = true;
     }
-    attention_tc_kernel<<<dim3((T + 127) / 128, BH), kThreads, smem, st>>>(mq, mk, mv, P);
+    if (tiled) attention_tc_tiled_kernel<<<dim3((T + 127) / 128, BH, nsplit), kThreads, smem, st>>>(mq, mk, mv, P, TK, chs);
+    else attention_tc_kernel<<<dim3((T + 127) / 128, BH), kThreads, smem, st>>>(mq, mk, mv, P);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }

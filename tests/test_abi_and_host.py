@@ -153,8 +153,10 @@ def test_support_predicates_and_argument_checks_without_gpu():
 
     assert L.anoddpm_attention_tc_supported(256, 512, 2) == 1 and L.anoddpm_attention_tc_supported(64, 512, 2) == 1
     assert L.anoddpm_attention_tc_supported(64, 512, 8) == 1            # head size 64 (num_head_channels=64)
-    assert L.anoddpm_attention_tc_supported(1024, 256, 2) == 0          # T > 256: CUDA-core kernel
-    assert L.anoddpm_attention_tc_supported(256, 512, 1) == 0           # head size 512: CUDA-core kernel
+    assert L.anoddpm_attention_tc_supported(1024, 256, 2) == 1          # T > 256: key-tiled tcgen05 kernel (32x32 maps)
+    assert L.anoddpm_attention_tc_supported(1024, 256, 1) == 1 and L.anoddpm_attention_tc_supported(256, 512, 1) == 1
+    assert L.anoddpm_attention_tc_supported(64, 512, 1) == 1            # single head of 512 channels (detection.py n_heads=1)
+    assert L.anoddpm_attention_tc_supported(320, 256, 1) == 0           # T > 256 must be a multiple of 256
     assert L.anoddpm_attention_tc_supported(256, 500, 3) == 0
     assert L.anoddpm_attention_tc_workspace_bytes(32, 256, 512) == 3 * 32 * 256 * 512 * 2
 

@@ -331,10 +331,13 @@ def test_attention_tensor_core_vs_reference_formula():
     L = _lib.lib()
     g = torch.Generator().manual_seed(10)
     assert L.anoddpm_attention_tc_supported(256, 512, 2) == 1
-    assert L.anoddpm_attention_tc_supported(1024, 256, 2) == 0
+    assert L.anoddpm_attention_tc_supported(1024, 256, 2) == 1 and L.anoddpm_attention_tc_supported(256, 512, 1) == 1
     assert L.anoddpm_attention_tc_supported(16, 256, 4) == 0
+    # the last four: the tiled kernel (keys in tiles of 256, wide heads split over CTAs) -- what the reference's constructor
+    # defaults instantiate: 32x32 maps = 1024 tokens, a single head of 256 / 512 channels (UNet.py:232; detection.py:168)
     for (B, C, T, heads, scale) in [(2, 512, 256, 2, 1.0), (3, 512, 64, 2, 1.0), (2, 128, 128, 2, 3.0), (1, 192, 192, 1, 1.0),
-                                    (32, 512, 256, 2, 2.0)]:
+                                    (32, 512, 256, 2, 2.0), (2, 256, 1024, 1, 1.0), (1, 256, 1024, 2, 2.0), (2, 512, 256, 1, 1.0),
+                                    (3, 512, 64, 1, 1.5), (1, 384, 512, 1, 1.0)]:
         qkv = (torch.randn(B, 3 * C, T, generator=g) * scale).to(DEV)
         ch = C // heads
         q, k, v = qkv.double().reshape(B * heads, 3 * ch, T).split(ch, dim=1)
