@@ -167,7 +167,7 @@ def test_support_predicates_and_argument_checks_without_gpu():
     d = desc(impl=1, out_f16=1)
     d.out, d.a, d.w = 256, 256, 256
     assert L.anoddpm_conv(ctypes.byref(d), None) < 0 and b"fp16 output" in L.anoddpm_last_error()
-    assert L.anoddpm_attention_tc(res, res, res, 1, 1024, 256, 2, 0, None) < 0 and b"not supported" in L.anoddpm_last_error()
+    assert L.anoddpm_attention_tc(res, res, res, 1, 320, 256, 2, 0, None) < 0 and b"not supported" in L.anoddpm_last_error()
     assert L.anoddpm_gn_apply_f16in(res, res, 100, res, res, res, None, None, 0, 1, 8, 8, 32, 1e-5, 1, 2, None) < 0
     assert L.anoddpm_linear(res, 8, res, 8, res, None, 1, 8, 8, 7, None) < 0
     assert L.anoddpm_vlb_terms(None, None, None, None, None, None, None, None, 10, 1, 16, None) < 0
