@@ -257,6 +257,29 @@ def run_native(args):
            "host_enqueue_ms_per_step": host_enqueue_ms, "fused_gn_stats_per_forward": getattr(eng, "fused_stats", 0),
            "gn_stats_passes_per_forward": getattr(eng, "stats_passes", 0)}
 
+    if rank == 0 and world == 1 and not args.no_default_model:
+        # secondary: the UNet the reference's scripts actually construct when they do not override the attention settings
+        # (UNet.py:232 attention_resolutions="32,16,8"; detection.py:168 n_heads=1): attention at 32x32 (T = 1024, one head of
+        # 256 channels), 16x16 and 8x8 (one head of 512) -- all on the key-tiled tcgen05 attention kernel; 562.6 GFLOP/image
+        from anoddpm_b200 import UNetModel
+        from anoddpm_b200.synth import fill_state_dict
+        x = None
+        torch.cuda.empty_cache()
+        m2 = UNetModel(img_size=256, base_channels=128).eval()
+        m2.load_state_dict(fill_state_dict(m2.state_dict(), seed=1))
+        m2 = m2.to(dev)
+        xs = diff.sample_q(x_host.to(dev), torch.full((B,), T_DISTANCE - 1, device=dev, dtype=torch.int64),
+                           noise_fn(x_host.to(dev), torch.full((B,), T_DISTANCE - 1, device=dev, dtype=torch.int64)))
+        xs = diff.reverse_steps(m2, xs, T_DISTANCE - 1, 4, "simplex")
+        torch.cuda.synchronize()
+        ev0.record()
+        xs = diff.reverse_steps(m2, xs, T_DISTANCE - 5, 8, "simplex")
+        ev1.record(); torch.cuda.synchronize()
+        ms2 = ev0.elapsed_time(ev1) / 8
+        out["secondary_default_model"] = {"model": "UNetModel(256, 128): attention_resolutions='32,16,8', n_heads=1 (562.6 GFLOP/image)",
+                                          "ms_per_step": ms2, "value": B / (T_DISTANCE * ms2 / 1e3), "unit": "images/s",
+                                          "tc_attention_sites": m2.engine().tc_attn, "finite": bool(torch.isfinite(xs).all())}
+        del m2, xs
     if rank == 0:
         x = None
         torch.cuda.empty_cache()
@@ -621,6 +644,7 @@ def main():
     ap.add_argument("--full-chain", action="store_true", help="a step = one whole 800-step chain")
     ap.add_argument("--conv-impl", default=None, choices=[None, "tc", "tc_tf32", "tc2", "tc1", "exact"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-default-model", action="store_true", help="skip the secondary line for the constructor-default UNet")
     ap.add_argument("--no-graphs", action="store_true", help="run the reverse loop eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
