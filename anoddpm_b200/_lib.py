@@ -69,7 +69,6 @@ SIGNATURES = {
     "anoddpm_conv_tc_supported": (c_int, [ctypes.POINTER(ConvDesc)]),
     "anoddpm_conv_tc3_supported": (c_int, [ctypes.POINTER(ConvDesc)]),
     "anoddpm_conv_stem": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
-    "anoddpm_conv_head_gn_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "anoddpm_conv_stem_fused": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "anoddpm_slice_resize_norm": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_i64, c_int, c_int, c_int, c_vp]),
     "anoddpm_conv_head": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),

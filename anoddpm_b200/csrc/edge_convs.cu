@@ -1,14 +1,10 @@
-// anoddpm_b200/csrc/edge_convs.cu -- the two convolutions of the UNet that are not GEMM-shaped (reference UNet.py:279-281
-// stem Conv2d(1 -> C, 3x3), UNet.py:384-388 head GroupNorm -> SiLU -> Conv2d(C -> 1, 3x3)), second generation: both are pure
-// HBM streams over a (B, H, W, C) fp32 tensor and are written to run as such.
-//   stem: out[b,p,:] = sum_tap x[b,p+tap] * w[:,tap] + bias.  One pass that ALSO emits what the first ResBlock needs: the
-//         per-channel GroupNorm statistics of the output (fp64 atomics into the replica layout) and an fp16 copy (the raw
-//         operand of the first conv with operand-side GroupNorm) -- so the stem output is never re-read by a statistics or
-//         normalisation pass.
-//   head: out[b,p] = bias + sum_tap sum_c act(GN(x))[b,p+tap,c] * w[tap][c].  Cout = 1 makes the conv SEPARABLE BY TAP:
-//         phase 1 normalises + activates every input pixel of an 18x18 halo tile once and reduces its C channels against the
-//         nine tap weight vectors (9 dot products per pixel, weights reused across 4 pixels in registers); phase 2 adds the nine
-//         shifted partial maps.  The feature map is read once (plus the halo from L2).
+// anoddpm_b200/csrc/edge_convs.cu -- edge kernels of the path: the fused stem and the device input pipeline.
+//   stem (reference UNet.py:279-281, Conv2d(1 -> C, 3x3)): out[b,p,:] = sum_tap x[b,p+tap] * w[:,tap] + bias in one pass that
+//         ALSO emits what the first ResBlock needs: the per-channel GroupNorm statistics of the output (fp64 atomics into the
+//         replica layout) and an fp16 copy (the raw operand of the first conv with operand-side GroupNorm) -- so the stem
+//         output is never re-read by a statistics or normalisation pass.
+//   (A tap-separable rewrite of the single-output head was measured 0.35 ms per step SLOWER than unet_ops.cu's
+//   conv_head_kernel on one box, 26.49 vs 26.14 ms, and was dropped.)
 #include "common.cuh"
 #include "anoddpm_b200.h"
 #include <cuda_fp16.h>
@@ -18,131 +14,6 @@ namespace {
 struct alignas(16) F4e { float x, y, z, w; };
 __device__ __forceinline__ F4e ld4e(const float* p) { return *reinterpret_cast<const F4e*>(p); }
 __device__ __forceinline__ float silu_e(float y) { return __fdividef(y, 1.0f + __expf(-y)); }
-
-// ------------------------------------------------------------------------------------------------ head (Cout = 1)
-constexpr int HD_T = 16;                  // 16 x 16 output pixels per CTA
-constexpr int HD_IN = HD_T + 2;           // 18 x 18 input pixels
-constexpr int HD_NPIX = HD_IN * HD_IN;    // 324
-
-__global__ void __launch_bounds__(256) conv_head_sep_kernel(float* __restrict__ out, const float* __restrict__ x,
-                                                            const double* __restrict__ stats, const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, const float* __restrict__ w,
-                                                            const float* __restrict__ bias, int B, int C, int H, int W,
-                                                            int groups, float eps) {
-    extern __shared__ __align__(16) float sm_head[];
-    float* s_w = sm_head;                 // [9][C]
-    float* s_sc = s_w + 9 * C;            // [C]
-    float* s_bi = s_sc + C;               // [C]
-    float* s_t = s_bi + C;                // [9][324] partial maps
-    __shared__ float s_mean[64], s_rstd[64];
-    const int tiles_x = W / HD_T, tiles_y = H / HD_T;
-    const int tile = blockIdx.x;
-    const int b = tile / (tiles_x * tiles_y), tr = tile - b * tiles_x * tiles_y;
-    const int y0 = (tr / tiles_x) * HD_T, x0 = (tr % tiles_x) * HD_T;
-    {   // group statistics exactly as gn_apply_kernel: thread (g, r) adds up replica r of group g
-        const int gs = C / groups;
-        const int g = threadIdx.x / ANODDPM_STAT_REPLICAS, r = threadIdx.x % ANODDPM_STAT_REPLICAS;
-        double s = 0.0, q = 0.0;
-        if (g < groups) {
-            for (int c = g * gs; c < (g + 1) * gs; ++c) {
-                const double* sp = stats + (size_t)r * B * C * 2 + ((size_t)b * C + c) * 2;
-                s += sp[0];
-                q += sp[1];
-            }
-        }
-#pragma unroll
-        for (int o = 1; o < ANODDPM_STAT_REPLICAS; o <<= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-            q += __shfl_xor_sync(0xffffffffu, q, o);
-        }
-        if (g < groups && r == 0) {
-            const double n = (double)H * W * gs;
-            const double m = s / n;
-            double var = q / n - m * m;
-            if (var < 0) var = 0;
-            s_mean[g] = (float)m;
-            s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
-        }
-        __syncthreads();
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const int gg = c / gs;
-            const float sc = s_rstd[gg] * gamma[c];
-            s_sc[c] = sc;
-            s_bi[c] = beta[c] - sc * s_mean[gg];
-        }
-        for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_w[i] = w[i];      // packed [tap][c]
-    }
-    __syncthreads();
-    // phase 1: item = (input pixel, 32-channel slice); a thread keeps its slice and walks pixels four at a time
-    const int nsl = C / 32;                        // slices (C % 32 == 0); adjacent threads = adjacent slices of one pixel
-    const int sl = threadIdx.x % nsl, lane_px = threadIdx.x / nsl, npl = 256 / nsl;
-    const unsigned full = 0xffffffffu;
-    const int n_it = (HD_NPIX + 4 * npl - 1) / (4 * npl);      // the same trip count for every thread (warp shuffles below)
-    for (int it = 0; it < n_it; ++it) {
-        const int p0 = lane_px + it * 4 * npl;
-        float acc[4][9];
-        const float* src[4];
-        bool ok[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int p = p0 + u * npl;
-            const int ly = p / HD_IN, lx = p - ly * HD_IN;
-            const int gy = y0 + ly - 1, gx = x0 + lx - 1;
-            ok[u] = p < HD_NPIX && gy >= 0 && gy < H && gx >= 0 && gx < W;
-            src[u] = x + (((size_t)b * H + (ok[u] ? gy : 0)) * W + (ok[u] ? gx : 0)) * C + sl * 32;
-#pragma unroll
-            for (int t = 0; t < 9; ++t) acc[u][t] = 0.f;
-        }
-#pragma unroll 2
-        for (int q = 0; q < 8; ++q) {
-            const int c = sl * 32 + q * 4;
-            const F4e sc = ld4e(s_sc + c), bi = ld4e(s_bi + c);
-            F4e v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                v[u] = ok[u] ? ld4e(src[u] + q * 4) : F4e{0.f, 0.f, 0.f, 0.f};
-                v[u].x = silu_e(v[u].x * sc.x + bi.x);
-                v[u].y = silu_e(v[u].y * sc.y + bi.y);
-                v[u].z = silu_e(v[u].z * sc.z + bi.z);
-                v[u].w = silu_e(v[u].w * sc.w + bi.w);
-            }
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const F4e ww = ld4e(s_w + t * C + c);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    acc[u][t] = fmaf(v[u].x, ww.x, acc[u][t]);
-                    acc[u][t] = fmaf(v[u].y, ww.y, acc[u][t]);
-                    acc[u][t] = fmaf(v[u].z, ww.z, acc[u][t]);
-                    acc[u][t] = fmaf(v[u].w, ww.w, acc[u][t]);
-                }
-            }
-        }
-        // add up the slices of each pixel (adjacent lanes), slice 0 stores the nine partial sums; out-of-image pixels are
-        // the zero padding of the ACTIVATED tensor
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                float a = ok[u] ? acc[u][t] : 0.f;
-                for (int o = 1; o < nsl; o <<= 1) a += __shfl_xor_sync(full, a, o);
-                acc[u][t] = a;
-            }
-            const int p = p0 + u * npl;
-            if (sl == 0 && p < HD_NPIX) {
-#pragma unroll
-                for (int t = 0; t < 9; ++t) s_t[t * HD_NPIX + p] = acc[u][t];
-            }
-        }
-    }
-    __syncthreads();
-    // phase 2: thread = output pixel; tap (ky, kx) reads the partial map of tap at the shifted position
-    const int py = threadIdx.x / HD_T, px = threadIdx.x % HD_T;
-    float o = bias ? bias[0] : 0.f;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) o += s_t[t * HD_NPIX + (py + t / 3) * HD_IN + px + t % 3];
-    out[((size_t)b * H + y0 + py) * W + x0 + px] = o;
-}
 
 // ------------------------------------------------------------------------------------------------ stem (Cin = 1)
 // thread = (4 output channels, pixel lane); a CTA walks 8-pixel row segments; per-channel statistics are kept per thread and
@@ -295,29 +166,6 @@ __global__ void __launch_bounds__(128) slice_resize_kernel(float* __restrict__ o
 }
 
 }  // namespace
-
-extern "C" int anoddpm_conv_head_gn_supported(int C, int H, int W, int Cout) {
-    return Cout == 1 && C % 32 == 0 && C <= 512 && (C / 32 == 1 || C / 32 == 2 || C / 32 == 4 || C / 32 == 8 || C / 32 == 16) &&
-           H % 16 == 0 && W % 16 == 0;
-}
-
-// the separable head: same contract as anoddpm_conv_head_gn, for Cout = 1 and 16-pixel-aligned images
-int anoddpm_conv_head_sep(float* out, const float* x, const double* stats, const float* gamma, const float* beta, const float* w,
-                          const float* bias, int B, int C, int H, int W, int groups, float eps, void* stream) {
-    const long long tiles = (long long)B * (H / HD_T) * (W / HD_T);
-    ADP_REQUIRE(tiles < (1LL << 31), "anoddpm_conv_head_gn: too many tiles");
-    const size_t smem = ((size_t)11 * C + 9 * HD_NPIX) * sizeof(float);
-    static bool attr_dev[64] = {};
-    int dev_ = 0;
-    ADP_CUDA(cudaGetDevice(&dev_));
-    if (!attr_dev[dev_ & 63]) {
-        ADP_CUDA(cudaFuncSetAttribute(conv_head_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_dev[dev_ & 63] = true;
-    }
-    conv_head_sep_kernel<<<(unsigned)tiles, 256, smem, (cudaStream_t)stream>>>(out, x, stats, gamma, beta, w, bias, B, C, H, W, groups, eps);
-    ADP_LAUNCH_CHECK();
-    return ANODDPM_OK;
-}
 
 extern "C" int anoddpm_conv_stem_fused(float* out_nhwc, void* out16_nhwc, double* stats, const float* x_nchw, const float* w_oihw,
                                        const float* bias, int B, int Cin, int H, int W, int Cout, void* stream) {

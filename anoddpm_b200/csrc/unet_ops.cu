@@ -8,8 +8,6 @@
 #include "common.cuh"
 #include "anoddpm_b200.h"
 #include <stdlib.h>
-int anoddpm_conv_head_sep(float* out, const float* x, const double* stats, const float* gamma, const float* beta, const float* w,
-                          const float* bias, int B, int C, int H, int W, int groups, float eps, void* stream);
 #include <cuda_fp16.h>
 #include <math.h>
 
@@ -1064,8 +1062,6 @@ extern "C" int anoddpm_conv_head_gn(float* out, const float* x, const double* st
                 HT_MAXC);
     ADP_REQUIRE(groups > 0 && groups * ANODDPM_STAT_REPLICAS <= 256 && Cin % groups == 0,
                 "anoddpm_conv_head_gn: bad groups (at most 32, dividing Cin)");
-    if (anoddpm_conv_head_gn_supported(Cin, H, W, Cout) && !getenv("ANODDPM_HEAD_V1"))     // separable single-output form (edge_convs.cu)
-        return anoddpm_conv_head_sep(out, x, stats, gamma, beta, w, bias, B, Cin, H, W, groups, eps, stream);
     const long long tiles = (long long)B * adp_ceil_div(H, HT_H) * adp_ceil_div(W, HT_W);
     ADP_REQUIRE(tiles < (1LL << 31), "anoddpm_conv_head_gn: too many tiles");
     cudaStream_t st = (cudaStream_t)stream;

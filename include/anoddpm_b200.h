@@ -211,8 +211,6 @@ int anoddpm_conv_head_gn(float* out_nchw, const float* x_nhwc, const double* sta
                          const float* w_packed, const float* bias, int B, int Cin, int H, int W, int Cout, int groups,
                          float eps, void* stream);
 
-/* 1 if anoddpm_conv_head_gn runs its separable single-output form (Cout == 1, C/32 a power of two <= 16, H, W % 16 == 0). */
-int anoddpm_conv_head_gn_supported(int C, int H, int W, int Cout);
 /* Stem for single-channel images in one pass that also emits what the first ResBlock needs: the per-channel GroupNorm
  * statistics of the output (stats, [REPLICAS][B][Cout][2] fp64, accumulated; may be NULL) and an fp16 copy of the output
  * (out16, may be NULL) -- the raw operand of a convolution with gn_table.  Cin == 1, W % 8 == 0.  UNet.py:279-281. */
