@@ -594,13 +594,13 @@ def run_train(args):
     x_host = (torch.rand(B, 1, 256, 256, generator=g) * 2 - 1).pin_memory()
     losses = []
 
-    def step():
+    def step():     # diffusion_training.py:91-107: batch to the device, p_loss, backward, optimiser + EMA, loss to the host
         x = x_host.to(dev, non_blocking=True)
         opt.zero_grad()
         loss, _ = diff.p_loss(model, x, targs)
         loss.backward()
         opt.step()
-        losses.append(loss.detach())
+        losses.append(loss.data.cpu())
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -619,7 +619,25 @@ def run_train(args):
     ms = D.max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
     D.barrier()
     if rank == 0:
-        print(json.dumps({"metric": "training px/s (256x256 bs 8 per GPU, simplex, AdamW + EMA)", "value": world * B * 65536 / (ms / 1e3),
+        # roofline of the dominant backward kernel: the tcgen05 weight gradient on the most frequent shape (128 -> 128 @256^2)
+        from anoddpm_b200 import _lib
+        pk = peaks()
+        a16 = torch.randn(B, 256, 256, 128, device=dev).half()
+        dy16 = torch.randn(B, 256, 256, 128, device=dev).half()
+        dw = torch.zeros(128, 9, 128, device=dev)
+        wms = _time_ms(lambda: _lib.call("anoddpm_conv_wgrad", _lib.ptr(dw), _lib.ptr(dy16), _lib.ptr(a16), B, 256, 256, 128, 128, 3, 1.0,
+                                         _lib.stream()))
+        wflop = 2.0 * B * 65536 * 128 * 128 * 9
+        roof = {"bound": "tensor", "kernel": "conv_wgrad_kernel (tcgen05.mma kind::f16, MN-major operands from NHWC, halo box shared by 3 taps, "
+                                              "one-wave split-K)", "shape": f"dW of conv3x3 128->128 @256^2 bs{B}", "achieved": wflop / wms / 1e9,
+                "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": wflop / wms / 1e9 / pk["bf16_burst"], "ms": wms,
+                "algorithmic": "2*B*H*W*Cout*Cin*9 flop per launch", "traffic": None}
+        v = world * B * 65536 / (ms / 1e3)
+        print(json.dumps({"metric": "training px/s (256x256 bs 8 per GPU, simplex, AdamW + EMA)", "value": v,
+                          "e2e": {"value": v, "unit": "px/s", "h2d_bytes_per_step": B * 65536 * 4, "d2h_bytes_per_step": 4,
+                                  "api": "x_pinned.to(cuda) -> GaussianDiffusionModel.p_loss -> loss.backward() -> FusedAdamWEMA.step() -> "
+                                         "loss.data.cpu(): the timed step IS the end-to-end step"},
+                          "roofline": roof, "gpu_launches": "about 2800 per step (tools/train_profile.py)",
                           "unit": "px/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f16 tensor-core operands (forward and backward), f32 accumulation / gradients / optimiser",
