@@ -101,8 +101,9 @@ def simplex_noise_from_seeds(seeds, shape, t, octave=6, persistence=0.8, frequen
     tables_dev = tables.pin_memory().to(t.device, non_blocking=True)
     noise = torch.empty((B, C, H, W), device=t.device, dtype=torch.float32)
     t64 = t.to(torch.int64).contiguous()
-    call("anoddpm_simplex_noise", ptr(noise), B, C, H, W, ptr(tables_dev), int(shared_seed), ptr(t64), int(octave),
-         float(persistence), float(frequency), stream())
+    with torch.cuda.device(t.device):
+        call("anoddpm_simplex_noise", ptr(noise), B, C, H, W, ptr(tables_dev), int(shared_seed), ptr(t64), int(octave),
+             float(persistence), float(frequency), stream())
     return noise
 
 
@@ -281,8 +282,9 @@ class GaussianDiffusionModel:
         tab = self._tables(x_t.device)
         sample, pred = torch.empty_like(x_t), torch.empty_like(x_t)
         B = x_t.shape[0]
-        call("anoddpm_p_sample", ptr(sample), ptr(pred), ptr(x_t), ptr(eps), ptr(noise), ptr(tt), ptr(tab[4:]),
-             self.num_timesteps, B, x_t.numel() // B, stream())
+        with torch.cuda.device(x_t.device):     # launch on the tensors' device, whichever device is current
+            call("anoddpm_p_sample", ptr(sample), ptr(pred), ptr(x_t), ptr(eps), ptr(noise), ptr(tt), ptr(tab[4:]),
+                 self.num_timesteps, B, x_t.numel() // B, stream())
         return {"sample": sample, "pred_x_0": pred}
 
     def _q(self, x, t, noise, row):
@@ -294,8 +296,9 @@ class GaussianDiffusionModel:
         tab = self._tables(x.device)
         out = torch.empty_like(x)
         B = x.shape[0]
-        call("anoddpm_q_sample", ptr(out), ptr(x), ptr(noise), ptr(tt), ptr(tab[row]), ptr(tab[row + 1]), B,
-             x.numel() // B, stream())
+        with torch.cuda.device(x.device):
+            call("anoddpm_q_sample", ptr(out), ptr(x), ptr(noise), ptr(tt), ptr(tab[row]), ptr(tab[row + 1]), B,
+                 x.numel() // B, stream())
         return out
 
     def sample_q(self, x_0, t, noise):
@@ -378,6 +381,10 @@ class GaussianDiffusionModel:
         return self._graph_loop(model, x, int(t_start), int(n_steps), mode)
 
     def _graph_loop(self, model, x, t_start, n_steps, mode):
+        with torch.cuda.device(x.device):
+            return self._graph_loop_on_device(model, x, t_start, n_steps, mode)
+
+    def _graph_loop_on_device(self, model, x, t_start, n_steps, mode):
         x = self._prep(x, "x")
         B, C, H, W = x.shape
         dev = x.device
