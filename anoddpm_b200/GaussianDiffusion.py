@@ -427,16 +427,38 @@ class GaussianDiffusionModel:
               "tables": torch.zeros((self.num_timesteps, B * chans * 512), device=dev, dtype=torch.int16)}
         x_out = torch.empty(shape, device=dev)
 
+        # the step's noise field does not depend on the UNet output: it is generated on a second, LOW-priority stream forked
+        # at the top of the step and joined before the posterior kernel, so its FP64 work fills the SMs the narrow levels of
+        # the UNet (8x8 / 16x16 maps: 64 busy CTAs) leave idle instead of extending the step (ANODDPM_NOISE_OVERLAP=0: serial)
+        # everything the UNet derives from t alone (timestep MLP + per-block embedding projections), for all T timesteps, once
+        use_ttab = os.environ.get("ANODDPM_TIME_TABLE", "1") != "0"
+        if use_ttab:
+            st["time_table"] = model.engine().time_table(self.num_timesteps, dev)    # kept alive with the graph that reads it
+        overlap = mode != "gauss" and os.environ.get("ANODDPM_NOISE_OVERLAP", "1") != "0"
+        noise_stream = torch.cuda.Stream(device=dev, priority=0) if overlap else None
+
+        def make_noise():
+            noise = torch.empty((B, chans, H, W), device=dev, dtype=torch.float32)
+            call("anoddpm_simplex_noise_steps", ptr(noise), B, chans, H, W, ptr(st["tables"]), ptr(st["step"]), 0,
+                 ptr(st["t"]), 6, 0.8, 64.0, stream())
+            if chans != C:
+                noise = noise.expand(shape).contiguous()
+            return noise
+
         def step():
-            eps = model.engine().forward(st["x"], st["t"])
             if mode == "gauss":
+                eps = model.engine().forward(st["x"], st["t"], time_table=use_ttab)
                 noise = torch.randn_like(st["x"])
+            elif overlap:
+                main = torch.cuda.current_stream(dev)
+                noise_stream.wait_stream(main)
+                with torch.cuda.stream(noise_stream):
+                    noise = make_noise()
+                eps = model.engine().forward(st["x"], st["t"], time_table=use_ttab)
+                main.wait_stream(noise_stream)
             else:
-                noise = torch.empty((B, chans, H, W), device=dev, dtype=torch.float32)
-                call("anoddpm_simplex_noise_steps", ptr(noise), B, chans, H, W, ptr(st["tables"]), ptr(st["step"]), 0,
-                     ptr(st["t"]), 6, 0.8, 64.0, stream())
-                if chans != C:
-                    noise = noise.expand(shape).contiguous()
+                eps = model.engine().forward(st["x"], st["t"], time_table=use_ttab)
+                noise = make_noise()
             call("anoddpm_p_sample", ptr(x_out), None, ptr(st["x"]), ptr(eps), ptr(noise), ptr(st["t"]), ptr(tab[4:]),
                  self.num_timesteps, B, st["x"].numel() // B, stream())
             st["x"].copy_(x_out)
@@ -454,7 +476,9 @@ class GaussianDiffusionModel:
         graph = torch.cuda.CUDAGraph()
         st["t"].fill_(self.num_timesteps - 1)
         st["step"].zero_()
-        with torch.cuda.graph(graph):
+        # captured on a HIGH-priority stream: kernel nodes inherit the priority of the stream they were captured from, so the
+        # UNet's CTAs are placed ahead of the noise kernel's wherever both are pending
+        with torch.cuda.graph(graph, stream=torch.cuda.Stream(device=dev, priority=-1) if overlap else None):
             step()
         torch.cuda.synchronize(dev)
         st["graph"] = graph

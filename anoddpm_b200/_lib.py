@@ -58,6 +58,7 @@ SIGNATURES = {
     "anoddpm_adamw_ema_step": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, c_f32, c_int,
                                        c_f32, c_f32, c_vp]),
     "anoddpm_timestep_embedding": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+    "anoddpm_gather_rows": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     "anoddpm_linear": (c_int, [c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "anoddpm_gn_stats": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_vp]),
     "anoddpm_gn_apply": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32,
@@ -74,6 +75,9 @@ SIGNATURES = {
     "anoddpm_conv_head": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "anoddpm_conv_head_gn": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_f32,
                              c_vp]),
+    "anoddpm_conv_head_sep_supported": (c_int, [c_int, c_int]),
+    "anoddpm_conv_head_sep_workspace_bytes": (ctypes.c_longlong, [c_int, c_int, c_int]),
+    "anoddpm_conv_head_sep": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "anoddpm_attention": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "anoddpm_attention_tc_supported": (c_int, [c_int, c_int, c_int]),
     "anoddpm_attention_tc_workspace_bytes": (ctypes.c_longlong, [c_int, c_int, c_int]),

@@ -48,7 +48,6 @@ constexpr int kMaxStages = 4;
 constexpr int kNAMax = 3;                           // GN variant: up to three A boxes in flight (ANODDPM_TC3_NA)
 constexpr int kEpiWarps = 8;
 constexpr int kStgBuf = 32 * 64;                    // one epilogue buffer: 32 pixel rows x 16 fp32 channels, SWIZZLE_64B
-constexpr int kStgBytes = kEpiWarps * 2 * kStgBuf;  // 8 epilogue warps x 2 buffers
 constexpr int kBeBytes = kEpiWarps * 128 * 4;       // per-warp (bias + embedding) row of the current tile
 constexpr int kStg16Buf = 32 * 32;                  // fp16 copy of a step: 32 pixel rows x 16 halves, no swizzle
 constexpr int kStg16Bytes = kEpiWarps * 2 * kStg16Buf;
@@ -84,6 +83,10 @@ struct Tc3Args {
     int na;                    // A boxes in flight: 2, or 3 in the GN variant when shared memory allows
     int dbg;                   // ANODDPM_TC3_DBG (attribution runs only): 1 = transform warps only forward the barrier,
                                // 2 = read + compute but no write-back
+    int stg_nbuf;              // fp32 epilogue buffers per warp: 2, or 3 with a residual (the residual box of step s+2 is
+                               // fetched once the store of step s-1 has read its buffer: no store latency on the step chain)
+    int res_pf;                // L2 prefetch of the next tile's residual boxes
+    int a_pf;                  // GN variant: L2 prefetch distance of the raw A boxes, in chunks (0 = off)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -273,15 +276,15 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint8_t* sA = smem;
     uint8_t* sB = smem + (P.single_box ? P.na * kBoxStride : S * kABytes);
     uint8_t* stg_all = sB + S * 3 * b_bytes;       // [8 warps][2][kStgBuf], 1024-byte aligned (ring sizes are multiples)
-    uint8_t* stg16_all = stg_all + kStgBytes;      // [8 warps][2][kStg16Buf] when the fp16 copy is requested
+    uint8_t* stg16_all = stg_all + kEpiWarps * P.stg_nbuf * kStgBuf;   // [8 warps][2][kStg16Buf] when the fp16 copy is requested
     float* be_all = reinterpret_cast<float*>(stg16_all + (P.has_out16 ? kStg16Bytes : 0));   // [8 warps][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(be_all) + kBeBytes);
     uint64_t* full = bars;                         // [S]   leader only
     uint64_t* empty = bars + kMaxStages;           // [S]   both CTAs (multicast commit)
     uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]   both CTAs (multicast commit)
     uint64_t* tmem_empty = tmem_full + kAccStages; // [2]   leader only, 2 x 256 arrivals
-    uint64_t* res_bar = tmem_empty + kAccStages;   // [8 warps][2] residual box landed
-    uint64_t* a_full = res_bar + 2 * kEpiWarps;    // [2]   single-box main loop: A box landed (leader only)
+    uint64_t* res_bar = tmem_empty + kAccStages;   // [8 warps][3] residual box landed
+    uint64_t* a_full = res_bar + 3 * kEpiWarps;    // [2]   single-box main loop: A box landed (leader only)
     uint64_t* a_empty = a_full + kNAMax;           // [3]   both CTAs (multicast commit)
     uint64_t* a_land = a_empty + kNAMax;           // [3]   GN: this CTA's raw A box landed (per CTA)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_land + kNAMax);
@@ -314,7 +317,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < S; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
         for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * 32 * kEpiWarps); }
-        for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
+        for (int i = 0; i < 3 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
         // GN: a_full collects one arrival per transform warp of both CTAs (4 + 4) instead of the two producers
         for (int i = 0; i < kNAMax; ++i) { mbar_init(&a_full[i], GN ? 2 * kTransformWarps : 2); mbar_init(&a_empty[i], 1); mbar_init(&a_land[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -339,9 +342,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (elected) {
                 int bc = 0, ac = 0;
                 const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
-                // L2 prefetch cursor: the raw box of the chunk `kPF` positions ahead of the one being loaded (the load of a box
-                // straight from HBM takes longer than one chunk of MMAs; from L2 it does not)
-                constexpr int kPF = 3;
+                // optional L2 prefetch cursor (ANODDPM_TC3_APF=n): the raw box of the chunk n positions ahead of the one being
+                // loaded.  Off by default: neutral for conv1 forms, and in the conv2 forms (residual / two-store epilogue
+                // competing for L2) the prefetched lines were re-fetched -- DRAM reads 2.15 GB instead of 1.68 GB, 2.5 % slower
+                const int kPF = P.a_pf;
                 const int n_my_tiles = tile_end > tile_first ? (tile_end - tile_first + tile_step - 1) / tile_step : 0;
                 const long long q_end = (long long)n_my_tiles * nchunks;
                 auto prefetch_chunk = [&](long long q) {
@@ -366,7 +370,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     for (int c = 0; c < nchunks; ++c, ++ac) {
                         const int ab = ac % P.na;
                         uint8_t* a_dst = sA + ab * kBoxStride;
-                        prefetch_chunk((long long)ac + kPF);
+                        if (kPF) prefetch_chunk((long long)ac + kPF);
                         mbar_wait(&a_empty[ab], ((ac / P.na) & 1) ^ 1);
                         if (c < P.chunks_a) {
                             const bool first = c < P.chunks_a1;
@@ -657,7 +661,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int ew = warp - 4;            // 0..7
         const int quarter = warp & 3;       // TMEM lanes 32*quarter.. : image rows 4*quarter..+3 of the subtile
         const int sub = ew >> 2;            // subtile (left / right 8 pixel columns of the 16x16 region)
-        uint8_t* stg = stg_all + ew * (2 * kStgBuf);
+        const int NB = P.stg_nbuf;
+        uint8_t* stg = stg_all + ew * (NB * kStgBuf);
         float* be = be_all + ew * 128;
         const bool has_res = P.res != nullptr;
         auto tile_region = [&](int tile, int& b, int& ybase, int& xbase, int& n0) -> bool {
@@ -804,7 +809,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // TMA, not register loads: measured, global loads issued by the epilogue warps (pixel-per-lane or coalesced, one
         // or two steps ahead) are 15-25% slower -- they queue behind the operand bursts of the main loop
         uint8_t* stg16 = stg16_all + ew * (2 * kStg16Buf);
-        uint64_t* rbar = res_bar + ew * 2;
+        uint64_t* rbar = res_bar + ew * 3;
         const uint32_t res_bytes = P.res_mode == 3 ? 8u * 64u : (uint32_t)kStgBuf;
         auto issue_res = [&](int tile, int cb, int buf) {
             int b, ybase, xbase, n0;
@@ -814,10 +819,21 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (P.res_mode == 3) tma_load_4d(stg + buf * kStgBuf, &map_res, &rbar[buf], n0 + cb, x >> 1, y >> 1, b);
             else tma_load_4d(stg + buf * kStgBuf, &map_res, &rbar[buf], n0 + cb, x, y, b);
         };
+        // L2 prefetch of a tile's residual boxes (lane = channel step): the TMA load of a step then pays L2, not HBM, latency
+        auto prefetch_res = [&](int tile, int first_step) {
+            int b, ybase, xbase, n0;
+            if (lane < first_step || lane * 16 >= P.BN || !tile_region(tile, b, ybase, xbase, n0)) return;
+            const int y = ybase + 4 * quarter, x = xbase + 8 * sub;
+            if (P.res_mode == 3) tma_prefetch_4d(&map_res, n0 + lane * 16, x >> 1, y >> 1, b);
+            else tma_prefetch_4d(&map_res, n0 + lane * 16, x, y, b);
+        };
         if (has_res && lane == 0) {
             issue_res(tile_first, 0, 0);
             issue_res(tile_first, 16, 1);
         }
+        if (has_res && P.res_pf) prefetch_res(tile_first, 2);
+        int buf = 0;
+        uint32_t phases = 0;
         // per-channel statistics: lane (g = lane >> 2, q = lane & 3) keeps the running sums of channels 16 g + 4 q .. + 3
         // of the current (sample, channel tile) in registers and flushes them with fp64 atomics when either changes
         float keep1[4] = {0.f, 0.f, 0.f, 0.f}, keep2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -841,6 +857,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int acc = it & 1;
             int b, ybase, xbase, n0;
             const bool valid = tile_region(tile, b, ybase, xbase, n0);
+            if (has_res && P.res_pf) prefetch_res(tile + tile_step, 0);
             if (P.gn_stats && valid) {
                 if (b != cur_b || n0 != cur_n0 || kept == 8) {   // bounded fp32 chains: at most 8 tiles per flush
                     flush_stats();
@@ -883,12 +900,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     mbar_arrive_remote(&tmem_empty[acc], 0);   // this warp's part of the accumulators is read
                 }
                 if (!valid) continue;
-                const int buf = step & 1;
                 const uint32_t sba = smem_u32(stg + buf * kStgBuf), bea = smem_u32(be + cb);
                 // 1. pixel pass: thread = pixel row `lane` of the buffer (64 B); 16-byte chunk j sits at j ^ ((row >> 1) & 3)
                 float4 rs[4];
                 if (has_res) {
-                    mbar_wait(&rbar[buf], (step >> 1) & 1);
+                    mbar_wait(&rbar[buf], (phases >> buf) & 1);
+                    phases ^= 1u << buf;
                     const int srow = P.res_mode == 3 ? ((lane >> 4) * 4 + ((lane & 7) >> 1)) : lane;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) rs[j] = lds128(sba + srow * 64 + ((j ^ ((srow >> 1) & 3)) << 4));
@@ -910,7 +927,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     h16[2 * j + 1] = pack_half2_sat(v4.z, v4.w);
                 }
                 if (P.has_out16) {   // fp16 copy of the same 32 px x 16 ch step: dense 32-byte rows (same group as the fp32 store)
-                    const uint32_t s16 = smem_u32(stg16 + buf * kStg16Buf) + lane * 32;
+                    const uint32_t s16 = smem_u32(stg16 + (step & 1) * kStg16Buf) + lane * 32;
                     sts128u(s16, make_uint4(h16[0], h16[1], h16[2], h16[3]));
                     sts128u(s16 + 16, make_uint4(h16[4], h16[5], h16[6], h16[7]));
                 }
@@ -920,7 +937,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 if (lane == 0) {
                     tma_store_4d(&map_out, stg + buf * kStgBuf, n0 + cb, xbase + 8 * sub, ybase + 4 * quarter, b);
                     if (P.has_out16)
-                        tma_store_4d(&map_out16, stg16 + buf * kStg16Buf, n0 + cb, xbase + 8 * sub, ybase + 4 * quarter, b);
+                        tma_store_4d(&map_out16, stg16 + (step & 1) * kStg16Buf, n0 + cb, xbase + 8 * sub, ybase + 4 * quarter, b);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 // 3. column pass: lane owns channels cc..cc+3 of rows (lane >> 2) + 8k -> per-channel statistics
@@ -948,13 +965,19 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     }
                 }
                 if (has_res) {
-                    // buffer free once the store has read it: fetch the residual of step + 2
+                    // fetch the residual of step + 2 into the buffer that will hold it: two buffers -> this step's own buffer,
+                    // once its store has read it; three -> the buffer of step - 1, whose store had a whole step to finish
                     __syncwarp();
                     if (lane == 0) {
-                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        if (cb + 32 < P.BN) issue_res(tile, cb + 32, buf);
-                        else issue_res(tile + tile_step, cb + 32 - P.BN, buf);
+                        const int nb = NB == 3 ? (buf == 0 ? 2 : buf - 1) : buf;
+                        if (NB == 3) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        if (cb + 32 < P.BN) issue_res(tile, cb + 32, nb);
+                        else issue_res(tile + tile_step, cb + 32 - P.BN, nb);
                     }
+                    buf = buf + 1 == NB ? 0 : buf + 1;
+                } else {
+                    buf ^= 1;
                 }
                 ++step;
             }
@@ -1112,7 +1135,12 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     // The operand-transform variant always runs the single-box loop.
     { const char* e = getenv("ANODDPM_TC3_SINGLEBOX"); P.single_box = e ? atoi(e) : ((d->Cr1 + d->Cr2) == 0 ? 1 : 0); }
     if (gn) P.single_box = 1;
-    const size_t fixed = (size_t)kStgBytes + (P.has_out16 ? kStg16Bytes : 0) + kBeBytes + 512 + 1024;
+    // three fp32 epilogue buffers per warp when a residual is fetched (ANODDPM_TC3_RBUF=2 restores two; measured neutral),
+    // optional L2 prefetch of the next tile's residual boxes (ANODDPM_TC3_RESPF=1; measured 4-6 % SLOWER: off)
+    { const char* e = getenv("ANODDPM_TC3_RBUF"); P.stg_nbuf = (d->res && !d->out_f16 && (!e || atoi(e) == 3)) ? 3 : 2; }
+    { const char* e = getenv("ANODDPM_TC3_RESPF"); P.res_pf = e ? atoi(e) : 0; }
+    { const char* e = getenv("ANODDPM_TC3_APF"); P.a_pf = e ? atoi(e) : 0; if (P.a_pf < 0 || P.a_pf > 8) P.a_pf = 0; }
+    const size_t fixed = (size_t)kEpiWarps * P.stg_nbuf * kStgBuf + (P.has_out16 ? kStg16Bytes : 0) + kBeBytes + 512 + 1024;
     const size_t budget = 227 * 1024 - fixed;
     P.na = 2;
     if (gn) { const char* e = getenv("ANODDPM_TC3_NA"); P.na = e ? atoi(e) : 2; if (P.na < 2 || P.na > kNAMax) P.na = 2; }

@@ -3,8 +3,13 @@
 //         ALSO emits what the first ResBlock needs: the per-channel GroupNorm statistics of the output (fp64 atomics into the
 //         replica layout) and an fp16 copy (the raw operand of the first conv with operand-side GroupNorm) -- so the stem
 //         output is never re-read by a statistics or normalisation pass.
-//   (A tap-separable rewrite of the single-output head was measured 0.35 ms per step SLOWER than unet_ops.cu's
-//   conv_head_kernel on one box, 26.49 vs 26.14 ms, and was dropped.)
+//   head (reference UNet.py:384-388, GroupNorm -> SiLU -> Conv2d(C -> 1, 3x3)): Cout = 1 makes the convolution separable by
+//         tap.  Pass 1 (head_proj_kernel) streams the last feature map ONCE, with no halo: per pixel it normalises + activates
+//         the C channels and reduces them against the nine tap weight vectors (lane = 4 channels, weights in registers, eight
+//         pixels per warp iteration, reduce-scatter butterfly over the lanes) -> nine fp32 maps t[k][b][y][x] (L2-resident,
+//         9 x 4 B per pixel against 4 C B read).  Pass 2 (head_gather_kernel) adds the nine shifted maps.  (A first
+//         tap-separable attempt with 18x18 halo tiles and a 32-channel slice per thread was measured slower than unet_ops.cu's
+//         conv_head_kernel -- 63 % lane utilisation, 27 % halo re-reads -- and dropped; this one has neither.)
 #include "common.cuh"
 #include "anoddpm_b200.h"
 #include <cuda_fp16.h>
@@ -14,6 +19,107 @@ namespace {
 struct alignas(16) F4e { float x, y, z, w; };
 __device__ __forceinline__ F4e ld4e(const float* p) { return *reinterpret_cast<const F4e*>(p); }
 __device__ __forceinline__ float silu_e(float y) { return __fdividef(y, 1.0f + __expf(-y)); }
+
+
+// ------------------------------------------------------------------------------------------------ head (Cout = 1), two passes
+// pass 1: t[k][pix] = sum_c SiLU(x[pix][c] * scale[b][c] + shift[b][c]) * w[k][c];  pix = linear (b, y, x) index.
+// CPL = float4 slices per lane (C = 128 * CPL); PB = pixels per warp iteration (8 for CPL 1, 4 for CPL 2).
+template <int CPL, int PB>
+__global__ void __launch_bounds__(256) head_proj_kernel(float* __restrict__ t, const float* __restrict__ x,
+                                                        const float2* __restrict__ tab, const float* __restrict__ w,
+                                                        long long HW, long long npix, int pix_per_cta) {
+    constexpr int C = 128 * CPL;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long cta0 = (long long)blockIdx.x * pix_per_cta;      // HW % pix_per_cta == 0: one sample per CTA
+    const int b = (int)(cta0 / HW);
+    float wk[CPL][9][4], sc[CPL][4], sh[CPL][4];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        const int c = 128 * j + 4 * lane;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const F4e v = ld4e(w + k * C + c);
+            wk[j][k][0] = v.x; wk[j][k][1] = v.y; wk[j][k][2] = v.z; wk[j][k][3] = v.w;
+        }
+        const F4e t0 = ld4e(reinterpret_cast<const float*>(tab + (size_t)b * C + c));
+        const F4e t1 = ld4e(reinterpret_cast<const float*>(tab + (size_t)b * C + c + 2));
+        sc[j][0] = t0.x; sh[j][0] = t0.y; sc[j][1] = t0.z; sh[j][1] = t0.w;
+        sc[j][2] = t1.x; sh[j][2] = t1.y; sc[j][3] = t1.z; sh[j][3] = t1.w;
+    }
+    const int per_warp = pix_per_cta / 8;
+    const long long p_begin = cta0 + (long long)warp * per_warp;
+    for (int i0 = 0; i0 < per_warp; i0 += PB) {
+        const long long p0 = p_begin + i0;
+        F4e v[PB][CPL];
+#pragma unroll
+        for (int u = 0; u < PB; ++u)
+#pragma unroll
+            for (int j = 0; j < CPL; ++j)
+                v[u][j] = (p0 + u < npix) ? ld4e(x + (size_t)(p0 + u) * C + 128 * j + 4 * lane) : F4e{0.f, 0.f, 0.f, 0.f};
+        float acc[PB][9];
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[u][k] = 0.f;
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                const float a0 = silu_e(fmaf(v[u][j].x, sc[j][0], sh[j][0])), a1 = silu_e(fmaf(v[u][j].y, sc[j][1], sh[j][1]));
+                const float a2 = silu_e(fmaf(v[u][j].z, sc[j][2], sh[j][2])), a3 = silu_e(fmaf(v[u][j].w, sc[j][3], sh[j][3]));
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    acc[u][k] = fmaf(a0, wk[j][k][0], acc[u][k]);
+                    acc[u][k] = fmaf(a1, wk[j][k][1], acc[u][k]);
+                    acc[u][k] = fmaf(a2, wk[j][k][2], acc[u][k]);
+                    acc[u][k] = fmaf(a3, wk[j][k][3], acc[u][k]);
+                }
+            }
+        }
+        // reduce-scatter over the lanes: each halving level keeps one half of the pixels and adds the partner's other half
+        // (lane bit 4 <-> pixel bit log2(PB)-1, ...), then the remaining levels all-reduce the nine sums of the lane's pixel
+        int mask = 16;
+#pragma unroll
+        for (int half = PB / 2; half >= 1; half >>= 1, mask >>= 1) {
+            const bool up = (lane & mask) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i)
+#pragma unroll
+                for (int k = 0; k < 9; ++k) {
+                    const float send = up ? acc[i][k] : acc[i + half][k];
+                    const float keep = up ? acc[i + half][k] : acc[i][k];
+                    acc[i][k] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+                }
+        }
+#pragma unroll
+        for (; mask >= 1; mask >>= 1)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) acc[0][k] += __shfl_xor_sync(0xffffffffu, acc[0][k], mask);
+        // the 32 / PB lanes of a pixel hold the same nine sums: they share the nine stores
+        constexpr int LPP = 32 / PB;                        // lanes per pixel
+        const int u = lane / LPP, jl = lane % LPP;
+        const long long p = p0 + u;
+        if (p < npix) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                if (k % LPP == jl) t[(size_t)k * npix + p] = acc[0][k];
+        }
+    }
+}
+
+// pass 2: out[b][y][x] = bias + sum over the nine taps of t[tap][b][y + dy][x + dx] (taps outside the image contribute zero:
+// the convolution pads the ACTIVATED tensor)
+__global__ void __launch_bounds__(256) head_gather_kernel(float* __restrict__ out, const float* __restrict__ t,
+                                                          const float* __restrict__ bias, int H, int W, long long npix) {
+    const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (p >= npix) return;
+    const int xq = (int)(p % W), yq = (int)((p / W) % H);
+    float o = bias ? bias[0] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const int dy = k / 3 - 1, dx = k % 3 - 1;
+        if ((unsigned)(yq + dy) < (unsigned)H && (unsigned)(xq + dx) < (unsigned)W) o += t[(size_t)k * npix + p + (long long)dy * W + dx];
+    }
+    out[p] = o;
+}
 
 // ------------------------------------------------------------------------------------------------ stem (Cin = 1)
 // thread = (4 output channels, pixel lane); a CTA walks 8-pixel row segments; per-channel statistics are kept per thread and
@@ -166,6 +272,32 @@ __global__ void __launch_bounds__(128) slice_resize_kernel(float* __restrict__ o
 }
 
 }  // namespace
+
+
+extern "C" int anoddpm_conv_head_sep_supported(int C, int Cout) { return Cout == 1 && (C == 128 || C == 256); }
+
+extern "C" long long anoddpm_conv_head_sep_workspace_bytes(int B, int H, int W) { return 9LL * B * H * W * (long long)sizeof(float); }
+
+extern "C" int anoddpm_conv_head_sep(float* out_nchw, const float* x_nhwc, const float* gn_table, const float* w_packed,
+                                     const float* bias, float* workspace, int B, int C, int H, int W, void* stream) {
+    ADP_REQUIRE(out_nchw && x_nhwc && gn_table && w_packed && workspace && B > 0 && H > 0 && W > 0,
+                "anoddpm_conv_head_sep: bad arguments");
+    ADP_REQUIRE(anoddpm_conv_head_sep_supported(C, 1), "anoddpm_conv_head_sep: C must be 128 or 256 (got %d)", C);
+    const long long HW = (long long)H * W, npix = (long long)B * HW;
+    int ppc = 512;                                  // pixels per CTA (64 per warp); must divide the pixels of one image
+    while (ppc > 64 && HW % ppc) ppc >>= 1;
+    ADP_REQUIRE(HW % ppc == 0, "anoddpm_conv_head_sep: H*W must be a multiple of 64 (got %lld)", HW);
+    const long long ctas = npix / ppc;
+    ADP_REQUIRE(ctas < (1LL << 31), "anoddpm_conv_head_sep: too many tiles");
+    cudaStream_t st = (cudaStream_t)stream;
+    const float2* tab = reinterpret_cast<const float2*>(gn_table);
+    if (C == 128) head_proj_kernel<1, 8><<<(unsigned)ctas, 256, 0, st>>>(workspace, x_nhwc, tab, w_packed, HW, npix, ppc);
+    else head_proj_kernel<2, 4><<<(unsigned)ctas, 256, 0, st>>>(workspace, x_nhwc, tab, w_packed, HW, npix, ppc);
+    ADP_LAUNCH_CHECK();
+    head_gather_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(out_nchw, workspace, bias, H, W, npix);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}
 
 extern "C" int anoddpm_conv_stem_fused(float* out_nhwc, void* out16_nhwc, double* stats, const float* x_nchw, const float* w_oihw,
                                        const float* bias, int B, int Cin, int H, int W, int Cout, void* stream) {

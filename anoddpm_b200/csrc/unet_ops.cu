@@ -37,6 +37,20 @@ __global__ void tembed_kernel(float* __restrict__ emb, const long long* __restri
     emb[(size_t)b * dim + half + j] = cosf(a);
 }
 
+// out[b][:] = table[idx[b]][:] (rows of S floats, S % 4 == 0); an index outside [0, T) poisons the row with NaN
+__global__ void __launch_bounds__(256) gather_rows_kernel(float* __restrict__ out, const float* __restrict__ table,
+                                                          const long long* __restrict__ idx, int B, int S4, int T) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= B * S4) return;
+    const int b = i / S4, c = i - b * S4;
+    const long long r = idx[b];
+    F4 v;
+    if (r >= 0 && r < T) v = ld4(table + ((size_t)r * S4 + c) * 4);
+    else v.x = v.y = v.z = v.w = __int_as_float(0x7fc00000);
+    st4(out + ((size_t)b * S4 + c) * 4, v);
+}
+
+
 // ---------------------------------------------------------------- linear: one warp per (b, n)
 // warp = (output feature n, group of LB samples): the weight row is read once per group instead of once per sample; per
 // (b, n) the summation order is unchanged (lane-strided partial sums, then a butterfly).  act: bit 0 = SiLU on the
@@ -867,6 +881,15 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 int anoddpm_conv_tc(const anoddpm_conv_desc* d, void* stream);   // conv_tc.cu  (impl 1)
 int anoddpm_conv_tc2(const anoddpm_conv_desc* d, void* stream);  // conv_tc2.cu (impl 2)
 int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream);  // conv_tc3.cu (impl 3)
+
+extern "C" int anoddpm_gather_rows(float* out, const float* table, const int64_t* idx, int B, int S, int T, void* stream) {
+    ADP_REQUIRE(out && table && idx && B > 0 && S > 0 && S % 4 == 0 && T > 0 && al16(out) && al16(table),
+                "anoddpm_gather_rows: bad arguments (S must be a multiple of 4)");
+    gather_rows_kernel<<<adp_ceil_div((long long)B * (S / 4), 256), 256, 0, (cudaStream_t)stream>>>(out, table, (const long long*)idx,
+                                                                                                  B, S / 4, T);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
+}
 
 extern "C" int anoddpm_timestep_embedding(float* emb, const int64_t* t, const float* freq, int B, int dim,
                                           void* stream) {

@@ -16,6 +16,7 @@ Resampling blocks, attention inputs and tensors without an fp16 copy still take 
 (gn_apply: +SiLU, +avg-pool / nearest-upsample, +fp16 rounding, +raw copy / pooled residual).
 """
 import ctypes
+import os
 
 import torch
 
@@ -84,6 +85,7 @@ class UNetEngine:
     def __init__(self, model):
         self.model = model
         self._sig = None
+        self._time_table = None
         self._gen = 0               # bumped by invalidate(): raw-pointer / .data writes do not bump p._version
         self.launches = 0           # native kernel launches issued (for bench.py's gpu_launches)
 
@@ -122,6 +124,7 @@ class UNetEngine:
         from .UNet import AttentionBlock, ResBlock
         m = self.model
         self.emb_w, self.emb_b, self.emb_off = [], [], 0
+        self._time_table = None     # per-timestep embedding rows of the previous weight version
 
         build_res = self._build_res
 
@@ -443,14 +446,48 @@ class UNetEngine:
                 h, H, W = self._res(e, [h], B, H, W, need16=i + 1 < len(entries))
         return h.t.permute(0, 3, 1, 2).contiguous()
 
+    # ------------------------------------------------------------------ timestep embedding
+    def _embedding_rows(self, t, dev):
+        """(len(t), S) rows: timestep embedding MLP (UNet.py:396-397) + every ResBlock's SiLU -> Linear projection
+        (UNet.py:206-207), four small launches."""
+        m = self.model
+        n = t.numel()
+        base, E = m.model_channels, m.model_channels * 4
+        temb = torch.empty((n, base), device=dev, dtype=torch.float32)
+        call("anoddpm_timestep_embedding", ptr(temb), ptr(t), ptr(self._freq(base, dev)), n, base, stream())
+        l1, l2 = m.time_embedding[1], m.time_embedding[3]
+        e1 = torch.empty((n, E), device=dev, dtype=torch.float32)
+        call("anoddpm_linear", ptr(e1), E, ptr(temb), base, ptr(l1.weight), ptr(l1.bias), n, E, base, 0, stream())
+        emb = torch.empty((n, E), device=dev, dtype=torch.float32)      # SiLU(time embedding): every ResBlock applies it
+        call("anoddpm_linear", ptr(emb), E, ptr(e1), E, ptr(l2.weight), ptr(l2.bias), n, E, E, 3, stream())
+        S = self.emb_cat_w.shape[0]
+        rows = torch.empty((n, S), device=dev, dtype=torch.float32)
+        call("anoddpm_linear", ptr(rows), S, ptr(emb), E, ptr(self.emb_cat_w), ptr(self.emb_cat_b), n, S, E, 0, stream())
+        return rows
+
+    @torch.no_grad()
+    def time_table(self, T, dev):
+        """Build (once per weight version) the [T][S] table of embedding rows for timesteps 0..T-1: everything the UNet
+        computes from t alone.  The sampling loop calls this before it captures its step; forward() then gathers one row per
+        sample (bit-identical: each row's summation order does not depend on the batch it is computed in).  Dropped whenever
+        the weights change (_build)."""
+        self._refresh()
+        if self._time_table is None or self._time_table.shape[0] != T or self._time_table.device != dev:
+            with torch.cuda.device(dev):
+                t = torch.arange(T, device=dev, dtype=torch.int64)
+                self._time_table = self._embedding_rows(t, dev)
+        return self._time_table
+
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, x, t):
+    def forward(self, x, t, time_table=False):
+        """time_table: take the timestep-embedding rows from the table built by time_table() (the sampling loop, whose t is
+        always inside [0, T)) instead of computing them for this batch."""
         _lib.require_cuda(x, "UNetModel input")
         with torch.cuda.device(x.device):       # kernels launch on the tensors' device, whichever device is current
-            return self._forward(x, t)
+            return self._forward(x, t, time_table)
 
-    def _forward(self, x, t):
+    def _forward(self, x, t, time_table=False):
         m = self.model
         p0 = next(m.parameters())
         if p0.device != x.device:
@@ -470,6 +507,7 @@ class UNetEngine:
         # GroupNorm + SiLU applied to the operand boxes inside the 3x3 convs (no normalised copies in HBM)
         self.fuse_gn = self.h1_f16 and getattr(m, "fuse_gn", True)
         self.fuse_gn2 = getattr(m, "fuse_gn2", True)
+        self.sep_head = getattr(m, "sep_head", True) and os.environ.get("ANODDPM_SEP_HEAD", "1") != "0"
         self.gn_tables = 0
         self.f16_outputs = 0
         self.f16_convs = 0
@@ -486,21 +524,16 @@ class UNetEngine:
         if t.numel() != B:
             raise RuntimeError("time must have one entry per sample")
         dev = x.device
-        base, E = m.model_channels, m.model_channels * 4
-
-        # timestep embedding MLP + all per-ResBlock projections in three small launches
-        temb = torch.empty((B, base), device=dev, dtype=torch.float32)
-        call("anoddpm_timestep_embedding", ptr(temb), ptr(t), ptr(self._freq(base, dev)), B, base, stream())
-        l1, l2 = m.time_embedding[1], m.time_embedding[3]
-        e1 = torch.empty((B, E), device=dev, dtype=torch.float32)
-        call("anoddpm_linear", ptr(e1), E, ptr(temb), base, ptr(l1.weight), ptr(l1.bias), B, E, base, 0, stream())
-        emb = torch.empty((B, E), device=dev, dtype=torch.float32)      # SiLU(time embedding): every ResBlock applies it
-        call("anoddpm_linear", ptr(emb), E, ptr(e1), E, ptr(l2.weight), ptr(l2.bias), B, E, E, 3, stream())
         S = self.emb_cat_w.shape[0]
-        self.emb_all = torch.empty((B, S), device=dev, dtype=torch.float32)
-        call("anoddpm_linear", ptr(self.emb_all), S, ptr(emb), E, ptr(self.emb_cat_w), ptr(self.emb_cat_b), B, S, E, 0,
-             stream())
-        self.launches += 4
+        ttab = self._time_table if time_table else None
+        if ttab is not None and ttab.device == dev and S % 4 == 0:
+            # sampling loop: the rows were computed once for every timestep (time_table()); one gather per step
+            self.emb_all = torch.empty((B, S), device=dev, dtype=torch.float32)
+            call("anoddpm_gather_rows", ptr(self.emb_all), ptr(ttab), ptr(t), B, S, ttab.shape[0], stream())
+            self.launches += 1
+        else:
+            self.emb_all = self._embedding_rows(t, dev)
+            self.launches += 4
         # per-channel statistics of every activation that feeds a GroupNorm, bump-allocated, one memset per forward
         self.stats_pool = torch.zeros(self._stats_pool_size(B), device=dev, dtype=torch.float64)
         self.stats_used = 0
@@ -532,7 +565,16 @@ class UNetEngine:
         hd = self.head
         out = torch.empty((B, m.out_channels, H, W), device=dev, dtype=torch.float32)
         C = h.t.shape[-1]
-        if C <= 512 and m.out_channels <= 4:
+        if (self.sep_head and _lib.lib().anoddpm_conv_head_sep_supported(C, m.out_channels) and (H * W) % 64 == 0
+                and hd["gn"].num_groups == 32):
+            # single-output head, separable by tap: one halo-free streaming pass (GroupNorm + SiLU + nine channel reductions per
+            # pixel) into nine L2-resident maps, then the nine shifted adds
+            tab = self._gn_table([h], hd["gn"], B, H * W)
+            ws = torch.empty(9 * B * H * W, device=dev, dtype=torch.float32)
+            call("anoddpm_conv_head_sep", ptr(out), ptr(h.t), ptr(tab), ptr(self.head_w), ptr(hd["conv"].bias), ptr(ws), B, C, H, W,
+                 stream())
+            self.launches += 1
+        elif C <= 512 and m.out_channels <= 4:
             # GroupNorm + SiLU applied while the head conv stages its tiles: the last feature map is read once
             gn = hd["gn"]
             call("anoddpm_conv_head_gn", ptr(out), ptr(h.t), ptr(self._stats_of(h, B, H * W)), ptr(gn.weight), ptr(gn.bias),

@@ -107,6 +107,11 @@ int anoddpm_vlb_terms(double* acc /* B x 2 */, float* pred_x0, const float* x_0,
 int anoddpm_timestep_embedding(float* emb /* B x dim */, const int64_t* t, const float* freq /* dim/2 */, int B,
                                int dim, void* stream);
 
+/* out[b][:] = table[idx[b]][:] for rows of S floats (S % 4 == 0): the per-timestep embedding table of the sampling loop --
+ * the timestep MLP and every ResBlock's embedding projection (UNet.py:206-207, 396-397) depend on t only, so the loop computes
+ * them once for all T timesteps and gathers a row per sample per step.  An index outside [0, T) fills the row with NaN. */
+int anoddpm_gather_rows(float* out, const float* table, const int64_t* idx, int B, int S, int T, void* stream);
+
 /* y[b, n] = g(sum_k f(x[b,k]) * w[n,k] + bias[n]); act bit 0: f = SiLU (else identity), bit 1: g = SiLU.
  * UNet.py:271-276, :185-188 (nn.Linear between nn.SiLU).  ldx / ldy: row strides of x / y (elements). */
 int anoddpm_linear(float* y, int ldy, const float* x, int ldx, const float* w, const float* bias, int B, int N, int K,
@@ -210,6 +215,16 @@ int anoddpm_conv_head(float* out_nchw, const float* a_nhwc, const float* w_packe
 int anoddpm_conv_head_gn(float* out_nchw, const float* x_nhwc, const double* stats, const float* gamma, const float* beta,
                          const float* w_packed, const float* bias, int B, int Cin, int H, int W, int Cout, int groups,
                          float eps, void* stream);
+
+/* The single-output head in two streaming passes (Cout == 1 makes the 3x3 convolution separable by tap): pass 1 reads the raw
+ * last feature map once, without halo, applies GroupNorm + SiLU from gn_table ([B][C] (scale, shift), anoddpm_gn_table) and
+ * reduces the C channels of every pixel against the nine tap weight vectors into nine fp32 maps in `workspace`
+ * (anoddpm_conv_head_sep_workspace_bytes, L2-sized); pass 2 adds the nine shifted maps + bias into out_nchw.  C == 128 or 256,
+ * H*W % 64 == 0.  UNet.py:384-388. */
+int anoddpm_conv_head_sep_supported(int C, int Cout /* [host] */);
+long long anoddpm_conv_head_sep_workspace_bytes(int B, int H, int W /* [host] */);
+int anoddpm_conv_head_sep(float* out_nchw, const float* x_nhwc, const float* gn_table, const float* w_packed,
+                          const float* bias, float* workspace, int B, int C, int H, int W, void* stream);
 
 /* Stem for single-channel images in one pass that also emits what the first ResBlock needs: the per-channel GroupNorm
  * statistics of the output (stats, [REPLICAS][B][Cout][2] fp64, accumulated; may be NULL) and an fp16 copy of the output

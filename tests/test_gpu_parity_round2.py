@@ -17,6 +17,7 @@ import random
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -322,7 +323,7 @@ def test_base256_fused_groupnorm_path_matches_unfused_and_golden(golden):
             assert eng.gn_tables >= 50, eng.gn_tables
             launches_fused = eng.launches_per_forward
         else:
-            assert eng.gn_tables == 0
+            assert eng.gn_tables <= 1       # only the separable head's table
     print(f"[parity] base256 tc: fused-GN rel={errs[True]:.3e}  separate-pass rel={errs[False]:.3e}  "
           f"launches {launches_fused} vs {eng.launches_per_forward}")
     assert errs[True] < 1e-3 and errs[False] < 1e-3
@@ -444,3 +445,40 @@ def test_fused_stem_features_statistics_and_fp16_copy():
         s = st.sum(0)
         assert torch.allclose(s[..., 0], ref.sum(dim=(1, 2)), rtol=1e-6, atol=1e-4)
         assert torch.allclose(s[..., 1], (ref ** 2).sum(dim=(1, 2)), rtol=1e-6, atol=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(2, 128, 32, 32), (3, 256, 24, 40), (1, 128, 256, 256)])
+def test_separable_head_vs_torch(shape):
+    """anoddpm_conv_head_sep (GroupNorm + SiLU + nine per-pixel channel reductions, then nine shifted adds) against the
+    plain torch fp32 GroupNorm -> SiLU -> Conv2d(C -> 1) of reference UNet.py:384-388 and against anoddpm_conv_head_gn."""
+    from anoddpm_b200 import _lib
+    from anoddpm_b200._lib import call, ptr, stream
+    from anoddpm_b200.engine import pack_conv_weight
+    B, C, H, W = shape
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = (torch.randn(B, C, H, W, generator=g) * 1.7 + 0.3).cuda()
+    gamma = (torch.rand(C, generator=g) + 0.5).cuda()
+    beta = (torch.randn(C, generator=g) * 0.2).cuda()
+    w = (torch.randn(1, C, 3, 3, generator=g) * 0.05).cuda()
+    bias = torch.randn(1, generator=g).cuda()
+    ref = F.conv2d(F.silu(F.group_norm(x.double(), 32, gamma.double(), beta.double(), 1e-5)), w.double(), bias.double(),
+                   padding=1).float()       # fp64: torch's fp32 GPU convolution runs on TF32 by default
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    st = torch.zeros(8 * B * C * 2, device="cuda", dtype=torch.float64)
+    call("anoddpm_gn_stats", ptr(st), ptr(xn), C, B, H * W, stream())
+    tab = torch.empty(B, C, 2, device="cuda")
+    call("anoddpm_gn_table", ptr(tab), ptr(st), C, None, 0, ptr(gamma), ptr(beta), None, None, 0, B, H * W, 32, 1e-5, stream())
+    wp = pack_conv_weight(w).contiguous().float()
+    L = _lib.lib()
+    assert L.anoddpm_conv_head_sep_supported(C, 1) == 1 and L.anoddpm_conv_head_sep_supported(192, 1) == 0
+    ws = torch.empty(L.anoddpm_conv_head_sep_workspace_bytes(B, H, W) // 4, device="cuda")
+    out = torch.empty(B, 1, H, W, device="cuda")
+    call("anoddpm_conv_head_sep", ptr(out), ptr(xn), ptr(tab), ptr(wp), ptr(bias), ptr(ws), B, C, H, W, stream())
+    old = torch.empty(B, 1, H, W, device="cuda")
+    call("anoddpm_conv_head_gn", ptr(old), ptr(xn), ptr(st), ptr(gamma), ptr(beta), ptr(wp), ptr(bias), B, C, H, W, 1, 32, 1e-5,
+         stream())
+    torch.cuda.synchronize()
+    e_ref = float((out - ref).abs().max() / ref.abs().max())
+    e_old = float((out - old).abs().max() / ref.abs().max())
+    print(f"separable head {shape}: vs torch {e_ref:.2e}, vs conv_head_gn {e_old:.2e}")
+    assert e_ref < 5e-6 and e_old < 5e-6        # fp32 both ways: summation order + __expf only (measured ~1e-6)

@@ -89,7 +89,28 @@ def main():
     ap.add_argument("--out16", action="store_true")
     ap.add_argument("--outf16", action="store_true")
     ap.add_argument("--gn-attrib", action="store_true", help="attribute the operand-transform overhead (ANODDPM_TC3_DBG)")
+    ap.add_argument("--conv2-attrib", action="store_true", help="attribute the conv2-form epilogue (residual / statistics / fp16 copy)")
     a = ap.parse_args()
+    if a.conv2_attrib:
+        print(f"| conv2 forms {a.ci}->{a.co} @{a.hw}^2 bs{a.batch} | RBUF | RESPF | ms | TFLOP/s |\n|---|---:|---:|---:|---:|")
+        forms = (("plain", dict(res=0, stats=False, emb=False)),
+                 ("+res1", dict(res=1, stats=False, emb=False)),
+                 ("+res1+stats", dict(res=1, stats=True, emb=False)),
+                 ("+res1+stats+fp16 copy", dict(res=1, stats=True, emb=False, out16=True)),
+                 ("+stats+fp16 copy (no residual)", dict(res=0, stats=True, emb=False, out16=True)),
+                 ("GN only", dict(res=0, stats=False, emb=False, gn=True)),
+                 ("GN +res1", dict(res=1, stats=False, emb=False, gn=True)),
+                 ("GN +res1+stats", dict(res=1, stats=True, emb=False, gn=True)),
+                 ("GN +res1+stats+fp16 copy (production conv2)", dict(res=1, stats=True, emb=False, out16=True, gn=True)),
+                 ("GN +res3+stats+fp16 copy (upsampled residual)", dict(res=3, stats=True, emb=False, out16=True, gn=True)))
+        for name, kw in forms:
+            combos = ((2, 0), (2, 1), (3, 0), (3, 1)) if kw["res"] else ((2, 0),)
+            for rbuf, pf in combos:
+                os.environ["ANODDPM_TC3_RBUF"] = str(rbuf)
+                os.environ["ANODDPM_TC3_RESPF"] = str(pf)
+                ms, tf = run(a, a.batch, a.ci, a.co, a.hw, **kw)
+                print(f"| {name} | {rbuf} | {pf} | {ms:.3f} | {tf:.0f} |", flush=True)
+        return
     if a.gn_attrib:
         print(f"| conv1 GN {a.ci}->{a.co} @{a.hw}^2 bs{a.batch}: transform variant | ms | TFLOP/s |\n|---|---:|---:|")
         for name, dbg in (("full transform", "0"), ("barrier forwarding only", "1"), ("read + compute, no write-back", "2")):
