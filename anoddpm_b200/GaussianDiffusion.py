@@ -434,7 +434,7 @@ class GaussianDiffusionModel:
         use_ttab = os.environ.get("ANODDPM_TIME_TABLE", "1") != "0"
         if use_ttab:
             st["time_table"] = model.engine().time_table(self.num_timesteps, dev)    # kept alive with the graph that reads it
-        overlap = mode != "gauss" and os.environ.get("ANODDPM_NOISE_OVERLAP", "1") != "0"
+        overlap = mode != "gauss" and os.environ.get("ANODDPM_NOISE_OVERLAP", "0") == "1"
         noise_stream = torch.cuda.Stream(device=dev, priority=0) if overlap else None
 
         def make_noise():

@@ -19,7 +19,8 @@ class ConvDesc(ctypes.Structure):
     _fields_ = [("out", c_vp), ("a", c_vp), ("r1", c_vp), ("r2", c_vp), ("w", c_vp), ("bias", c_vp), ("emb", c_vp),
                 ("res", c_vp), ("B", c_int), ("H", c_int), ("W", c_int), ("Ca", c_int), ("Cr1", c_int), ("Cr2", c_int),
                 ("Cout", c_int), ("ksize", c_int), ("emb_stride", c_int), ("res_mode", c_int), ("impl", c_int), ("operand_f16", c_int), ("gn_stats", c_vp),
-                ("out_f16", c_int), ("a2", c_vp), ("Ca2", c_int), ("gn_table", c_vp), ("out16", c_vp)]
+                ("out_f16", c_int), ("a2", c_vp), ("Ca2", c_int), ("gn_table", c_vp), ("out16", c_vp), ("workspace", c_vp),
+                ("workspace_bytes", ctypes.c_longlong)]
 
 
 # name -> (restype, argtypes); every symbol of include/anoddpm_b200.h
@@ -67,6 +68,7 @@ SIGNATURES = {
                                c_int, c_int, c_vp]),
     "anoddpm_gn_table": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32, c_vp]),
     "anoddpm_conv": (c_int, [ctypes.POINTER(ConvDesc), c_vp]),
+    "anoddpm_conv_workspace_bytes": (ctypes.c_longlong, [ctypes.POINTER(ConvDesc)]),
     "anoddpm_conv_tc_supported": (c_int, [ctypes.POINTER(ConvDesc)]),
     "anoddpm_conv_tc3_supported": (c_int, [ctypes.POINTER(ConvDesc)]),
     "anoddpm_conv_stem": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),

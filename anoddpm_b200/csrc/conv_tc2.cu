@@ -45,6 +45,14 @@ struct Tc2Args {
     int n_tiles_n, n_tiles;   // tiles along N, total pair tiles
     double* gn_stats;          // optional [REPLICAS][B][Cout][2]: per-channel (sum, sum of squares) of the output
     long long stat_replica_stride;
+    // split-K (small maps: fewer tiles than CTA pairs): a work item = (tile, K range); partial accumulators go to `ws_part`
+    // ([splits][M_pad][ws_ld] fp32) and the LAST warp to finish a 32-row block (arrival counter) adds the partials in split
+    // order (deterministic) and runs the normal epilogue on the sum
+    int splits;
+    float* ws_part;
+    int* ws_cnt;               // [n_tiles][2 ranks][4 warps], zero on entry, reset by the last arriver
+    int ws_ld;                 // n_tiles_n * BN
+    long long ws_split_stride; // M_pad * ws_ld
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -172,6 +180,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     const int nkb = P.nkb_a + P.nkb_r1 + P.nkb_r2;
+    const int n_items = P.n_tiles * P.splits;
 
     cluster_sync_all();   // both CTAs resident before the pair-wide TMEM allocation
     if (warp == 0 && lane == 0) {
@@ -199,12 +208,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (elect_one()) {
             const int pad = P.ks / 2;
             int kbc = 0;
-            for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters) {
+            for (int item = cluster_id; item < n_items; item += n_clusters) {
+                const int tile = item / P.splits, sp = item - tile * P.splits;
+                const int kb0 = (int)((long long)sp * nkb / P.splits), kb1 = (int)((long long)(sp + 1) * nkb / P.splits);
                 const int mp = tile / P.n_tiles_n, nt = tile - mp * P.n_tiles_n;
                 const int m0 = (mp * 2 + (int)rank) * kBM;
                 const int n0 = nt * P.BN + (int)rank * (P.BN / 2);
                 const int w0 = m0 % P.W, h0 = (m0 / P.W) % P.H, b0 = m0 / (P.W * P.H);
-                for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+                for (int kb = kb0; kb < kb1; ++kb, ++kbc) {
                     const int s = kbc % S;
                     mbar_wait(&empty[s], ((kbc / S) & 1) ^ 1);
                     if (leader) mbar_expect_tx(&full[s], (uint32_t)(2 * (kABytes + b_bytes)));
@@ -236,12 +247,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.BN >> 3) << 17) |
                                    ((uint32_t)(256 >> 4) << 24);
             int kbc = 0, it = 0;
-            for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters, ++it) {
+            for (int item = cluster_id; item < n_items; item += n_clusters, ++it) {
+                const int sp = item % P.splits;
+                const int kb0 = (int)((long long)sp * nkb / P.splits), kb1 = (int)((long long)(sp + 1) * nkb / P.splits);
                 const int acc = it & 1;
                 mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * P.BN);
-                for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+                for (int kb = kb0; kb < kb1; ++kb, ++kbc) {
                     const int s = kbc % S;
                     mbar_wait(&full[s], (kbc / S) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -250,9 +263,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         const uint64_t bd = make_sdesc(smem_u32(sB + s * b_bytes));
 #pragma unroll
                         for (int k = 0; k < kKSteps; ++k)
-                            umma2<F16>(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                            umma2<F16>(tmem_d, ad + 2 * k, bd + 2 * k, idesc, ((kb - kb0) | k) ? 1u : 0u);
                         umma2_commit(&empty[s]);
-                        if (kb == nkb - 1) umma2_commit(&tmem_full[acc]);
+                        if (kb == kb1 - 1) umma2_commit(&tmem_full[acc]);
                     }
                     __syncwarp();
                 }
@@ -263,7 +276,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         int it = 0;
-        for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters, ++it) {
+        for (int item = cluster_id; item < n_items; item += n_clusters, ++it) {
+            const int tile = item / P.splits, sp = item - tile * P.splits;
             const int acc = it & 1;
             const int mp = tile / P.n_tiles_n, nt = tile - mp * P.n_tiles_n;
             const int m0 = (mp * 2 + (int)rank) * kBM;
@@ -272,10 +286,74 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const bool valid = q < P.M;
             int w = 0, h = 0, b = 0;
             if (valid) { w = q % P.W; h = (q / P.W) % P.H; b = q / (P.W * P.H); }
-            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int cb = 0; cb < P.BN; cb += 32) {
-                uint32_t r[32];
+            // the shared tail of both modes: bias / embedding / residual, store, statistics of 32 accumulator columns
+            auto finish = [&](uint32_t (&r)[32], int cb) {
+                    const int nb = n0 + cb;
+                    // statistics: the 32 rows of a warp belong to one sample (host checks H*W % 32 == 0)
+                    const int q0 = m0 + quarter * 32;
+                    const bool wvalid = q0 < P.M;
+                    const int bw = wvalid ? q0 / (P.W * P.H) : 0;
+                    float sv[64];     // [0, 32): final values of this row's 32 channels, [32, 64): their squares (0 for invalid rows)
+    #pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const int n = nb + j;
+                        float v[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (valid && n < P.Cout) {
+    #pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                v[e] = __uint_as_float(r[j + e]);
+                                if (P.bias) v[e] += P.bias[n + e];
+                                if (P.emb) v[e] += P.emb[(size_t)b * P.emb_stride + n + e];
+                            }
+                            if (P.res_mode == 1) {
+                                const float4 t = *reinterpret_cast<const float4*>(P.res + (size_t)q * P.Cout + n);
+                                v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                            } else if (P.res_mode == 2) {
+                                const int H2 = P.H * 2, W2 = P.W * 2;
+                                const float* rb = P.res + (((size_t)b * H2 + 2 * h) * W2 + 2 * w) * P.Cout + n;
+                                const float4 r0 = *reinterpret_cast<const float4*>(rb);
+                                const float4 r1 = *reinterpret_cast<const float4*>(rb + P.Cout);
+                                const float4 r2 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout);
+                                const float4 r3 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout + P.Cout);
+                                v[0] += (r0.x + r1.x + r2.x + r3.x) * 0.25f;
+                                v[1] += (r0.y + r1.y + r2.y + r3.y) * 0.25f;
+                                v[2] += (r0.z + r1.z + r2.z + r3.z) * 0.25f;
+                                v[3] += (r0.w + r1.w + r2.w + r3.w) * 0.25f;
+                            } else if (P.res_mode == 3) {
+                                const int Hh = P.H / 2, Wh = P.W / 2;
+                                const float4 t = *reinterpret_cast<const float4*>(
+                                    P.res + (((size_t)b * Hh + (h >> 1)) * Wh + (w >> 1)) * P.Cout + n);
+                                v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+                            }
+                            *reinterpret_cast<float4*>(P.out + (size_t)q * P.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
+                        }
+    #pragma unroll
+                        for (int e = 0; e < 4; ++e) { sv[j + e] = v[e]; sv[32 + j + e] = v[e] * v[e]; }
+                    }
+                    if (P.gn_stats) {   // warp-uniform
+                        // column sums over the warp's 32 rows by a reduce-scatter butterfly (62 shuffles for 64 values): each
+                        // step halves the values a lane keeps; lane L ends with entries 2L, 2L+1 (L < 16: sums of channels
+                        // 2L, 2L+1; L >= 16: their sums of squares)
+    #pragma unroll
+                        for (int half = 32, o = 16; half >= 2; half >>= 1, o >>= 1) {
+                            const bool up = (lane & o) != 0;
+    #pragma unroll
+                            for (int i = 0; i < half; ++i) {
+                                const float send = up ? sv[i] : sv[i + half];
+                                const float keep = up ? sv[i + half] : sv[i];
+                                sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                            }
+                        }
+                        const int ch = nb + 2 * (lane & 15);
+                        if (wvalid && ch < P.Cout) {
+                            double* st = P.gn_stats + (size_t)(cluster_id % ANODDPM_STAT_REPLICAS) * P.stat_replica_stride +
+                                         ((size_t)bw * P.Cout + ch) * 2 + (lane >> 4);
+                            atomicAdd(st, (double)sv[0]);
+                            atomicAdd(st + 2, (double)sv[1]);
+                        }
+                    }
+            };
+            auto load_acc = [&](uint32_t (&r)[32], int cb) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.BN + cb);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -293,68 +371,50 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive_remote(&tmem_empty[acc], 0);
                 }
-                const int nb = n0 + cb;
-                // statistics: the 32 rows of a warp belong to one sample (host checks H*W % 32 == 0)
-                const int q0 = m0 + quarter * 32;
-                const bool wvalid = q0 < P.M;
-                const int bw = wvalid ? q0 / (P.W * P.H) : 0;
-                float sv[64];     // [0, 32): final values of this row's 32 channels, [32, 64): their squares (0 for invalid rows)
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int n = nb + j;
-                    float v[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (valid && n < P.Cout) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            v[e] = __uint_as_float(r[j + e]);
-                            if (P.bias) v[e] += P.bias[n + e];
-                            if (P.emb) v[e] += P.emb[(size_t)b * P.emb_stride + n + e];
-                        }
-                        if (P.res_mode == 1) {
-                            const float4 t = *reinterpret_cast<const float4*>(P.res + (size_t)q * P.Cout + n);
-                            v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
-                        } else if (P.res_mode == 2) {
-                            const int H2 = P.H * 2, W2 = P.W * 2;
-                            const float* rb = P.res + (((size_t)b * H2 + 2 * h) * W2 + 2 * w) * P.Cout + n;
-                            const float4 r0 = *reinterpret_cast<const float4*>(rb);
-                            const float4 r1 = *reinterpret_cast<const float4*>(rb + P.Cout);
-                            const float4 r2 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout);
-                            const float4 r3 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout + P.Cout);
-                            v[0] += (r0.x + r1.x + r2.x + r3.x) * 0.25f;
-                            v[1] += (r0.y + r1.y + r2.y + r3.y) * 0.25f;
-                            v[2] += (r0.z + r1.z + r2.z + r3.z) * 0.25f;
-                            v[3] += (r0.w + r1.w + r2.w + r3.w) * 0.25f;
-                        } else if (P.res_mode == 3) {
-                            const int Hh = P.H / 2, Wh = P.W / 2;
-                            const float4 t = *reinterpret_cast<const float4*>(
-                                P.res + (((size_t)b * Hh + (h >> 1)) * Wh + (w >> 1)) * P.Cout + n);
-                            v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
-                        }
-                        *reinterpret_cast<float4*>(P.out + (size_t)q * P.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
-                    }
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { sv[j + e] = v[e]; sv[32 + j + e] = v[e] * v[e]; }
+            };
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (P.splits == 1) {
+                for (int cb = 0; cb < P.BN; cb += 32) {
+                    uint32_t r[32];
+                    load_acc(r, cb);
+                    finish(r, cb);
                 }
-                if (P.gn_stats) {   // warp-uniform
-                    // column sums over the warp's 32 rows by a reduce-scatter butterfly (62 shuffles for 64 values): each
-                    // step halves the values a lane keeps; lane L ends with entries 2L, 2L+1 (L < 16: sums of channels
-                    // 2L, 2L+1; L >= 16: their sums of squares)
+            } else {
+                // partial accumulators of this K range -> workspace (thread = row: 128 contiguous bytes per 32 columns)
+                float* wrow = P.ws_part + (size_t)sp * P.ws_split_stride + (size_t)q * P.ws_ld + n0;
+                for (int cb = 0; cb < P.BN; cb += 32) {
+                    uint32_t r[32];
+                    load_acc(r, cb);
 #pragma unroll
-                    for (int half = 32, o = 16; half >= 2; half >>= 1, o >>= 1) {
-                        const bool up = (lane & o) != 0;
+                    for (int j = 0; j < 32; j += 4)
+                        __stcg(reinterpret_cast<float4*>(wrow + cb + j), make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                                      __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+                }
+                __threadfence();
+                __syncwarp();
+                int last = 0;
+                if (lane == 0) {
+                    int* cnt = P.ws_cnt + ((size_t)tile * 2 + rank) * 4 + quarter;
+                    last = atomicAdd(cnt, 1) == P.splits - 1;
+                    if (last) { *cnt = 0; __threadfence(); }      // ready for the next launch; orders the partial reads below
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    const float* prow = P.ws_part + (size_t)q * P.ws_ld + n0;
+                    for (int cb = 0; cb < P.BN; cb += 32) {
+                        uint32_t r[32];
 #pragma unroll
-                        for (int i = 0; i < half; ++i) {
-                            const float send = up ? sv[i] : sv[i + half];
-                            const float keep = up ? sv[i + half] : sv[i];
-                            sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 a4 = __ldcg(reinterpret_cast<const float4*>(prow + cb + j));
+                            for (int s2 = 1; s2 < P.splits; ++s2) {
+                                const float4 t4 = __ldcg(reinterpret_cast<const float4*>(prow + (size_t)s2 * P.ws_split_stride + cb + j));
+                                a4.x += t4.x; a4.y += t4.y; a4.z += t4.z; a4.w += t4.w;
+                            }
+                            r[j] = __float_as_uint(a4.x); r[j + 1] = __float_as_uint(a4.y);
+                            r[j + 2] = __float_as_uint(a4.z); r[j + 3] = __float_as_uint(a4.w);
                         }
-                    }
-                    const int ch = nb + 2 * (lane & 15);
-                    if (wvalid && ch < P.Cout) {
-                        double* st = P.gn_stats + (size_t)(cluster_id % ANODDPM_STAT_REPLICAS) * P.stat_replica_stride +
-                                     ((size_t)bw * P.Cout + ch) * 2 + (lane >> 4);
-                        atomicAdd(st, (double)sv[0]);
-                        atomicAdd(st + 2, (double)sv[1]);
+                        finish(r, cb);
                     }
                 }
             }
@@ -421,9 +481,51 @@ int make_w_map2(CUtensorMap* m, const void* p, int f16, int Ktot, int Cout, int 
     return ANODDPM_OK;
 }
 
+// Pair-tile N for a problem of m_pairs 256-row tiles, Cout columns and nkb K-blocks.  The kernel is bound by the per-SM L2->SM
+// operand stream (one 16 KB A tile + BN/2 weight rows of 128 B per K-block and CTA), so a small map is fastest when its tiles
+// cover the 74 CTA pairs even if that means narrow tiles: 8x8 maps at bs 32 (8 row tiles) run 16 tiles with BN = 256 and 64
+// with BN = 64.  cost = rounds x (K-blocks x bytes per K-block + a fixed per-tile term), ties to the wider tile.
+int tc2_pick_bn(int Cout, int m_pairs, int nkb) {
+    if (Cout < 128) return Cout;
+    int best = 0;
+    long long best_cost = 0;
+    for (int bn = 256; bn >= 32; bn >>= 1) {
+        if (Cout % bn) continue;
+        const long long tiles = (long long)m_pairs * (Cout / bn);
+        const long long rounds = (tiles + 73) / 74;
+        const long long cost = rounds * ((long long)nkb * (kABytes + (bn / 2) * kRowBytes) + 48 * 1024 + (long long)bn * 512);
+        if (!best || cost < best_cost) { best = bn; best_cost = cost; }
+    }
+    return best ? best : 128;
+}
+
+// K splits for a problem of n_tiles pair tiles and nkb K-blocks: fill the 74 CTA pairs, at least 8 K-blocks per split
+int tc2_splits(int n_tiles, int nkb) {
+    if (n_tiles * 2 > 74 || nkb < 16) return 1;
+    int s = 74 / n_tiles;
+    if (s > nkb / 8) s = nkb / 8;
+    if (s > 8) s = 8;
+    return s < 1 ? 1 : s;
+}
+
 }  // namespace
 
 extern "C" int anoddpm_conv_tc_supported(const anoddpm_conv_desc* d);
+
+// bytes of anoddpm_conv_desc::workspace that let impl 2 split the K loop of this problem (0: the problem is not split)
+extern "C" long long anoddpm_conv_workspace_bytes(const anoddpm_conv_desc* d) {
+    if (!d || d->impl != 2 || !anoddpm_conv_tc_supported(d)) return 0;
+    const int ke = d->operand_f16 ? 64 : 32;
+    const int m_pairs = adp_ceil_div((long long)d->B * d->H * d->W, 2 * kBM);
+    const int nkb = (d->ksize * d->ksize * d->Ca + d->Cr1 + d->Cr2) / ke;
+    const int BN = tc2_pick_bn(d->Cout, m_pairs, nkb);
+    const int n_tiles_n = adp_ceil_div(d->Cout, BN);
+    const int n_tiles = m_pairs * n_tiles_n;
+    const int splits = tc2_splits(n_tiles, nkb);
+    if (splits == 1) return 0;
+    const long long cnt_bytes = (((long long)n_tiles * 8 * (long long)sizeof(int)) + 255) / 256 * 256;
+    return cnt_bytes + (long long)splits * m_pairs * 2 * kBM * n_tiles_n * BN * (long long)sizeof(float);
+}
 
 int anoddpm_conv_tc2(const anoddpm_conv_desc* d, void* stream) {
     ADP_REQUIRE(anoddpm_conv_tc_supported(d), "anoddpm_conv(impl=2): shape not covered by the tensor-core tiling "
@@ -447,7 +549,8 @@ int anoddpm_conv_tc2(const anoddpm_conv_desc* d, void* stream) {
     P.nkb_a = d->ksize * d->ksize * P.chunks_a;
     P.nkb_r1 = d->Cr1 / P.ke;
     P.nkb_r2 = d->Cr2 / P.ke;
-    P.BN = (d->Cout % 256 == 0) ? 256 : (d->Cout < 128 ? d->Cout : 128);
+    const int m_pairs = adp_ceil_div(P.M, 2 * kBM);
+    P.BN = tc2_pick_bn(d->Cout, m_pairs, P.nkb_a + P.nkb_r1 + P.nkb_r2);
     const int acc_cols = kAccStages * P.BN;
     P.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
     const int Ktot = (P.nkb_a + P.nkb_r1 + P.nkb_r2) * P.ke;
@@ -456,8 +559,17 @@ int anoddpm_conv_tc2(const anoddpm_conv_desc* d, void* stream) {
     if (stages > kMaxStages) stages = kMaxStages;
     P.stages = stages;
     P.n_tiles_n = adp_ceil_div(d->Cout, P.BN);
-    const int m_pairs = adp_ceil_div(P.M, 2 * kBM);
     P.n_tiles = m_pairs * P.n_tiles_n;
+    // split-K when the tiles do not fill the machine (8x8 maps at bs 32: 16 tiles for 74 CTA pairs) and the caller gave a
+    // workspace: each (tile, K range) item is one CTA-pair job, the last arriver of a 32-row block reduces + finishes it
+    P.splits = tc2_splits(P.n_tiles, P.nkb_a + P.nkb_r1 + P.nkb_r2);
+    P.ws_ld = P.n_tiles_n * P.BN;
+    P.ws_split_stride = (long long)m_pairs * 2 * kBM * P.ws_ld;
+    const long long cnt_bytes = (((long long)P.n_tiles * 8 * (long long)sizeof(int)) + 255) / 256 * 256;
+    if (P.splits > 1 && (!d->workspace || d->workspace_bytes < cnt_bytes + P.splits * P.ws_split_stride * (long long)sizeof(float)))
+        P.splits = 1;
+    P.ws_cnt = static_cast<int*>(d->workspace);
+    P.ws_part = P.splits > 1 ? reinterpret_cast<float*>(static_cast<char*>(d->workspace) + cnt_bytes) : nullptr;
 
     CUtensorMap ma, m1, m2, mw;
     int rc;
@@ -477,7 +589,8 @@ int anoddpm_conv_tc2(const anoddpm_conv_desc* d, void* stream) {
         attr_dev[dev_ & 63] = true;
     }
     int sms = 148;
-    int n_clusters = P.n_tiles < sms / 2 ? P.n_tiles : sms / 2;
+    const int n_items = P.n_tiles * P.splits;
+    int n_clusters = n_items < sms / 2 ? n_items : sms / 2;
     if (f16) conv_tc2_kernel<true><<<dim3(2 * n_clusters), kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, P);
     else conv_tc2_kernel<false><<<dim3(2 * n_clusters), kThreads, smem, (cudaStream_t)stream>>>(ma, m1, m2, mw, P);
     ADP_LAUNCH_CHECK();

@@ -122,8 +122,11 @@ __global__ void __launch_bounds__(256) head_gather_kernel(float* __restrict__ ou
 }
 
 // ------------------------------------------------------------------------------------------------ stem (Cin = 1)
-// thread = (4 output channels, pixel lane); a CTA walks 8-pixel row segments; per-channel statistics are kept per thread and
-// reduced once per CTA.  grid-stride over (b, y, x-segment) with all segments of a CTA belonging to one sample.
+// thread = (4 output channels, pixel lane) x PPT consecutive pixels; a CTA walks (8 PPT)-pixel row segments; per-channel statistics
+// are kept per thread and reduced once per CTA.  All segments of a CTA belong to one sample.  PPT = 4 keeps four pixels' stores
+// (3 KB per warp) in flight per iteration of the load -> FMA -> store chain: one pixel per iteration left the kernel latency-bound
+// at 1.85 TB/s.
+template <int PPT>
 __global__ void __launch_bounds__(256) conv_stem_fused_kernel(float* __restrict__ out, __half* __restrict__ out16,
                                                               double* __restrict__ stats, const float* __restrict__ x,
                                                               const float* __restrict__ w, const float* __restrict__ bias, int B,
@@ -138,9 +141,10 @@ __global__ void __launch_bounds__(256) conv_stem_fused_kernel(float* __restrict_
     }
     for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
     __syncthreads();
+    constexpr int SEG = 8 * PPT;                           // pixels per segment
     const int nc4 = Cout >> 2, lanes = 256 / nc4;          // pixel lanes (Cout = 128: 8 lanes)
     const int pl = threadIdx.x / nc4, c4 = (threadIdx.x - pl * nc4) * 4;
-    const int segs_x = W / 8, segs_img = segs_x * H;
+    const int segs_x = W / SEG, segs_img = segs_x * H;
     const long long seg0 = (long long)blockIdx.x * segs_per_cta;
     const int b = (int)(seg0 / segs_img);                  // segs_img % segs_per_cta == 0: one sample per CTA
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
@@ -151,36 +155,44 @@ __global__ void __launch_bounds__(256) conv_stem_fused_kernel(float* __restrict_
     if (pl < lanes) {
         for (int s = 0; s < segs_per_cta; ++s) {
             const int sg = (int)((seg0 + s) % segs_img);
-            const int y = sg / segs_x, xs = (sg - y * segs_x) * 8;
-            // this thread's pixel of the segment: lanes pixels in parallel, 8 / lanes rounds
-            for (int px = pl; px < 8; px += lanes) {
+            const int y = sg / segs_x, xs = (sg - y * segs_x) * SEG;
+            // this thread's PPT consecutive pixels of the segment
+            for (int px = pl * PPT; px < SEG; px += lanes * PPT) {
                 const int xx = xs + px;
-                float win[9];
+                float win[3][PPT + 2];
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const int yy = y + t / 3 - 1, xq = xx + t % 3 - 1;
-                    win[t] = (yy >= 0 && yy < H && xq >= 0 && xq < W) ? __ldg(x + ((size_t)b * H + yy) * W + xq) : 0.f;
-                }
-                F4e a = bv;
+                for (int r = 0; r < 3; ++r) {
+                    const int yy = y + r - 1;
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    a.x = fmaf(win[t], wv[t].x, a.x);
-                    a.y = fmaf(win[t], wv[t].y, a.y);
-                    a.z = fmaf(win[t], wv[t].z, a.z);
-                    a.w = fmaf(win[t], wv[t].w, a.w);
+                    for (int c = 0; c < PPT + 2; ++c) {
+                        const int xq = xx + c - 1;
+                        win[r][c] = (yy >= 0 && yy < H && xq >= 0 && xq < W) ? __ldg(x + ((size_t)b * H + yy) * W + xq) : 0.f;
+                    }
                 }
-                const size_t o = (((size_t)b * H + y) * W + xx) * Cout + c4;
-                *reinterpret_cast<F4e*>(out + o) = a;
-                if (out16) {
-                    const __half2 h0 = __floats2half2_rn(fminf(fmaxf(a.x, -65504.f), 65504.f), fminf(fmaxf(a.y, -65504.f), 65504.f));
-                    const __half2 h1 = __floats2half2_rn(fminf(fmaxf(a.z, -65504.f), 65504.f), fminf(fmaxf(a.w, -65504.f), 65504.f));
-                    uint2 u;
-                    u.x = *reinterpret_cast<const uint32_t*>(&h0);
-                    u.y = *reinterpret_cast<const uint32_t*>(&h1);
-                    *reinterpret_cast<uint2*>(out16 + o) = u;
+#pragma unroll
+                for (int i = 0; i < PPT; ++i) {
+                    F4e a = bv;
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const float v = win[t / 3][i + t % 3];
+                        a.x = fmaf(v, wv[t].x, a.x);
+                        a.y = fmaf(v, wv[t].y, a.y);
+                        a.z = fmaf(v, wv[t].z, a.z);
+                        a.w = fmaf(v, wv[t].w, a.w);
+                    }
+                    const size_t o = (((size_t)b * H + y) * W + xx + i) * Cout + c4;
+                    *reinterpret_cast<F4e*>(out + o) = a;
+                    if (out16) {
+                        const __half2 h0 = __floats2half2_rn(fminf(fmaxf(a.x, -65504.f), 65504.f), fminf(fmaxf(a.y, -65504.f), 65504.f));
+                        const __half2 h1 = __floats2half2_rn(fminf(fmaxf(a.z, -65504.f), 65504.f), fminf(fmaxf(a.w, -65504.f), 65504.f));
+                        uint2 u;
+                        u.x = *reinterpret_cast<const uint32_t*>(&h0);
+                        u.y = *reinterpret_cast<const uint32_t*>(&h1);
+                        *reinterpret_cast<uint2*>(out16 + o) = u;
+                    }
+                    s1[0] += a.x; s1[1] += a.y; s1[2] += a.z; s1[3] += a.w;
+                    s2[0] += a.x * a.x; s2[1] += a.y * a.y; s2[2] += a.z * a.z; s2[3] += a.w * a.w;
                 }
-                s1[0] += a.x; s1[1] += a.y; s1[2] += a.z; s1[3] += a.w;
-                s2[0] += a.x * a.x; s2[1] += a.y * a.y; s2[2] += a.z * a.z; s2[3] += a.w * a.w;
             }
         }
     }
@@ -304,13 +316,18 @@ extern "C" int anoddpm_conv_stem_fused(float* out_nhwc, void* out16_nhwc, double
     ADP_REQUIRE(out_nhwc && x_nchw && w_oihw && B > 0 && H > 0 && W > 0, "anoddpm_conv_stem_fused: bad arguments");
     ADP_REQUIRE(Cin == 1 && Cout % 4 == 0 && Cout <= 1024 && 256 % (Cout / 4) == 0 && W % 8 == 0,
                 "anoddpm_conv_stem_fused: needs Cin == 1, Cout/4 dividing 256, W %% 8 == 0 (Cin=%d Cout=%d W=%d)", Cin, Cout, W);
-    const int segs_img = (W / 8) * H;
-    int spc = 64;                                   // segments per CTA; must divide the segments of one image
+    const int ppt = (W % 32 == 0) ? 4 : 1;          // pixels per thread: segments of 32 (or 8) pixels
+    const int segs_img = (W / (8 * ppt)) * H;
+    int spc = 64 / ppt;                             // segments per CTA; must divide the segments of one image
     while (spc > 1 && (segs_img % spc || (long long)B * segs_img / spc < 148 * 8)) spc >>= 1;
     const long long ctas = (long long)B * segs_img / spc;
     const size_t smem = ((size_t)10 * Cout + 256 * 8) * sizeof(float);
-    conv_stem_fused_kernel<<<(unsigned)ctas, 256, smem, (cudaStream_t)stream>>>(out_nhwc, static_cast<__half*>(out16_nhwc), stats,
-                                                                                 x_nchw, w_oihw, bias, B, H, W, Cout, spc);
+    if (ppt == 4)
+        conv_stem_fused_kernel<4><<<(unsigned)ctas, 256, smem, (cudaStream_t)stream>>>(out_nhwc, static_cast<__half*>(out16_nhwc), stats,
+                                                                                        x_nchw, w_oihw, bias, B, H, W, Cout, spc);
+    else
+        conv_stem_fused_kernel<1><<<(unsigned)ctas, 256, smem, (cudaStream_t)stream>>>(out_nhwc, static_cast<__half*>(out16_nhwc), stats,
+                                                                                        x_nchw, w_oihw, bias, B, H, W, Cout, spc);
     ADP_LAUNCH_CHECK();
     return ANODDPM_OK;
 }

@@ -86,6 +86,8 @@ class UNetEngine:
         self.model = model
         self._sig = None
         self._time_table = None
+        self._ws, self._ws_keep = {}, []
+        self.split_k, self.split_convs, self.sep_head = False, 0, True      # per-forward switches (set again by _forward)
         self._gen = 0               # bumped by invalidate(): raw-pointer / .data writes do not bump p._version
         self.launches = 0           # native kernel launches issued (for bench.py's gpu_launches)
 
@@ -293,6 +295,13 @@ class UNetEngine:
             st = self._stats_slot(B, cout)
             d.gn_stats = st.data_ptr()
             self.fused_stats += 1
+        if impl == 2 and self.split_k:
+            # small maps: split-K over a persistent, zero-initialised workspace (arrival counters reset themselves)
+            need = _lib.lib().anoddpm_conv_workspace_bytes(ctypes.byref(d))
+            if need > 0:
+                ws = self._workspace(need, a.device)
+                d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+                self.split_convs += 1
         call("anoddpm_conv", ctypes.byref(d), stream())
         self.launches += 1
         self.tc_convs += 1 if impl else 0
@@ -302,6 +311,16 @@ class UNetEngine:
             self.f16_outputs += 1
             return _T(out, st, shift=(b, emb))
         return _T(out, st, t16=out16)
+
+    def _workspace(self, nbytes, dev):
+        """Persistent zeroed scratch for the split-K convolutions of this engine (grow-only; earlier buffers stay alive because
+        captured CUDA graphs may still point at them)."""
+        ws = self._ws.get(dev)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.zeros(int(nbytes), device=dev, dtype=torch.uint8)
+            self._ws_keep.append(ws)
+            self._ws[dev] = ws
+        return ws
 
     def _plan(self, H, W, Ca, Cr, cout, ksize):
         """(impl, f16) for a conv with main source Ca channels and (single, concatenated) skip source Cr channels."""
@@ -508,6 +527,10 @@ class UNetEngine:
         self.fuse_gn = self.h1_f16 and getattr(m, "fuse_gn", True)
         self.fuse_gn2 = getattr(m, "fuse_gn2", True)
         self.sep_head = getattr(m, "sep_head", True) and os.environ.get("ANODDPM_SEP_HEAD", "1") != "0"
+        # split-K of small-map convs: measured SLOWER than narrow tiles at bs 32 (the last arriver's reduction is a serial tail);
+        # conv_tc2 picks a narrower pair tile instead (tc2_pick_bn).  ANODDPM_SPLIT_K=1 enables it (tiny batches)
+        self.split_k = os.environ.get("ANODDPM_SPLIT_K", "0") == "1"
+        self.split_convs = 0
         self.gn_tables = 0
         self.f16_outputs = 0
         self.f16_convs = 0

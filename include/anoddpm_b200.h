@@ -196,8 +196,17 @@ typedef struct anoddpm_conv_desc {
                                math, rounded to nearest fp16) before the tensor cores read it; zero padding stays zero */
     void* out16;            /* optional fp16 copy of the fp32 output (same NHWC shape): the raw operand of the next
                                convolution with gn_table, and of a fused 1x1 skip convolution; not with out_f16 */
+    /* ---- impl 2, small maps: split-K.  When the problem has fewer tiles than CTA pairs (8x8 maps), each tile's K loop is
+     * cut into up to 8 ranges that run as separate CTA-pair jobs; partial accumulators meet in `workspace` and the last job
+     * to arrive finishes the tile (sums in split order: deterministic).  The first anoddpm_conv_workspace_bytes() bytes
+     * must be ZERO on first use (arrival counters; the kernel leaves them zero) and the buffer must not be shared by
+     * convolutions running concurrently.  NULL / too small: no split. ---- */
+    void* workspace;
+    long long workspace_bytes;
 } anoddpm_conv_desc;
 int anoddpm_conv(const anoddpm_conv_desc* d /* [host] */, void* stream);
+/* bytes of `workspace` that enable split-K for this problem (0 if it would not be split) */
+long long anoddpm_conv_workspace_bytes(const anoddpm_conv_desc* d /* [host] */);
 /* 1 if impl=1/2 (tcgen05 tiles: channels % 32, Cout % 16, power-of-two W) covers the problem, else 0. */
 int anoddpm_conv_tc_supported(const anoddpm_conv_desc* d /* [host] */);
 /* 1 if impl=3 covers the problem (ksize 3, H % 16 == W % 16 == 0, channels % 32 == 0, Cout % 16 == 0). */

@@ -430,7 +430,7 @@ def test_fused_stem_features_statistics_and_fp16_copy():
     import torch.nn.functional as F
     from anoddpm_b200 import _lib
     g = torch.Generator().manual_seed(12)
-    for (B, H, W, C) in [(3, 32, 48, 128), (1, 256, 256, 128), (2, 16, 8, 64)]:
+    for (B, H, W, C) in [(3, 32, 48, 128), (1, 256, 256, 128), (2, 16, 8, 64), (2, 16, 64, 128), (1, 8, 32, 64)]:
         x = torch.randn(B, 1, H, W, generator=g).to(DEV)
         w = (torch.randn(C, 1, 3, 3, generator=g) * 0.3).to(DEV)
         b = torch.randn(C, generator=g).to(DEV)

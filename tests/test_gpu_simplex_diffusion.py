@@ -110,6 +110,22 @@ def test_batched_simplex_is_per_sample_reference():
         assert np.array_equal(sh[b, 0], ref[0].astype(np.float32))
 
 
+@pytest.mark.parametrize("freq", [48.0, 10.0, 64.0, 0.5, 2.0 ** -3])
+def test_octave_frequencies_division_and_power_of_two_paths(freq):
+    """Power-of-two frequencies take the multiply-by-reciprocal path of the octave kernel, the others the IEEE division of the
+    reference (simplex.py:75-93): both bit-exact against the oracle."""
+    from anoddpm_b200.simplex import Simplex_CLASS
+    from oracle.simplex_oracle import OracleSimplex
+    S = Simplex_CLASS()
+    S.newSeed(4242)
+    O = OracleSimplex(4242)
+    a = S.rand_3d_fixed_T_octaves((40, 24), np.array([7, 901]), 5, 0.7, freq)
+    b = O.rand_3d_fixed_T_octaves((40, 24), np.array([7, 901]), 5, 0.7, freq)
+    assert np.array_equal(a, b)
+    v = S.rand_3d_octaves((3, 16, 24), 4, 0.6, freq)
+    assert np.array_equal(v, O.rand_3d_octaves((3, 16, 24), 4, 0.6, freq))
+
+
 @pytest.mark.parametrize("T,name", [(100, "linear"), (1000, "linear"), (100, "cosine"), (1000, "cosine")])
 def test_diffusion_steps_bit_exact_vs_reference_golden(golden, T, name):
     from anoddpm_b200.GaussianDiffusion import GaussianDiffusionModel, get_beta_schedule

@@ -606,3 +606,52 @@ def test_fused_adamw_ema_step_matches_torch_sequence():
     with torch.no_grad():
         y = m2(torch.randn(1, 1, 32, 32, device=DEV), torch.tensor([5], device=DEV))
     assert bool(torch.isfinite(y).all())
+
+
+@pytest.mark.parametrize("case", [dict(B=32, H=8, W=8, Ca=512, Cout=512, ks=3), dict(B=32, H=8, W=8, Ca=1024, Cout=512, ks=3),
+                                  dict(B=4, H=8, W=8, Ca=256, Cout=256, ks=3), dict(B=8, H=8, W=8, Ca=512, Cout=384, ks=3)])
+def test_conv_tc2_split_k_matches_unsplit_and_torch(case):
+    """impl 2 on small maps with a workspace (K loop split over CTA pairs, last arriver reduces + finishes the tile) against
+    the same kernel without a workspace and against torch fp64 on the same fp16-rounded operands; epilogue extras (embedding
+    row, residual, per-channel statistics) included.  Runs twice on one workspace: the arrival counters must reset."""
+    from anoddpm_b200 import _lib
+    from anoddpm_b200.engine import pack_conv_weight
+    B, H, W, Ca, Cout = case["B"], case["H"], case["W"], case["Ca"], case["Cout"]
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(B, Ca, H, W, generator=g).to(DEV)
+    w = (torch.randn(Cout, Ca, 3, 3, generator=g) * (1.0 / (3 * Ca ** 0.5))).to(DEV)
+    bias = torch.randn(Cout, generator=g).to(DEV)
+    emb = torch.randn(B, Cout, generator=g).to(DEV)
+    res = torch.randn(B, Cout, H, W, generator=g).to(DEV)
+    an = nhwc(a).half()
+    wp = pack_conv_weight(w).contiguous().half()
+    resn = nhwc(res)
+
+    def run(ws):
+        out = torch.empty(B, H, W, Cout, device=DEV)
+        st = torch.zeros(REPL * B * Cout * 2, device=DEV, dtype=torch.float64)
+        d = _lib.ConvDesc()
+        d.out, d.a, d.w, d.bias = out.data_ptr(), an.data_ptr(), wp.data_ptr(), bias.data_ptr()
+        d.B, d.H, d.W, d.Ca, d.Cout, d.ksize, d.impl, d.operand_f16 = B, H, W, Ca, Cout, 3, 2, 1
+        d.emb, d.emb_stride = emb.data_ptr(), Cout
+        d.res, d.res_mode = resn.data_ptr(), 1
+        d.gn_stats = st.data_ptr()
+        need = _lib.lib().anoddpm_conv_workspace_bytes(ctypes.byref(d))
+        if ws is not None:
+            assert need > 0 and ws.numel() >= need
+            d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
+        _lib.call("anoddpm_conv", ctypes.byref(d), _lib.stream())
+        torch.cuda.synchronize()
+        return out, st.view(REPL, B, Cout, 2).sum(0), need
+
+    base, st0, need = run(None)
+    ws = torch.zeros(need, device=DEV, dtype=torch.uint8)
+    o1, st1, _ = run(ws)
+    o2, st2, _ = run(ws)          # second launch on the same workspace: counters were reset by the kernel
+    ref = F.conv2d(an.permute(0, 3, 1, 2).double(), wp.view(Cout, 3, 3, Ca).permute(0, 3, 1, 2).double(), bias.double(), padding=1)
+    ref = nhwc(ref + emb.double()[:, :, None, None] + res.double()).float()
+    print(f"[parity] conv_tc2 split-K {case}: vs torch fp64 {rel(o1, ref):.2e}, vs unsplit {rel(o1, base):.2e}")
+    assert torch.equal(o1, o2) and torch.equal(st1, st2)       # deterministic: partials are added in split order
+    assert rel(o1, ref) < 2e-5 and rel(base, ref) < 2e-5 and rel(o1, base) < 2e-5      # fp32 summation order only (measured <= 6.4e-6)
+    assert torch.allclose(st1[..., 0], ref.double().sum(dim=(1, 2)), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(st1, st0, rtol=1e-5, atol=1e-3)
