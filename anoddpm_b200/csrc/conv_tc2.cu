@@ -28,6 +28,7 @@ constexpr int kThreads = 256;
 constexpr int kABytes = kBM * kRowBytes;
 constexpr int kAccStages = 2;
 constexpr int kMaxStages = 8;
+constexpr int kEpiTileBytes = 4 * 32 * 33 * 4;   // per epilogue warp a 32 x 33 fp32 transpose tile
 
 struct Tc2Args {
     float* out;
@@ -174,6 +175,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint64_t* tmem_full = bars + 2 * kMaxStages; // [2]   both CTAs (multicast commit)
     uint64_t* tmem_empty = tmem_full + kAccStages;  // [2] leader only, 2 x 128 arrivals
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kAccStages);
+    float* epi_tiles = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][32][33]: accumulator chunk transpose
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
@@ -275,6 +277,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ---------------- epilogue (both CTAs): TMEM -> registers -> global (NHWC) ----------------
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
+        float* tbuf = epi_tiles + quarter * (32 * 33);
         int it = 0;
         for (int item = cluster_id; item < n_items; item += n_clusters, ++it) {
             const int tile = item / P.splits, sp = item - tile * P.splits;
@@ -283,75 +286,77 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int m0 = (mp * 2 + (int)rank) * kBM;
             const int n0 = nt * P.BN;
             const int q = m0 + row;
-            const bool valid = q < P.M;
-            int w = 0, h = 0, b = 0;
-            if (valid) { w = q % P.W; h = (q / P.W) % P.H; b = q / (P.W * P.H); }
             // the shared tail of both modes: bias / embedding / residual, store, statistics of 32 accumulator columns
+            // Through a per-warp 32 x 33 shared-memory tile the accumulator chunk changes from lane = row (TMEM) to lane = column:
+            // every global access of the tail is then one contiguous 128-byte row segment (the lane-per-row form touched 32
+            // lines with 16 bytes each per instruction and left the 1x1 convolutions of the attention blocks store-bound at
+            // 0.7 TB/s), bias / embedding are per-lane scalars, and a column's statistics are a plain register sum over the rows.
+            const int HW = P.H * P.W;
+            const int q0 = m0 + quarter * 32;            // first row of this warp
+            const bool wvalid = q0 < P.M;
+            const int b0 = wvalid ? q0 / HW : 0;
+            const int rb = (b0 + 1) * HW - q0;           // rows >= rb belong to sample b0 + 1
+            const int rows = P.M - q0 < 32 ? P.M - q0 : 32;
             auto finish = [&](uint32_t (&r)[32], int cb) {
-                    const int nb = n0 + cb;
-                    // statistics: the 32 rows of a warp belong to one sample (host checks H*W % 32 == 0)
-                    const int q0 = m0 + quarter * 32;
-                    const bool wvalid = q0 < P.M;
-                    const int bw = wvalid ? q0 / (P.W * P.H) : 0;
-                    float sv[64];     // [0, 32): final values of this row's 32 channels, [32, 64): their squares (0 for invalid rows)
-    #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const int n = nb + j;
-                        float v[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (valid && n < P.Cout) {
-    #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                v[e] = __uint_as_float(r[j + e]);
-                                if (P.bias) v[e] += P.bias[n + e];
-                                if (P.emb) v[e] += P.emb[(size_t)b * P.emb_stride + n + e];
-                            }
-                            if (P.res_mode == 1) {
-                                const float4 t = *reinterpret_cast<const float4*>(P.res + (size_t)q * P.Cout + n);
-                                v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
-                            } else if (P.res_mode == 2) {
-                                const int H2 = P.H * 2, W2 = P.W * 2;
-                                const float* rb = P.res + (((size_t)b * H2 + 2 * h) * W2 + 2 * w) * P.Cout + n;
-                                const float4 r0 = *reinterpret_cast<const float4*>(rb);
-                                const float4 r1 = *reinterpret_cast<const float4*>(rb + P.Cout);
-                                const float4 r2 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout);
-                                const float4 r3 = *reinterpret_cast<const float4*>(rb + (size_t)W2 * P.Cout + P.Cout);
-                                v[0] += (r0.x + r1.x + r2.x + r3.x) * 0.25f;
-                                v[1] += (r0.y + r1.y + r2.y + r3.y) * 0.25f;
-                                v[2] += (r0.z + r1.z + r2.z + r3.z) * 0.25f;
-                                v[3] += (r0.w + r1.w + r2.w + r3.w) * 0.25f;
-                            } else if (P.res_mode == 3) {
-                                const int Hh = P.H / 2, Wh = P.W / 2;
-                                const float4 t = *reinterpret_cast<const float4*>(
-                                    P.res + (((size_t)b * Hh + (h >> 1)) * Wh + (w >> 1)) * P.Cout + n);
-                                v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
-                            }
-                            *reinterpret_cast<float4*>(P.out + (size_t)q * P.Cout + n) = make_float4(v[0], v[1], v[2], v[3]);
-                        }
-    #pragma unroll
-                        for (int e = 0; e < 4; ++e) { sv[j + e] = v[e]; sv[32 + j + e] = v[e] * v[e]; }
+                const int n = n0 + cb + lane;
+                const bool cvalid = n < P.Cout;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = __uint_as_float(r[j]);
+                __syncwarp();
+                float add0 = 0.f, add1 = 0.f;
+                if (cvalid) {
+                    if (P.bias) add0 = add1 = P.bias[n];
+                    if (P.emb) {
+                        add0 += P.emb[(size_t)b0 * P.emb_stride + n];
+                        if (rb < rows) add1 += P.emb[(size_t)(b0 + 1) * P.emb_stride + n];
                     }
-                    if (P.gn_stats) {   // warp-uniform
-                        // column sums over the warp's 32 rows by a reduce-scatter butterfly (62 shuffles for 64 values): each
-                        // step halves the values a lane keeps; lane L ends with entries 2L, 2L+1 (L < 16: sums of channels
-                        // 2L, 2L+1; L >= 16: their sums of squares)
-    #pragma unroll
-                        for (int half = 32, o = 16; half >= 2; half >>= 1, o >>= 1) {
-                            const bool up = (lane & o) != 0;
-    #pragma unroll
-                            for (int i = 0; i < half; ++i) {
-                                const float send = up ? sv[i] : sv[i + half];
-                                const float keep = up ? sv[i + half] : sv[i];
-                                sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+                float s1 = 0.f, s2 = 0.f;
+                if (cvalid) {
+                    // residual values of the 32 rows first: 32 independent loads in flight instead of one latency per row
+                    float rv[32];
+                    if (P.res_mode == 1) {
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr) rv[rr] = rr < rows ? __ldg(P.res + (size_t)(q0 + rr) * P.Cout + n) : 0.f;
+                    } else if (P.res_mode == 2 || P.res_mode == 3) {
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr) {
+                            float t = 0.f;
+                            if (rr < rows) {
+                                const int br = rr < rb ? b0 : b0 + 1;
+                                const int pix = q0 + rr - br * HW, hr = pix / P.W, wr = pix - hr * P.W;
+                                if (P.res_mode == 2) {
+                                    const int H2 = P.H * 2, W2 = P.W * 2;
+                                    const float* rp = P.res + (((size_t)br * H2 + 2 * hr) * W2 + 2 * wr) * P.Cout + n;
+                                    t = (rp[0] + rp[P.Cout] + rp[(size_t)W2 * P.Cout] + rp[(size_t)W2 * P.Cout + P.Cout]) * 0.25f;
+                                } else {
+                                    const int Hh = P.H / 2, Wh = P.W / 2;
+                                    t = P.res[(((size_t)br * Hh + (hr >> 1)) * Wh + (wr >> 1)) * P.Cout + n];
+                                }
                             }
+                            rv[rr] = t;
                         }
-                        const int ch = nb + 2 * (lane & 15);
-                        if (wvalid && ch < P.Cout) {
-                            double* st = P.gn_stats + (size_t)(cluster_id % ANODDPM_STAT_REPLICAS) * P.stat_replica_stride +
-                                         ((size_t)bw * P.Cout + ch) * 2 + (lane >> 4);
-                            atomicAdd(st, (double)sv[0]);
-                            atomicAdd(st + 2, (double)sv[1]);
+                    } else {
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr) rv[rr] = 0.f;
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 32; ++rr) {
+                        if (rr < rows) {
+                            const float v = (tbuf[rr * 33 + lane] + (rr < rb ? add0 : add1)) + rv[rr];
+                            P.out[(size_t)(q0 + rr) * P.Cout + n] = v;
+                            s1 += v;
+                            s2 += v * v;
                         }
                     }
+                    if (P.gn_stats && wvalid) {   // the 32 rows of a warp belong to one sample (host checks H*W % 32 == 0)
+                        double* st = P.gn_stats + (size_t)(cluster_id % ANODDPM_STAT_REPLICAS) * P.stat_replica_stride +
+                                     ((size_t)b0 * P.Cout + n) * 2;
+                        atomicAdd(st, (double)s1);
+                        atomicAdd(st + 1, (double)s2);
+                    }
+                }
+                __syncwarp();      // the tile is rewritten by the next chunk
             };
             auto load_acc = [&](uint32_t (&r)[32], int cb) {
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * P.BN + cb);
@@ -555,7 +560,7 @@ int anoddpm_conv_tc2(const anoddpm_conv_desc* d, void* stream) {
     P.tmem_cols = acc_cols <= 32 ? 32 : acc_cols <= 64 ? 64 : acc_cols <= 128 ? 128 : acc_cols <= 256 ? 256 : 512;
     const int Ktot = (P.nkb_a + P.nkb_r1 + P.nkb_r2) * P.ke;
     const int b_bytes = (P.BN / 2) * kRowBytes;
-    int stages = (196 * 1024) / (kABytes + b_bytes);
+    int stages = (192 * 1024) / (kABytes + b_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     P.stages = stages;
     P.n_tiles_n = adp_ceil_div(d->Cout, P.BN);
@@ -579,7 +584,7 @@ int anoddpm_conv_tc2(const anoddpm_conv_desc* d, void* stream) {
     if (d->r2 && (rc = make_act_map2(&m2, d->r2, f16, d->Cr2, d->W, d->H, d->B, TW, TH, TB))) return rc;
     if ((rc = make_w_map2(&mw, d->w, f16, Ktot, d->Cout, P.BN / 2))) return rc;
 
-    const size_t smem = (size_t)stages * (kABytes + b_bytes) + (2 * kMaxStages + 2 * kAccStages) * 8 + 16 + 1024;
+    const size_t smem = (size_t)stages * (kABytes + b_bytes) + (2 * kMaxStages + 2 * kAccStages) * 8 + 16 + kEpiTileBytes + 1024;
     static bool attr_dev[64] = {};   // the attribute is per device
     int dev_ = 0;
     ADP_CUDA(cudaGetDevice(&dev_));

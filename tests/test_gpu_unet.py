@@ -608,8 +608,8 @@ def test_fused_adamw_ema_step_matches_torch_sequence():
     assert bool(torch.isfinite(y).all())
 
 
-@pytest.mark.parametrize("case", [dict(B=32, H=8, W=8, Ca=512, Cout=512, ks=3), dict(B=32, H=8, W=8, Ca=1024, Cout=512, ks=3),
-                                  dict(B=4, H=8, W=8, Ca=256, Cout=256, ks=3), dict(B=8, H=8, W=8, Ca=512, Cout=384, ks=3)])
+@pytest.mark.parametrize("case", [dict(B=32, H=8, W=8, Ca=512, Cout=512, ks=3, split=False), dict(B=2, H=8, W=8, Ca=1024, Cout=512, ks=3, split=True),
+                                  dict(B=4, H=8, W=8, Ca=256, Cout=256, ks=3, split=True), dict(B=8, H=8, W=8, Ca=512, Cout=384, ks=3, split=True)])
 def test_conv_tc2_split_k_matches_unsplit_and_torch(case):
     """impl 2 on small maps with a workspace (K loop split over CTA pairs, last arriver reduces + finishes the tile) against
     the same kernel without a workspace and against torch fp64 on the same fp16-rounded operands; epilogue extras (embedding
@@ -638,14 +638,15 @@ def test_conv_tc2_split_k_matches_unsplit_and_torch(case):
         d.gn_stats = st.data_ptr()
         need = _lib.lib().anoddpm_conv_workspace_bytes(ctypes.byref(d))
         if ws is not None:
-            assert need > 0 and ws.numel() >= need
+            assert ws.numel() >= need
             d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
         _lib.call("anoddpm_conv", ctypes.byref(d), _lib.stream())
         torch.cuda.synchronize()
         return out, st.view(REPL, B, Cout, 2).sum(0), need
 
     base, st0, need = run(None)
-    ws = torch.zeros(need, device=DEV, dtype=torch.uint8)
+    assert (need > 0) == case["split"]      # bs 32 fills the machine with narrow tiles (tc2_pick_bn): nothing to split
+    ws = torch.zeros(max(need, 16), device=DEV, dtype=torch.uint8)
     o1, st1, _ = run(ws)
     o2, st2, _ = run(ws)          # second launch on the same workspace: counters were reset by the kernel
     ref = F.conv2d(an.permute(0, 3, 1, 2).double(), wp.view(Cout, 3, 3, Ca).permute(0, 3, 1, 2).double(), bias.double(), padding=1)
