@@ -811,13 +811,21 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         uint8_t* stg16 = stg16_all + ew * (2 * kStg16Buf);
         uint64_t* rbar = res_bar + ew * 3;
         const uint32_t res_bytes = P.res_mode == 3 ? 8u * 64u : (uint32_t)kStgBuf;
-        auto issue_res = [&](int tile, int cb, int buf) {
-            int b, ybase, xbase, n0;
-            if (!tile_region(tile, b, ybase, xbase, n0)) return;
+        // region of the current tile and of the next one, computed ONCE per tile: the per-step residual fetch below used to
+        // re-derive them (three integer divisions by run-time values per step, 13 % of the kernel's stall samples)
+        struct Reg { int b, y, x, n0; bool ok; };
+        auto region_of = [&](int tile) {
+            Reg g;
+            g.ok = tile_region(tile, g.b, g.y, g.x, g.n0);
+            return g;
+        };
+        Reg cur = region_of(tile_first), nxt = cur;
+        auto issue_res = [&](const Reg& g, int cb, int buf) {
+            if (!g.ok) return;
             mbar_expect_tx(&rbar[buf], res_bytes);
-            const int y = ybase + 4 * quarter, x = xbase + 8 * sub;
-            if (P.res_mode == 3) tma_load_4d(stg + buf * kStgBuf, &map_res, &rbar[buf], n0 + cb, x >> 1, y >> 1, b);
-            else tma_load_4d(stg + buf * kStgBuf, &map_res, &rbar[buf], n0 + cb, x, y, b);
+            const int y = g.y + 4 * quarter, x = g.x + 8 * sub;
+            if (P.res_mode == 3) tma_load_4d(stg + buf * kStgBuf, &map_res, &rbar[buf], g.n0 + cb, x >> 1, y >> 1, g.b);
+            else tma_load_4d(stg + buf * kStgBuf, &map_res, &rbar[buf], g.n0 + cb, x, y, g.b);
         };
         // L2 prefetch of a tile's residual boxes (lane = channel step): the TMA load of a step then pays L2, not HBM, latency
         auto prefetch_res = [&](int tile, int first_step) {
@@ -828,8 +836,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             else tma_prefetch_4d(&map_res, n0 + lane * 16, x, y, b);
         };
         if (has_res && lane == 0) {
-            issue_res(tile_first, 0, 0);
-            issue_res(tile_first, 16, 1);
+            issue_res(cur, 0, 0);
+            issue_res(cur, 16, 1);
         }
         if (has_res && P.res_pf) prefetch_res(tile_first, 2);
         int buf = 0;
@@ -855,8 +863,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         int it = 0, step = 0;
         for (int tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
             const int acc = it & 1;
-            int b, ybase, xbase, n0;
-            const bool valid = tile_region(tile, b, ybase, xbase, n0);
+            if (tile != tile_first) cur = nxt;
+            nxt = region_of(tile + tile_step);
+            const int b = cur.b, ybase = cur.y, xbase = cur.x, n0 = cur.n0;
+            const bool valid = cur.ok;
             if (has_res && P.res_pf) prefetch_res(tile + tile_step, 0);
             if (P.gn_stats && valid) {
                 if (b != cur_b || n0 != cur_n0 || kept == 8) {   // bounded fp32 chains: at most 8 tiles per flush
@@ -972,8 +982,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         const int nb = NB == 3 ? (buf == 0 ? 2 : buf - 1) : buf;
                         if (NB == 3) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                         else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        if (cb + 32 < P.BN) issue_res(tile, cb + 32, nb);
-                        else issue_res(tile + tile_step, cb + 32 - P.BN, nb);
+                        if (cb + 32 < P.BN) issue_res(cur, cb + 32, nb);
+                        else issue_res(nxt, cb + 32 - P.BN, nb);
                     }
                     buf = buf + 1 == NB ? 0 : buf + 1;
                 } else {
