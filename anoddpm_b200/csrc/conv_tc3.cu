@@ -128,6 +128,10 @@ __device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32
         "r"(cta)
         : "memory");
 }
+// arrive on a barrier of this CTA (release at CTA scope)
+__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -287,7 +291,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint64_t* a_full = res_bar + 3 * kEpiWarps;    // [2]   single-box main loop: A box landed (leader only)
     uint64_t* a_empty = a_full + kNAMax;           // [3]   both CTAs (multicast commit)
     uint64_t* a_land = a_empty + kNAMax;           // [3]   GN: this CTA's raw A box landed (per CTA)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_land + kNAMax);
+    uint64_t* t_done = a_land + kNAMax;            // [3]   GN: this CTA's transform warps are done with the box (per CTA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_done + kNAMax);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
@@ -318,8 +323,10 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int i = 0; i < S; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
         for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * 32 * kEpiWarps); }
         for (int i = 0; i < 3 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
-        // GN: a_full collects one arrival per transform warp of both CTAs (4 + 4) instead of the two producers
-        for (int i = 0; i < kNAMax; ++i) { mbar_init(&a_full[i], GN ? 2 * kTransformWarps : 2); mbar_init(&a_empty[i], 1); mbar_init(&a_land[i], 1); }
+        // GN: a_full collects one arrival per CTA (the relay warp, once its CTA's transform warps are done with the box)
+        for (int i = 0; i < kNAMax; ++i) {
+            mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); mbar_init(&a_land[i], 1); mbar_init(&t_done[i], kTransformWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -651,9 +658,25 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             if (ok[u] && P.dbg != 2) sts128u(addr[u], v[u]);      // rows outside the image keep TMA's zero fill
                     }
                 }
+                // done with the box: a cheap CTA-local arrive; the relay warp (warp 3) turns the eight of them into ONE cluster-scope
+                // release on the leader's a_full.  (Each transform warp used to do that release itself and sat ~10 % of its
+                // samples in it -- profiles/r02b_ncu_conv_tc3_conv2.md.)
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive_remote_release(&a_full[ab], 0);
+                if (lane == 0) mbar_arrive_local(&t_done[ab]);
+            }
+        }
+    } else if (GN && warp == 3) {
+        // ---------------- relay (both CTAs): transform warps done -> release the box to the MMA issuer ----------------
+        if (lane == 0) {
+            const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
+            int ac = 0;
+            for (int tile = tile_first; tile < tile_end; tile += tile_step) {
+                for (int c = 0; c < nchunks; ++c, ++ac) {
+                    const int ab = ac % P.na;
+                    mbar_wait(&t_done[ab], (ac / P.na) & 1);
+                    mbar_arrive_remote_release(&a_full[ab], 0);
+                }
             }
         }
     } else if (warp >= 4 && warp < 12) {

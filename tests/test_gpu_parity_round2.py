@@ -482,3 +482,25 @@ def test_separable_head_vs_torch(shape):
     e_old = float((out - old).abs().max() / ref.abs().max())
     print(f"separable head {shape}: vs torch {e_ref:.2e}, vs conv_head_gn {e_old:.2e}")
     assert e_ref < 5e-6 and e_old < 5e-6        # fp32 both ways: summation order + __expf only (measured ~1e-6)
+
+
+def test_graph_loop_switches_leave_the_chain_unchanged(monkeypatch):
+    """The captured reverse step with its optional pieces toggled (per-timestep embedding table, noise field on a forked
+    stream) must produce the chain of the plain configuration: the table rows are bit-identical to the per-step
+    computation and the noise kernel does not depend on where it runs."""
+    from anoddpm_b200 import GaussianDiffusionModel, get_beta_schedule
+    m = build_model(dict(img_size=64, base_channels=64, n_heads=2, attention_resolutions="16,8"), "tc")
+    x0 = (torch.rand(2, 1, 64, 64, generator=torch.Generator().manual_seed(3)) * 2 - 1).to(DEV)
+    outs = {}
+    for name, env in (("plain", {"ANODDPM_TIME_TABLE": "0", "ANODDPM_NOISE_OVERLAP": "0"}),
+                      ("table", {"ANODDPM_TIME_TABLE": "1", "ANODDPM_NOISE_OVERLAP": "0"}),
+                      ("table+overlap", {"ANODDPM_TIME_TABLE": "1", "ANODDPM_NOISE_OVERLAP": "1"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        diff = GaussianDiffusionModel([64, 64], get_beta_schedule(1000, "linear"), noise="simplex")
+        diff.simplex_seed_source = lambda step, n: [1000 + 17 * step + i for i in range(n)]
+        with torch.no_grad():
+            outs[name] = diff.reverse_steps(m, x0.clone(), 40, 6, "simplex")
+    assert torch.isfinite(outs["plain"]).all()
+    assert torch.equal(outs["plain"], outs["table"])
+    assert torch.equal(outs["plain"], outs["table+overlap"])
