@@ -179,6 +179,11 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
     return v;
 }
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sts128(uint32_t a, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -698,7 +703,6 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             n0 = nt * P.BN;
             return tile < tile_end && R < P.n_regions;
         };
-        const int cc = (lane & 3) * 4;      // channel quad of the column pass
         if constexpr (OUT16) {
             // ---- fp16 output: the convolution sum only (no bias / embedding, no residual), statistics of sum + bias + emb.
             // Steps of (32 pixels x 32 channels): 64-byte fp16 rows in the same SWIZZLE_64B buffers.
@@ -865,21 +869,26 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (has_res && P.res_pf) prefetch_res(tile_first, 2);
         int buf = 0;
         uint32_t phases = 0;
-        // per-channel statistics: lane (g = lane >> 2, q = lane & 3) keeps the running sums of channels 16 g + 4 q .. + 3
-        // of the current (sample, channel tile) in registers and flushes them with fp64 atomics when either changes
+        // per-channel statistics: lane (c = lane & 15, hf = lane >> 4) owns channel c of every 16-channel step; it keeps the
+        // running sums of steps 4 hf .. 4 hf + 3 (channels 16 (4 hf + k) + c) of the current (sample, channel tile) in registers
+        // and flushes them with fp64 atomics when either changes
+        const int sc_c = lane & 15, sc_h = lane >> 4;
         float keep1[4] = {0.f, 0.f, 0.f, 0.f}, keep2[4] = {0.f, 0.f, 0.f, 0.f};
         int cur_b = -1, cur_n0 = 0, kept = 0;
         auto flush_stats = [&]() {
-            if (cur_b >= 0 && 16 * (lane >> 2) < P.BN) {
+            if (cur_b >= 0) {
                 // replica = cluster id mod 8 spreads the CTAs that work on the same image over 8x more addresses
                 double* st = P.gn_stats + (size_t)(cluster_id % ANODDPM_STAT_REPLICAS) * P.stat_replica_stride +
-                             ((size_t)cur_b * P.Cout + cur_n0 + 16 * (lane >> 2) + cc) * 2;
+                             ((size_t)cur_b * P.Cout + cur_n0) * 2;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    atomicAdd(st + 2 * e, (double)keep1[e]);
-                    atomicAdd(st + 2 * e + 1, (double)keep2[e]);
-                    keep1[e] = 0.f;
-                    keep2[e] = 0.f;
+                for (int k = 0; k < 4; ++k) {
+                    const int ch = 16 * (4 * sc_h + k) + sc_c;
+                    if (ch < P.BN) {
+                        atomicAdd(st + 2 * ch, (double)keep1[k]);
+                        atomicAdd(st + 2 * ch + 1, (double)keep2[k]);
+                    }
+                    keep1[k] = 0.f;
+                    keep2[k] = 0.f;
                 }
             }
         };
@@ -973,28 +982,26 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         tma_store_4d(&map_out16, stg16 + (step & 1) * kStg16Buf, n0 + cb, xbase + 8 * sub, ybase + 4 * quarter, b);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                // 3. column pass: lane owns channels cc..cc+3 of rows (lane >> 2) + 8k -> per-channel statistics
+                // 3. column pass: lane owns channel sc_c; the two half-warps read alternate rows (16 conflict-free scalar loads each,
+                //    no shuffles but the final exchange between the halves) -> per-channel statistics
                 if (P.gn_stats) {   // warp-uniform; all pixels of the CTA's region belong to sample b
-                    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+                    float s1 = 0.f, s2 = 0.f;
+                    const uint32_t cbase = sba + (uint32_t)sc_h * 64 + (uint32_t)(sc_c & 3) * 4;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {     // row 2 i + sc_h; its 16-byte chunk q sits at q ^ (i & 3)
+                        const float t = lds32(cbase + (uint32_t)i * 128 + (uint32_t)(((sc_c >> 2) ^ (i & 3)) << 4));
+                        s1 += t;
+                        s2 = fmaf(t, t, s2);
+                    }
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+                    const int sti = cb >> 4;
+                    const bool mine = (sti >> 2) == sc_h;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const int row = 8 * k + (lane >> 2);
-                        const float4 t4 = lds128(sba + row * 64 + (((lane & 3) ^ ((row >> 1) & 3)) << 4));
-                        s1[0] += t4.x; s1[1] += t4.y; s1[2] += t4.z; s1[3] += t4.w;
-                        s2[0] += t4.x * t4.x; s2[1] += t4.y * t4.y; s2[2] += t4.z * t4.z; s2[3] += t4.w * t4.w;
-                    }
-                    // lanes with equal (lane & 3) hold the same 4 channels for different pixel rows
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-#pragma unroll
-                        for (int o = 4; o < 32; o <<= 1) {
-                            s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
-                            s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
-                        }
-                    }
-                    if ((lane >> 2) == (cb >> 4)) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) { keep1[e] += s1[e]; keep2[e] += s2[e]; }
+                        const bool sel = mine && (sti & 3) == k;
+                        keep1[k] += sel ? s1 : 0.f;
+                        keep2[k] += sel ? s2 : 0.f;
                     }
                 }
                 if (has_res) {
