@@ -270,7 +270,7 @@ __device__ __forceinline__ uint64_t make_sdesc_sbo(uint32_t saddr, uint32_t sbo)
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
-template <bool F16, bool OUT16, bool GN>
+template <bool F16, bool OUT16, bool GN, bool T12 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GN ? kThreadsGN : kThreads, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                 const __grid_constant__ CUtensorMap map_r1,
@@ -300,6 +300,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_done + kNAMax);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 relay (GN), then kE epilogue warps, then kT transform warps.
+    // The conv1 form (GN + fp16 output) has a light epilogue and a transform-bound main loop: 4 epilogue warps (each drains
+    // both subtiles of its TMEM lane quarter) leave room for 12 transform warps in the same 640 threads.
+    constexpr int kE = T12 ? 4 : kEpiWarps;
+    constexpr int kT = T12 ? 12 : kTransformWarps;
+    static_assert(!T12 || (GN && OUT16), "12 transform warps: conv1 form only");
     const uint32_t rank = cluster_rank();
     const bool leader = rank == 0;
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
@@ -326,11 +332,11 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < S; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * 32 * kEpiWarps); }
+        for (int i = 0; i < kAccStages; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * 32 * kE); }
         for (int i = 0; i < 3 * kEpiWarps; ++i) mbar_init(&res_bar[i], 1);
         // GN: a_full collects one arrival per CTA (the relay warp, once its CTA's transform warps are done with the box)
         for (int i = 0; i < kNAMax; ++i) {
-            mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); mbar_init(&a_land[i], 1); mbar_init(&t_done[i], kTransformWarps);
+            mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); mbar_init(&a_land[i], 1); mbar_init(&t_done[i], kT);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -595,14 +601,14 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
             }
         }
-    } else if (GN && warp >= 12) {
+    } else if (GN && warp >= 4 + kE) {
         // ---------------- operand transform (both CTAs): GroupNorm + SiLU on the landed raw box, in place ----------------
         // thread = (16-byte chunk j = channels 8j..8j+7 of the K-block, row lane rl); box row r = pixel (r / 18, r % 18) of
         // the 18x18 halo region sits at r * 128 B, its chunk j at j ^ (r & 7) (SWIZZLE_128B on a 1024-byte aligned buffer).
         // Pixels outside the image keep TMA's zero fill: the convolution pads AFTER normalisation + activation.
-        const int tid = (warp - 12) * 32 + lane;
+        const int tid = (warp - (4 + kE)) * 32 + lane;
         const int j = tid & 7, rl = tid >> 3;
-        constexpr int kRowLanes = kTransformWarps * 4;                  // 32 box rows per sweep of the transform warps
+        constexpr int kRowLanes = kT * 4;                               // box rows per sweep of the transform warps (32 or 48)
         constexpr int kSweeps = (18 * 18 + kRowLanes - 1) / kRowLanes;  // 11
         constexpr int kU = 4;                                           // rows in flight per thread (the loop is latency-bound)
         const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
@@ -684,7 +690,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
             }
         }
-    } else if (warp >= 4 && warp < 12) {
+    } else if (warp >= 4 && warp < 4 + kE) {
         // ---------------- epilogue (both CTAs) ----------------
         const int ew = warp - 4;            // 0..7
         const int quarter = warp & 3;       // TMEM lanes 32*quarter.. : image rows 4*quarter..+3 of the subtile
@@ -754,10 +760,14 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
                 mbar_wait(&tmem_full[acc], (it >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // with four epilogue warps (GN variant) each warp drains both subtiles of its TMEM lane quarter
+#pragma unroll 1
+                for (int sb = 0; sb < (kE == 4 ? 2 : 1); ++sb) {
+                const int sub_ = kE == 4 ? sb : sub;
 #pragma unroll 1
                 for (int cb = 0; cb < P.BN; cb += 32) {
                     uint32_t r[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * 2 + sub) * P.BN + cb);
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * 2 + sub_) * P.BN + cb);
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -769,7 +779,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                           "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                         : "r"(taddr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (cb + 32 >= P.BN) {
+                    if (cb + 32 >= P.BN && (kE != 4 || sb == 1)) {
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         mbar_arrive_remote(&tmem_empty[acc], 0);
                     }
@@ -791,7 +801,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_4d(&map_out, stg + buf * kStgBuf, n0 + cb, xbase + 8 * sub, ybase + 4 * quarter, b);
+                        tma_store_4d(&map_out, stg + buf * kStgBuf, n0 + cb, xbase + 8 * sub_, ybase + 4 * quarter, b);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     if (P.gn_stats) {
@@ -828,6 +838,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         }
                     }
                     ++step;
+                }
                 }
             }
             if (P.gn_stats) flush_stats();
@@ -1228,6 +1239,7 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
         ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        ADP_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_dev[dev_ & 63] = true;
     }
     const int sms = 148;
@@ -1235,7 +1247,10 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     const dim3 grid(2 * n_clusters);
     cudaStream_t st = (cudaStream_t)stream;
     if (gn) {
-        if (d->out_f16) conv_tc3_kernel<true, true, true><<<grid, kThreadsGN, smem, st>>>(ma, ma2, m1, m2, mw, mres, mout, mout16, P);
+        // conv1 form: 4 epilogue + 12 transform warps (ANODDPM_TC3_T12=0: 8 + 8)
+        static const int t12 = [] { const char* e = getenv("ANODDPM_TC3_T12"); return e ? atoi(e) : 1; }();
+        if (d->out_f16 && t12) conv_tc3_kernel<true, true, true, true><<<grid, kThreadsGN, smem, st>>>(ma, ma2, m1, m2, mw, mres, mout, mout16, P);
+        else if (d->out_f16) conv_tc3_kernel<true, true, true><<<grid, kThreadsGN, smem, st>>>(ma, ma2, m1, m2, mw, mres, mout, mout16, P);
         else conv_tc3_kernel<true, false, true><<<grid, kThreadsGN, smem, st>>>(ma, ma2, m1, m2, mw, mres, mout, mout16, P);
     } else if (d->out_f16) {
         if (f16) conv_tc3_kernel<true, true, false><<<grid, kThreads, smem, st>>>(ma, ma2, m1, m2, mw, mres, mout, mout16, P);
