@@ -359,7 +359,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             // leader's a_full); weight stages as in the single-box loop
             if (elected) {
                 int bc = 0, ac = 0;
-                const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
+                const int nchunks = T12 ? P.chunks_a : P.chunks_a + P.chunks_r1 + P.chunks_r2;   // T12: no skip sources (host)
                 // optional L2 prefetch cursor (ANODDPM_TC3_APF=n): the raw box of the chunk n positions ahead of the one being
                 // loaded.  Off by default: neutral for conv1 forms, and in the conv2 forms (residual / two-store epilogue
                 // competing for L2) the prefetched lines were re-fetched -- DRAM reads 2.15 GB instead of 1.68 GB, 2.5 % slower
@@ -410,9 +410,12 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             const bool first = cs < P.chunks_r1;
                             const CUtensorMap* am = first ? &map_r1 : &map_r2;
                             const int c0 = (first ? cs : cs - P.chunks_r1) * P.ke;
-                            mbar_expect_tx(&a_land[ab], 2u * (16 * 8 * kRowBytes));
-                            tma_load_4d(a_dst, am, &a_land[ab], c0, x0, y0, b0);
-                            tma_load_4d(a_dst + 16 * 8 * kRowBytes, am, &a_land[ab], c0, x0 + 8, y0, b0);
+                            // raw skip boxes need no transform: they signal the leader's a_full directly (one expect_tx arrival
+                            // from the leader + one plain arrival from the peer = the two arrivals a relayed box delivers)
+                            if (leader) mbar_expect_tx(&a_full[ab], 2u * 2u * (16 * 8 * kRowBytes));
+                            else mbar_arrive_remote(&a_full[ab], 0);
+                            tma2_load_4d(a_dst, am, &a_full[ab], c0, x0, y0, b0);
+                            tma2_load_4d(a_dst + 16 * 8 * kRowBytes, am, &a_full[ab], c0, x0 + 8, y0, b0);
                             const int s = bc % S;
                             mbar_wait(&empty[s], ((bc / S) & 1) ^ 1);
                             if (leader) mbar_expect_tx(&full[s], 2u * (uint32_t)b_bytes);
@@ -432,7 +435,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const int b0 = R / P.regions_per_img, rr = R - b0 * P.regions_per_img;
                 const int y0 = (rr / P.regions_x) * 16, x0 = (rr % P.regions_x) * 16;
                 const int n0 = nt * P.BN + (int)rank * (P.BN / 2);
-                const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
+                const int nchunks = T12 ? P.chunks_a : P.chunks_a + P.chunks_r1 + P.chunks_r2;   // T12: no skip sources (host)
                 for (int c = 0; c < nchunks; ++c, ++ac) {
                     const int ab = ac % P.na;
                     uint8_t* a_dst = sA + ab * kBoxStride;
@@ -516,7 +519,7 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             int kbc = 0, it = 0;
             if (P.single_box) {
                 int bc = 0, ac = 0;
-                const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
+                const int nchunks = T12 ? P.chunks_a : P.chunks_a + P.chunks_r1 + P.chunks_r2;   // T12: no skip sources (host)
                 for (int tile = tile_first; tile < tile_end; tile += tile_step, ++it) {
                     const int acc = it & 1;
                     mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
@@ -611,8 +614,9 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         constexpr int kRowLanes = kT * 4;                               // box rows per sweep of the transform warps (32 or 48)
         constexpr int kSweeps = (18 * 18 + kRowLanes - 1) / kRowLanes;  // 11
         constexpr int kU = 4;                                           // rows in flight per thread (the loop is latency-bound)
-        const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
+        const int nchunks = T12 ? P.chunks_a : P.chunks_a + P.chunks_r1 + P.chunks_r2;   // T12: no skip sources (host)
         int ac = 0;
+        uint32_t land_ph = 0;      // phase bit per A slot: a_land / t_done complete once per MAIN chunk that uses the slot
         for (int tile = tile_first; tile < tile_end; tile += tile_step) {
             const int pair = tile / P.n_tiles_n;
             const int R = pair * 2 + (int)rank;
@@ -620,15 +624,17 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int y0 = (rr / P.regions_x) * 16, x0 = (rr % P.regions_x) * 16;
             const bool live = R < P.n_regions;
             for (int c = 0; c < nchunks; ++c, ++ac) {
+                if (c >= P.chunks_a) continue;      // skip-conv boxes go straight to the MMA issuer
                 const int ab = ac % P.na;
-                const bool work = live && c < P.chunks_a && P.dbg != 1;
+                const bool work = live && P.dbg != 1;
                 float4 t4[4];
                 if (work) {   // table row of this thread's 8 channels: issued before the wait, it does not depend on the box
                     const float4* tp = reinterpret_cast<const float4*>(P.gn_table + (size_t)b0 * P.c_tab + c * 64 + 8 * j);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) t4[q] = __ldg(tp + q);
                 }
-                mbar_wait(&a_land[ab], (ac / P.na) & 1);
+                mbar_wait(&a_land[ab], (land_ph >> ab) & 1);
+                land_ph ^= 1u << ab;
                 if (work) {
                     const uint32_t a_base = smem_u32(sA + ab * kBoxStride);
                     // y = v * sc + sh;  SiLU(y) = y / (1 + 2^(v * nsc + nsh)) with (nsc, nsh) = -log2(e) * (sc, sh)
@@ -680,12 +686,15 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     } else if (GN && warp == 3) {
         // ---------------- relay (both CTAs): transform warps done -> release the box to the MMA issuer ----------------
         if (lane == 0) {
-            const int nchunks = P.chunks_a + P.chunks_r1 + P.chunks_r2;
+            const int nchunks = T12 ? P.chunks_a : P.chunks_a + P.chunks_r1 + P.chunks_r2;   // T12: no skip sources (host)
             int ac = 0;
+            uint32_t done_ph = 0;
             for (int tile = tile_first; tile < tile_end; tile += tile_step) {
                 for (int c = 0; c < nchunks; ++c, ++ac) {
+                    if (c >= P.chunks_a) continue;
                     const int ab = ac % P.na;
-                    mbar_wait(&t_done[ab], (ac / P.na) & 1);
+                    mbar_wait(&t_done[ab], (done_ph >> ab) & 1);
+                    done_ph ^= 1u << ab;
                     mbar_arrive_remote_release(&a_full[ab], 0);
                 }
             }
@@ -1249,7 +1258,7 @@ int anoddpm_conv_tc3(const anoddpm_conv_desc* d, void* stream) {
     if (gn) {
         // conv1 form: 4 epilogue + 12 transform warps (ANODDPM_TC3_T12=0: 8 + 8)
         static const int t12 = [] { const char* e = getenv("ANODDPM_TC3_T12"); return e ? atoi(e) : 1; }();
-        if (d->out_f16 && t12) conv_tc3_kernel<true, true, true, true><<<grid, kThreadsGN, smem, st>>>(ma, ma2, m1, m2, mw, mres, mout, mout16, P);
+        if (d->out_f16 && t12 && d->Cr1 + d->Cr2 == 0) conv_tc3_kernel<true, true, true, true><<<grid, kThreadsGN, smem, st>>>(ma, ma2, m1, m2, mw, mres, mout, mout16, P);
         else if (d->out_f16) conv_tc3_kernel<true, true, true><<<grid, kThreadsGN, smem, st>>>(ma, ma2, m1, m2, mw, mres, mout, mout16, P);
         else conv_tc3_kernel<true, false, true><<<grid, kThreadsGN, smem, st>>>(ma, ma2, m1, m2, mw, mres, mout, mout16, P);
     } else if (d->out_f16) {
