@@ -28,6 +28,10 @@ def launches(path):
     ps = [i for i, n in enumerate(names) if n.startswith("p_sample")]
     if len(ps) >= 2:
         a, b = ps[0] + 1, ps[1] + 1
+        for i, j in zip(ps[:-1], ps[1:]):      # prefer a window without the chain's q_sample (+ its own noise launch)
+            if not any(n.startswith("q_sample") for n in names[i + 1:j + 1]):
+                a, b = i + 1, j + 1
+                break
         title = f"one reverse step (launches {a}..{b} of the capture, p_sample to p_sample)"
     else:
         a, b = 0, len(rows)
