@@ -173,3 +173,31 @@ def test_support_predicates_and_argument_checks_without_gpu():
     assert L.anoddpm_vlb_terms(None, None, None, None, None, None, None, None, 10, 1, 16, None) < 0
     assert L.anoddpm_conv_head_gn(res, res, res, res, res, res, None, 1, 1024, 8, 8, 1, 32, 1e-5, None) < 0
     assert b"at most" in L.anoddpm_last_error()
+
+
+def test_round2_planning_entry_points_host_only():
+    """Host-side planners added in round 2 (no GPU): separable-head support / workspace, split-K workspace of the small-map
+    conv kernel (follows the pair-tile planner: bs 32 fills the machine with narrow tiles, tiny batches split K), argument
+    errors of the new entry points."""
+    import ctypes
+    from anoddpm_b200 import _lib
+    from anoddpm_b200._lib import ConvDesc
+    L = _lib.lib()
+    assert L.anoddpm_conv_head_sep_supported(128, 1) == 1 and L.anoddpm_conv_head_sep_supported(256, 1) == 1
+    assert L.anoddpm_conv_head_sep_supported(128, 2) == 0 and L.anoddpm_conv_head_sep_supported(192, 1) == 0
+    assert L.anoddpm_conv_head_sep_workspace_bytes(32, 256, 256) == 9 * 32 * 256 * 256 * 4
+
+    def desc(B, H, W, Ca, Cout, ks=3, impl=2):
+        d = ConvDesc()
+        d.B, d.H, d.W, d.Ca, d.Cout, d.ksize, d.impl, d.operand_f16 = B, H, W, Ca, Cout, ks, impl, 1
+        return d
+    assert L.anoddpm_conv_workspace_bytes(ctypes.byref(desc(32, 8, 8, 512, 512))) == 0          # 64 narrow tiles: no split
+    assert L.anoddpm_conv_workspace_bytes(ctypes.byref(desc(32, 16, 16, 512, 1536, ks=1))) == 0  # qkv 1x1: plenty of tiles
+    need = L.anoddpm_conv_workspace_bytes(ctypes.byref(desc(4, 8, 8, 256, 256)))
+    assert need > 0 and need % 4 == 0
+    assert L.anoddpm_conv_workspace_bytes(ctypes.byref(desc(4, 8, 8, 256, 256, impl=3))) == 0   # split-K is impl 2 only
+    assert L.anoddpm_conv_workspace_bytes(None) == 0
+    # argument errors (checked before any CUDA call)
+    assert L.anoddpm_gather_rows(None, None, None, 1, 8, 10, None) < 0
+    assert L.anoddpm_conv_head_sep(None, None, None, None, None, None, 1, 128, 8, 8, None) < 0
+    assert b"anoddpm_conv_head_sep" in L.anoddpm_last_error()
