@@ -596,7 +596,7 @@ class UNetEngine:
             ws = torch.empty(9 * B * H * W, device=dev, dtype=torch.float32)
             call("anoddpm_conv_head_sep", ptr(out), ptr(h.t), ptr(tab), ptr(self.head_w), ptr(hd["conv"].bias), ptr(ws), B, C, H, W,
                  stream())
-            self.launches += 1
+            self.launches += 1      # two kernels (projection + gather); the second one is counted by the common += 1 below
         elif C <= 512 and m.out_channels <= 4:
             # GroupNorm + SiLU applied while the head conv stages its tiles: the last feature map is read once
             gn = hd["gn"]
