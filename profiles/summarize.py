@@ -76,5 +76,33 @@ def kernel(path):
         print()
 
 
+def aux(path):
+    """one table row per captured kernel: duration, DRAM bytes / rate, SM and tensor-pipe activity, registers"""
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+
+    def val(r, k, scale_unit=None):
+        v = float(r[idx[k]].replace(",", ""))
+        u = units[idx[k]]
+        if scale_unit == "MB":
+            v *= {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}[u]
+        if scale_unit == "us":
+            v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3}[u]
+        return v
+    print("| kernel | grid | us | DRAM read MB | DRAM write MB | dram GB/s | dram % of peak | SM % | tensor pipe % | regs |")
+    print("|---|---|---:|---:|---:|---:|---:|---:|---:|---:|")
+    for r in rows[2:]:
+        name = re.sub(r"\(.*", "", r[idx["Kernel Name"]].replace("void ", "").replace("<unnamed>::", ""))
+        us = val(r, "gpu__time_duration.sum", "us")
+        rd, wr = val(r, "dram__bytes_read.sum", "MB"), val(r, "dram__bytes_write.sum", "MB")
+        print(f"| `{name}` | {r[idx['Grid Size']]} | {us:.1f} | {rd:.1f} | {wr:.1f} | {(rd + wr) / us * 1e3:.0f} | "
+              f"{val(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
+              f"{val(r, 'sm__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
+              f"{val(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'):.1f} | "
+              f"{int(val(r, 'launch__registers_per_thread'))} |")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernel": kernel, "aux": aux}[sys.argv[1]](sys.argv[2])
