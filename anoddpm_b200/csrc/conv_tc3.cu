@@ -34,7 +34,6 @@
 
 namespace {
 
-constexpr int kBM = 128;
 constexpr int kRowBytes = 128;   // one K-block row: 32 fp32 (TF32 MMA) or 64 fp16 elements
 constexpr int kKSteps = 4;       // MMAs per K-block: 32 B of K each (8 tf32 / 16 f16 elements)
 constexpr int kThreads = 384;       // warps 0-3: TMA producer, MMA issuer, TMEM allocator, idle; warps 4-11: epilogue
