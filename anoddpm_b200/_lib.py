@@ -38,6 +38,8 @@ SIGNATURES = {
     "anoddpm_simplex_grid2": (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
     "anoddpm_q_sample": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp]),
     "anoddpm_p_sample": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
+    "anoddpm_p_sample_simplex": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f64,
+                                         c_f64, c_vp]),
     "anoddpm_detection_counts": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_int, c_i64, c_vp]),
     "anoddpm_vlb_terms": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_vp]),
     "anoddpm_conv_wgrad_supported": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),

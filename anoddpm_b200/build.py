@@ -28,7 +28,7 @@ def _stale(target, deps):
 
 
 def build(force=False, verbose=False):
-    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "anoddpm_b200.h"), __file__]
+    hdrs = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "diffusion_step.cuh"), os.path.join(ROOT, "include", "anoddpm_b200.h"), __file__]
     objs = []
     bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)

@@ -15,6 +15,7 @@
 // 128-bit vectorised, coalesced loads/stores; t is per sample, so one coefficient fetch per CTA row.
 #include "common.cuh"
 #include "anoddpm_b200.h"
+#include "diffusion_step.cuh"
 
 namespace {
 
@@ -48,15 +49,6 @@ __global__ void __launch_bounds__(256) q_sample_kernel(float* __restrict__ out, 
         for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_sample; i += (long long)gridDim.x * blockDim.x)
             out[base + i] = a * x[base + i] + c * noise[base + i];
     }
-}
-
-__device__ __forceinline__ float p_step(float xt, float e, float z, float ra, float rm1, float c1, float c2, float sg,
-                                        float& x0_out) {
-    float x0 = ra * xt - rm1 * e;
-    x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
-    x0_out = x0;
-    const float mean = c1 * x0 + c2 * xt;
-    return mean + sg * z;
 }
 
 template <bool VEC>

@@ -16,6 +16,7 @@
 // Roofline class: FP64-ALU bound (~146 flop per voxel-octave, 4 B written per voxel).
 #include "common.cuh"
 #include "anoddpm_b200.h"
+#include "diffusion_step.cuh"
 #include <math.h>
 
 namespace {
@@ -293,6 +294,53 @@ __global__ void __launch_bounds__(256) simplex3_octaves_kernel(
     }
 }
 
+// One reverse step with the noise generated in place (the 12 B/px form of sample_p): per pixel the 6-octave
+// simplex value of (x, y, t_b) under the seed table of (step, sample), cast to fp32 exactly like simplex3_octaves_kernel<float>
+// stores it, then the posterior step of p_sample_kernel -- bit-identical to running the two kernels, without the noise tensor.
+// Single-channel images (slice = sample).  grid (pixel chunks, B).
+__global__ void __launch_bounds__(256) p_sample_simplex_kernel(
+    float* __restrict__ sample, float* __restrict__ pred_x0, const float* __restrict__ x_t, const float* __restrict__ eps,
+    int H, int W, const int16_t* __restrict__ tables, const long long* __restrict__ table_step, long long tables_per_step,
+    const long long* __restrict__ t, const float* __restrict__ tab, int T, int octaves, double persistence, double frequency,
+    int freq_pow2) {
+    __shared__ SeedTables s;
+    const int b = blockIdx.y;
+    if (table_step) tables += (size_t)(*table_step) * (size_t)tables_per_step * 512;
+    load_tables(s, tables + (size_t)b * 512);
+    long long tb = t[b];
+    const double zval = (double)tb;               // the noise field uses t as given, like anoddpm_simplex_noise
+    const bool t_bad = tb < 0 || tb >= T;         // out-of-range timestep: poison instead of an out-of-bounds table read
+    if (t_bad) tb = 0;
+    const float poison = t_bad ? __int_as_float(0x7fc00000) : 0.0f;
+    const float ra = tab[tb] + poison, rm1 = tab[T + tb], c1 = tab[2 * T + tb], c2 = tab[3 * T + tb] + poison, sg = tab[4 * T + tb];
+    const int npix = H * W;
+    const size_t base = (size_t)b * npix;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+        const int yi = p / W, xi = p - yi * W;
+        double f = frequency, amp = 1.0, acc = 0.0;
+        if (freq_pow2) {
+            double inv = 1.0 / f;
+            for (int oc = 0; oc < octaves; ++oc) {
+                const double n = noise3(s, (double)xi * inv, (double)yi * inv, zval * inv);
+                acc += amp * n;
+                inv *= 2;
+                amp *= persistence;
+            }
+        } else {
+            for (int oc = 0; oc < octaves; ++oc) {
+                const double n = noise3(s, (double)xi / f, (double)yi / f, zval / f);
+                acc += amp * n;
+                f /= 2;
+                amp *= persistence;
+            }
+        }
+        float x0;
+        const float smp = p_step(x_t[base + p], eps[base + p], (float)acc, ra, rm1, c1, c2, sg, x0);
+        sample[base + p] = smp;
+        if (pred_x0) pred_x0[base + p] = x0;
+    }
+}
+
 // Generic grid: out[z][y][x] = noise3(X[x], Y[y], Z[z])  (reference _noise3a, simplex.py:833-840)
 __global__ void __launch_bounds__(256) simplex3_grid_kernel(double* __restrict__ out, const double* __restrict__ X,
                                                             int nx, const double* __restrict__ Y, int ny,
@@ -402,6 +450,27 @@ extern "C" int anoddpm_simplex_noise_steps(float* out, int B, int C, int H, int 
     ADP_REQUIRE(B > 0 && C > 0, "anoddpm_simplex_noise_steps: bad batch/channels");
     return launch_octaves(out, 0, B * C, H, W, tables_all, shared_seed ? 2 : 0, C, t, nullptr, C, octaves, persistence,
                           frequency, stream, step, shared_seed ? C : (long long)B * C);
+}
+
+extern "C" int anoddpm_p_sample_simplex(float* sample, float* pred_x0, const float* x_t, const float* eps,
+                                        const int16_t* tables_all, const int64_t* step, const int64_t* t, const float* tables,
+                                        int T, int B, int H, int W, int octaves, double persistence, double frequency,
+                                        void* stream) {
+    ADP_REQUIRE(sample && x_t && eps && tables_all && t && tables, "anoddpm_p_sample_simplex: null pointer");
+    ADP_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0 && T > 0, "anoddpm_p_sample_simplex: bad sizes");
+    ADP_REQUIRE(octaves >= 0 && frequency != 0.0, "anoddpm_p_sample_simplex: bad octaves/frequency");
+    const long long npix = (long long)H * W;
+    int bx = adp_ceil_div(npix, 256);
+    if (bx > 4096) bx = 4096;
+    int fexp = 0;
+    const double fm = frexp(frequency, &fexp);
+    const int pow2 = (fm == 0.5 || fm == -0.5) && fexp > -900 + octaves && fexp < 900;
+    p_sample_simplex_kernel<<<dim3(bx, B), 256, 0, (cudaStream_t)stream>>>(sample, pred_x0, x_t, eps, H, W, tables_all,
+                                                                          (const long long*)step, (long long)B,
+                                                                          (const long long*)t, tables, T, octaves, persistence,
+                                                                          frequency, pow2);
+    ADP_LAUNCH_CHECK();
+    return ANODDPM_OK;
 }
 
 extern "C" int anoddpm_simplex_octaves(void* out, int out_f64, int D, int H, int W, const int16_t* tables,

@@ -85,6 +85,16 @@ int anoddpm_q_sample(float* out, const float* x, const float* noise, const int64
 int anoddpm_p_sample(float* sample, float* pred_x0, const float* x_t, const float* eps, const float* noise,
                      const int64_t* t, const float* tables, int T, int B, int64_t per_sample, void* stream);
 
+/* The same reverse step with its simplex noise generated in place (single-channel images): per pixel the `octaves`-octave
+ * noise3 value of (x, y, t_b) under seed table tables_all[*step][b] (the layout of anoddpm_simplex_noise_steps; step may be
+ * NULL = 0), cast to fp32, then the posterior arithmetic of anoddpm_p_sample -- bit-identical to anoddpm_simplex_noise_steps
+ * followed by anoddpm_p_sample, without writing or reading the noise tensor (12 B/px instead of 16 + 4).
+ * GaussianDiffusion.py:96-137 + 298-318. */
+int anoddpm_p_sample_simplex(float* sample, float* pred_x0, const float* x_t, const float* eps,
+                             const int16_t* tables_all /* [steps][B][512] */, const int64_t* step /* [device], may be NULL */,
+                             const int64_t* t, const float* tables, int T, int B, int H, int W, int octaves,
+                             double persistence, double frequency, void* stream);
+
 /* Detection epilogue in one pass (reference detection.py:229-250 + evaluation.py:26-76 do ~10 torch/numpy passes with
  * D2H copies): counts[b] += {n11, n10, n01, n00, sum((image-recon)^2)} and counts[b][5] = max(counts[b][5], max(image)),
  * where "1/0" pairs are (mask == 1, (image-recon)^2 > threshold).  Caller initialises counts to {0,0,0,0,0,-inf}. */

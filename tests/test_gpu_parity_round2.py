@@ -486,15 +486,16 @@ def test_separable_head_vs_torch(shape):
 
 def test_graph_loop_switches_leave_the_chain_unchanged(monkeypatch):
     """The captured reverse step with its optional pieces toggled (per-timestep embedding table, noise field on a forked
-    stream) must produce the chain of the plain configuration: the table rows are bit-identical to the per-step
+    stream, noise generated inside the posterior kernel) must produce the chain of the plain configuration: the table rows are bit-identical to the per-step
     computation and the noise kernel does not depend on where it runs."""
     from anoddpm_b200 import GaussianDiffusionModel, get_beta_schedule
     m = build_model(dict(img_size=64, base_channels=64, n_heads=2, attention_resolutions="16,8"), "tc")
     x0 = (torch.rand(2, 1, 64, 64, generator=torch.Generator().manual_seed(3)) * 2 - 1).to(DEV)
     outs = {}
-    for name, env in (("plain", {"ANODDPM_TIME_TABLE": "0", "ANODDPM_NOISE_OVERLAP": "0"}),
-                      ("table", {"ANODDPM_TIME_TABLE": "1", "ANODDPM_NOISE_OVERLAP": "0"}),
-                      ("table+overlap", {"ANODDPM_TIME_TABLE": "1", "ANODDPM_NOISE_OVERLAP": "1"})):
+    for name, env in (("plain", {"ANODDPM_TIME_TABLE": "0", "ANODDPM_NOISE_OVERLAP": "0", "ANODDPM_FUSED_NOISE": "0"}),
+                      ("table", {"ANODDPM_TIME_TABLE": "1", "ANODDPM_NOISE_OVERLAP": "0", "ANODDPM_FUSED_NOISE": "0"}),
+                      ("table+overlap", {"ANODDPM_TIME_TABLE": "1", "ANODDPM_NOISE_OVERLAP": "1", "ANODDPM_FUSED_NOISE": "0"}),
+                      ("table+fused noise", {"ANODDPM_TIME_TABLE": "1", "ANODDPM_NOISE_OVERLAP": "0", "ANODDPM_FUSED_NOISE": "1"})):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         diff = GaussianDiffusionModel([64, 64], get_beta_schedule(1000, "linear"), noise="simplex")
@@ -504,3 +505,4 @@ def test_graph_loop_switches_leave_the_chain_unchanged(monkeypatch):
     assert torch.isfinite(outs["plain"]).all()
     assert torch.equal(outs["plain"], outs["table"])
     assert torch.equal(outs["plain"], outs["table+overlap"])
+    assert torch.equal(outs["plain"], outs["table+fused noise"])      # noise generated inside the posterior kernel: same bits

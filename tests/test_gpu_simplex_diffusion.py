@@ -213,3 +213,36 @@ def test_vlb_term_fused_kernel_vs_reference_golden(golden, T, name):
     r2["output"].sum().backward()
     assert bool(torch.isfinite(e2.grad).all()) and float(e2.grad.abs().max()) > 0
     assert torch.allclose(D.prior_vlb(x0, {"Batch_Size": 5}).cpu(), torch.from_numpy(g[k + "prior_vlb"]), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("shape", [(3, 40, 24), (2, 64, 64)])
+def test_fused_noise_posterior_kernel_is_bit_identical_to_the_two_kernels(shape):
+    """anoddpm_p_sample_simplex (noise3 octaves evaluated inside the posterior kernel: SURVEY 8(d)'s 12 B/px form of sample_p)
+    against anoddpm_simplex_noise_steps followed by anoddpm_p_sample, including an out-of-range timestep (poisoned)."""
+    from anoddpm_b200 import GaussianDiffusionModel, get_beta_schedule
+    from anoddpm_b200._lib import call, ptr, stream
+    from anoddpm_b200.simplex import init_tables
+    B, H, W = shape
+    T = 1000
+    D = GaussianDiffusionModel([H, W], get_beta_schedule(T, "linear"), noise="simplex")
+    tab = D._tables(torch.device(DEV))
+    g = torch.Generator().manual_seed(21)
+    x_t = torch.randn(B, 1, H, W, generator=g).to(DEV)
+    eps = torch.randn(B, 1, H, W, generator=g).to(DEV)
+    steps = 3
+    tables = torch.from_numpy(init_tables([7 + 13 * i for i in range(steps * B)])).view(steps, B * 512).to(DEV)
+    step = torch.tensor([2], device=DEV, dtype=torch.int64)
+    for tvals in ([5, 999, 0][:B] + [17] * max(0, B - 3), [1000] + [3] * (B - 1)):
+        t = torch.tensor(tvals[:B], device=DEV, dtype=torch.int64)
+        noise = torch.empty(B, 1, H, W, device=DEV)
+        call("anoddpm_simplex_noise_steps", ptr(noise), B, 1, H, W, ptr(tables), ptr(step), 0, ptr(t), 6, 0.8, 64.0, stream())
+        ref_s, ref_p = torch.empty_like(x_t), torch.empty_like(x_t)
+        call("anoddpm_p_sample", ptr(ref_s), ptr(ref_p), ptr(x_t), ptr(eps), ptr(noise), ptr(t), ptr(tab[4:]), T, B, H * W, stream())
+        out_s, out_p = torch.empty_like(x_t), torch.empty_like(x_t)
+        call("anoddpm_p_sample_simplex", ptr(out_s), ptr(out_p), ptr(x_t), ptr(eps), ptr(tables), ptr(step), ptr(t), ptr(tab[4:]), T, B,
+             H, W, 6, 0.8, 64.0, stream())
+        torch.cuda.synchronize()
+        for a, b in ((out_s, ref_s), (out_p, ref_p)):      # bit-identical; a poisoned (out-of-range t) sample is NaN in both
+            assert torch.equal(torch.isnan(a), torch.isnan(b))
+            assert torch.equal(torch.nan_to_num(a).view(torch.int32), torch.nan_to_num(b).view(torch.int32))
+        assert bool(torch.isnan(ref_s[0]).all()) == (tvals[0] >= T)
